@@ -1,0 +1,113 @@
+/*
+ * partgs_b200 — C ABI of the B200-native (sm_100a) PartGS rendering hot path.
+ *
+ * Plain C: raw device pointers, sizes, a cudaStream_t passed as void*.  No torch
+ * types.  Every entry point returns >= 0 on success and a negative pgs_status on
+ * failure; pgs_last_error() returns a human-readable message for the calling thread.
+ * All work is enqueued on `stream`; the only host synchronisation is the read-back
+ * of the instance count inside pgs_dsr_forward / pgs_dsrp_forward (the reference
+ * has the same one: rasterizer_impl.cu:282).
+ *
+ * Each declaration names the reference interface it replaces
+ * (paths relative to zhirui-gao/PartGS; DSR = submodules/diff-surfel-rasterization,
+ * DSRP = submodules/diff-surfel-rasterization_part, KNN = submodules/simple-knn).
+ */
+#ifndef PARTGS_B200_H_
+#define PARTGS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  PGS_OK = 0,
+  PGS_ERR_INVALID_ARG = -1,
+  PGS_ERR_CUDA = -2,
+  PGS_ERR_ALLOC = -3,
+  PGS_ERR_UNSUPPORTED = -4
+} pgs_status;
+
+/* Resizable-buffer callback: must return a device pointer to at least `bytes`
+ * bytes that stays valid until the matching backward call.  C equivalent of the
+ * reference's std::function<char*(size_t)> (DSR/cuda_rasterizer/rasterizer.h:36-38,
+ * produced by resizeFunctional in DSR/rasterize_points.cu:31-37). */
+typedef char* (*pgs_alloc_fn)(size_t bytes, void* user);
+
+const char* pgs_last_error(void);
+int pgs_version(void);
+/* Number of kernels launched by this library in the calling process so far. */
+unsigned long long pgs_launch_count(void);
+
+/* ---- base rasteriser ----------------------------------------------------------
+ * Replaces CudaRasterizer::Rasterizer::forward (DSR/cuda_rasterizer/rasterizer.h:31-61,
+ * rasterizer_impl.cu:198-342).  Same argument meaning; optional inputs are NULL
+ * (shs / colors_precomp, scales+rotations / transMat_precomp).  Returns num_rendered.
+ * out_color [3,H,W], out_others [7,H,W], radii [P] (may be NULL). */
+int pgs_dsr_forward(pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_alloc_fn binning_buffer,
+                    void* binning_user, pgs_alloc_fn image_buffer, void* image_user, int P, int D, int M,
+                    const float* background, int width, int height, const float* means3D, const float* shs,
+                    const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,
+                    const float* rotations, const float* transMat_precomp, const float* viewmatrix,
+                    const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered,
+                    float* out_color, float* out_others, int* radii, int debug, void* stream);
+
+/* Bytes of scratch pgs_dsr_backward needs (per-surfel gradient accumulators). */
+size_t pgs_dsr_backward_scratch_bytes(int P);
+
+/* Replaces CudaRasterizer::Rasterizer::backward (DSR/cuda_rasterizer/rasterizer.h:63-94,
+ * rasterizer_impl.cu:346-448).  R = num_rendered returned by the forward call that
+ * filled the three buffers.  All nine gradient arrays are fully written (no
+ * pre-zeroing required): dL_dmean2D [P,3], dL_dopacity [P], dL_dcolor [P,3],
+ * dL_dmean3D [P,3], dL_dtransMat [P,9], dL_dsh [P,M,3], dL_dscale [P,2], dL_drot [P,4].
+ * `scratch` replaces the reference's internal dL_dnormal [P,3] tensor. */
+int pgs_dsr_backward(int P, int D, int M, int R, const float* background, int width, int height,
+                     const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
+                     float scale_modifier, const float* rotations, const float* transMat_precomp,
+                     const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
+                     float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                     const float* dL_dpix, const float* dL_dothers, float* dL_dmean2D, float* scratch,
+                     float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh,
+                     float* dL_dscale, float* dL_drot, int debug, void* stream);
+
+/* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:24-29, rasterizer_impl.cu:141-153).
+ * present: one byte per point (bool). */
+int pgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     unsigned char* present, void* stream);
+
+/* ---- binning stages, individually callable (parity tests compare each stage) ---- */
+/* cub::DeviceScan::InclusiveSum, rasterizer_impl.cu:278 */
+size_t pgs_scan_temp_bytes(int n);
+int pgs_inclusive_scan_u32(const uint32_t* in, uint32_t* out, int n, void* temp, void* stream);
+/* cub::DeviceRadixSort::SortPairs(u64,u32, bits [0,end_bit)), rasterizer_impl.cu:304-309.
+ * Returns 0 if the sorted output is in (keys_a, vals_a), 1 if in (keys_b, vals_b). */
+size_t pgs_sort_temp_bytes(int n, int end_bit);
+int pgs_sort_pairs_u64(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int n, int end_bit,
+                       void* temp, void* stream);
+/* duplicateWithKeys, rasterizer_impl.cu:70-111, run on a geometry buffer filled by
+ * pgs_dsr_forward; keys/values must hold num_rendered entries. */
+int pgs_dsr_duplicate_with_keys(int P, const char* geom_buffer, int width, int height, const int* radii,
+                                uint64_t* keys, uint32_t* values, void* stream);
+/* identifyTileRanges, rasterizer_impl.cu:116-138 (ranges [ntiles] uint2, zeroed here). */
+int pgs_identify_tile_ranges(int L, const uint64_t* sorted_keys, uint32_t* ranges, int ntiles, void* stream);
+/* getHigherMsb, rasterizer_impl.cu:35-50 */
+uint32_t pgs_higher_msb(uint32_t n);
+
+/* Layout of the opaque buffers (byte offsets from the buffer base, which must be
+ * 256-byte aligned), so that tests can inspect intermediate state the way the
+ * reference's fromChunk does (rasterizer_impl.cu:155-194). */
+typedef struct {
+  size_t geom_bytes, geom_rec, geom_bbox, geom_radii, geom_tiles_touched, geom_point_offsets;
+  size_t image_bytes, image_final_T, image_n_contrib, image_ranges;
+  size_t binning_bytes, binning_keys_sorted, binning_point_list;
+  int rec_floats;  /* floats per surfel record */
+  int tile_pixels; /* per-pixel state is tile-major [tile][256] */
+} pgs_dsr_layout;
+int pgs_dsr_get_layout(int P, int width, int height, int R, pgs_dsr_layout* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARTGS_B200_H_ */

@@ -1,0 +1,125 @@
+"""ctypes binding of libpartgs_b200.so (the C ABI declared in include/partgs_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails
+the caller gets an exception.  PyTorch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libpartgs_b200.so"
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
+
+_f32p = C.c_void_p  # device pointers travel as plain addresses
+_vp = C.c_void_p
+
+
+class DsrLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in (
+        "geom_bytes", "geom_rec", "geom_bbox", "geom_radii", "geom_tiles_touched", "geom_point_offsets",
+        "image_bytes", "image_final_T", "image_n_contrib", "image_ranges",
+        "binning_bytes", "binning_keys_sorted", "binning_point_list")] + [
+        ("rec_floats", C.c_int), ("tile_pixels", C.c_int)]
+
+
+# name -> (restype, argtypes); must list every symbol include/partgs_b200.h declares
+SIGNATURES = {
+    "pgs_last_error": (C.c_char_p, []),
+    "pgs_version": (C.c_int, []),
+    "pgs_launch_count": (C.c_ulonglong, []),
+    "pgs_dsr_forward": (C.c_int, [ALLOC_FN, _vp, ALLOC_FN, _vp, ALLOC_FN, _vp, C.c_int, C.c_int, C.c_int,
+                                  _f32p, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, _f32p,
+                                  _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_int, _f32p, _f32p, _vp,
+                                  C.c_int, _vp]),
+    "pgs_dsr_backward_scratch_bytes": (C.c_size_t, [C.c_int]),
+    "pgs_dsr_backward": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, _f32p, _f32p,
+                                   _f32p, _f32p, C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float,
+                                   C.c_float, _vp, _vp, _vp, _vp, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
+                                   _f32p, _f32p, _f32p, _f32p, C.c_int, _vp]),
+    "pgs_mark_visible": (C.c_int, [C.c_int, _f32p, _f32p, _f32p, _vp, _vp]),
+    "pgs_scan_temp_bytes": (C.c_size_t, [C.c_int]),
+    "pgs_inclusive_scan_u32": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    "pgs_sort_temp_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "pgs_sort_pairs_u64": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
+    "pgs_dsr_duplicate_with_keys": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "pgs_identify_tile_ranges": (C.c_int, [C.c_int, _vp, _vp, C.c_int, _vp]),
+    "pgs_higher_msb": (C.c_uint32, [C.c_uint32]),
+    "pgs_dsr_get_layout": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DsrLayout)]),
+}
+
+_lib = None
+
+
+class PartGSError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once) and attach the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise PartGSError(
+            f"{LIB_PATH} is missing: build it with `python -m partgs_b200.build` "
+            "(there is no CPU or PyTorch fallback for the rasteriser)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> int:
+    if rc < 0:
+        msg = load().pgs_last_error().decode(errors="replace")
+        raise PartGSError(f"{what} failed ({rc}): {msg}")
+    return rc
+
+
+def ptr(t):
+    """Device address of a tensor, or None (NULL) for an absent / empty tensor."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def current_stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class ByteBuffer:
+    """Growable device byte buffer handed to the library through the alloc callback
+    (the role resizeFunctional plays in the reference glue, rasterize_points.cu:31-37)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        self.error = None
+
+        def _cb(nbytes, _user):
+            try:
+                self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+                return self.tensor.data_ptr()
+            except Exception as ex:  # surfaced by the caller; returning NULL makes the C side fail cleanly
+                self.error = ex
+                return None
+
+        self.callback = ALLOC_FN(_cb)
+
+
+def require_cuda_float(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

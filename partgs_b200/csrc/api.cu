@@ -1,0 +1,345 @@
+// C-ABI layer of partgs_b200 (see include/partgs_b200.h).  Host orchestration of the
+// base rasteriser: buffer carving, kernel sequencing on the caller's stream.
+// Mirrors the call order of reference CudaRasterizer::Rasterizer::forward/backward
+// (cuda_rasterizer/rasterizer_impl.cu:198-342, 346-448).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/partgs_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pgs {
+
+static thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int check_cuda(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(PGS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+int check_sync(cudaStream_t s, const char* what) {
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return set_error(PGS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+// reference getHigherMsb (rasterizer_impl.cu:35-50)
+static uint32_t higher_msb(uint32_t n) {
+  uint32_t msb = sizeof(n) * 4;
+  uint32_t step = msb;
+  while (step > 1) {
+    step /= 2;
+    if (n >> msb)
+      msb += step;
+    else
+      msb -= step;
+  }
+  if (n >> msb) msb++;
+  return msb;
+}
+
+struct GeomState {
+  float4* rec;
+  float4* bbox;
+  int* radii;
+  uint32_t* tiles_touched;
+  uint32_t* point_offsets;
+  char* scan_temp;
+  static GeomState from(char*& p, size_t P) {
+    GeomState g;
+    carve(p, g.rec, P * REC_QUADS);
+    carve(p, g.bbox, P);
+    carve(p, g.radii, P);
+    carve(p, g.tiles_touched, P);
+    carve(p, g.point_offsets, P);
+    carve(p, g.scan_temp, scan_temp_bytes((int)P));
+    return g;
+  }
+};
+struct ImageState {
+  float* final_T;
+  uint32_t* n_contrib;
+  uint2* ranges;
+  static ImageState from(char*& p, size_t ntiles) {
+    ImageState s;
+    carve(p, s.final_T, 3 * ntiles * TILE_PIX);
+    carve(p, s.n_contrib, 2 * ntiles * TILE_PIX);
+    carve(p, s.ranges, ntiles);
+    return s;
+  }
+};
+struct BinningState {
+  uint64_t* keys_a;
+  uint64_t* keys_b;
+  uint32_t* vals_a;
+  uint32_t* vals_b;
+  char* sort_temp;
+  static BinningState from(char*& p, size_t R, int end_bit) {
+    BinningState b;
+    carve(p, b.keys_a, R);
+    carve(p, b.keys_b, R);
+    carve(p, b.vals_a, R);
+    carve(p, b.vals_b, R);
+    carve(p, b.sort_temp, radix_sort_temp_bytes((int)R, end_bit));
+    return b;
+  }
+};
+template <typename F> static size_t required(F f) {
+  char* p = nullptr;
+  f(p);
+  return (size_t)p + 256;
+}
+
+}  // namespace pgs
+
+using namespace pgs;
+
+extern "C" {
+
+const char* pgs_last_error(void) { return g_err; }
+int pgs_version(void) { return 100; }
+unsigned long long pgs_launch_count(void) { return g_launches.load(); }
+uint32_t pgs_higher_msb(uint32_t n) { return higher_msb(n); }
+
+int pgs_dsr_get_layout(int P, int width, int height, int R, pgs_dsr_layout* out) {
+  if (!out || P < 0 || width <= 0 || height <= 0 || R < 0) return set_error(PGS_ERR_INVALID_ARG, "bad layout query");
+  const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+  const size_t ntiles = (size_t)gx * gy;
+  const int end_bit = 32 + (int)higher_msb(gx * gy);
+  memset(out, 0, sizeof(*out));
+  {
+    char* p = nullptr;
+    GeomState g = GeomState::from(p, P);
+    out->geom_bytes = (size_t)p + 256;
+    out->geom_rec = (size_t)g.rec;
+    out->geom_bbox = (size_t)g.bbox;
+    out->geom_radii = (size_t)g.radii;
+    out->geom_tiles_touched = (size_t)g.tiles_touched;
+    out->geom_point_offsets = (size_t)g.point_offsets;
+  }
+  {
+    char* p = nullptr;
+    ImageState s = ImageState::from(p, ntiles);
+    out->image_bytes = (size_t)p + 256;
+    out->image_final_T = (size_t)s.final_T;
+    out->image_n_contrib = (size_t)s.n_contrib;
+    out->image_ranges = (size_t)s.ranges;
+  }
+  {
+    char* p = nullptr;
+    BinningState b = BinningState::from(p, R, end_bit);
+    out->binning_bytes = (size_t)p + 256;
+    const bool in_b = ((end_bit + 7) / 8) & 1;
+    out->binning_keys_sorted = in_b ? (size_t)b.keys_b : (size_t)b.keys_a;
+    out->binning_point_list = in_b ? (size_t)b.vals_b : (size_t)b.vals_a;
+  }
+  out->rec_floats = REC_FLOATS;
+  out->tile_pixels = TILE_PIX;
+  return 0;
+}
+
+int pgs_dsr_forward(pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_alloc_fn binning_buffer,
+                    void* binning_user, pgs_alloc_fn image_buffer, void* image_user, int P, int D, int M,
+                    const float* background, int width, int height, const float* means3D, const float* shs,
+                    const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,
+                    const float* rotations, const float* transMat_precomp, const float* viewmatrix,
+                    const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered,
+                    float* out_color, float* out_others, int* radii, int debug, void* stream) {
+  (void)prefiltered;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (P <= 0 || width <= 0 || height <= 0) return set_error(PGS_ERR_INVALID_ARG, "P, width, height must be positive");
+  if (!geometry_buffer || !binning_buffer || !image_buffer) return set_error(PGS_ERR_INVALID_ARG, "null allocator");
+  if (!means3D || !opacities || !background || !viewmatrix || !projmatrix || !out_color || !out_others)
+    return set_error(PGS_ERR_INVALID_ARG, "null required pointer");
+  if (!shs && !colors_precomp)
+    return set_error(PGS_ERR_INVALID_ARG, "provide SHs or precomputed colours");  // rasterizer_impl.cu:243-246
+  if (shs && (!cam_pos || M <= 0)) return set_error(PGS_ERR_INVALID_ARG, "SH path needs campos and M > 0");
+  if (!transMat_precomp && (!scales || !rotations))
+    return set_error(PGS_ERR_INVALID_ARG, "provide scales+rotations or transMat_precomp");
+  if (D < 0 || D > 3 || (shs && (D + 1) * (D + 1) > M)) return set_error(PGS_ERR_INVALID_ARG, "bad SH degree");
+
+  const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+  const size_t ntiles = (size_t)gx * gy;
+
+  size_t geom_bytes = required([&](char*& p) { GeomState::from(p, P); });
+  char* gptr = geometry_buffer(geom_bytes, geometry_user);
+  if (!gptr) return set_error(PGS_ERR_ALLOC, "geometry buffer allocation failed (%zu B)", geom_bytes);
+  GeomState geom = GeomState::from(gptr, P);
+  if (radii == nullptr) radii = geom.radii;
+
+  size_t img_bytes = required([&](char*& p) { ImageState::from(p, ntiles); });
+  char* iptr = image_buffer(img_bytes, image_user);
+  if (!iptr) return set_error(PGS_ERR_ALLOC, "image buffer allocation failed (%zu B)", img_bytes);
+  ImageState img = ImageState::from(iptr, ntiles);
+
+  PreprocessFwdArgs pa;
+  pa.P = P; pa.D = D; pa.M = M;
+  pa.means3D = means3D; pa.scales = scales; pa.scale_modifier = scale_modifier; pa.rotations = rotations;
+  pa.opacities = opacities; pa.shs = shs; pa.transMat_precomp = transMat_precomp;
+  pa.colors_precomp = colors_precomp; pa.viewmatrix = viewmatrix; pa.projmatrix = projmatrix; pa.cam_pos = cam_pos;
+  pa.W = width; pa.H = height; pa.grid_x = gx; pa.grid_y = gy;
+  pa.radii = radii; pa.rec = geom.rec; pa.bbox = geom.bbox; pa.tiles_touched = geom.tiles_touched;
+  launch_preprocess_fwd(pa, s);
+  if (int e = check_cuda("preprocess_fwd")) return e;
+  if (debug) if (int e = check_sync(s, "preprocess_fwd")) return e;
+
+  launch_inclusive_scan_u32(geom.tiles_touched, geom.point_offsets, P, geom.scan_temp, s);
+  if (int e = check_cuda("scan")) return e;
+
+  // number of surfel x tile instances; sizes the binning buffer (reference: rasterizer_impl.cu:282)
+  int num_rendered = 0;
+  cudaError_t ce = cudaMemcpyAsync(&num_rendered, geom.point_offsets + P - 1, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (ce != cudaSuccess) return set_error(PGS_ERR_CUDA, "memcpy num_rendered: %s", cudaGetErrorString(ce));
+  if (int e = check_sync(s, "scan/num_rendered")) return e;
+  if (num_rendered < 0) return set_error(PGS_ERR_UNSUPPORTED, "more than 2^31 surfel-tile instances");
+
+  const int end_bit = 32 + (int)higher_msb(gx * gy);
+  size_t bin_bytes = required([&](char*& p) { BinningState::from(p, num_rendered, end_bit); });
+  char* bptr = binning_buffer(bin_bytes, binning_user);
+  if (!bptr) return set_error(PGS_ERR_ALLOC, "binning buffer allocation failed (%zu B)", bin_bytes);
+  BinningState bin = BinningState::from(bptr, num_rendered, end_bit);
+
+  cudaMemsetAsync(img.ranges, 0, ntiles * sizeof(uint2), s);
+  const uint32_t* point_list = bin.vals_a;
+  if (num_rendered > 0) {
+    launch_duplicate_with_keys(P, geom.rec, geom.point_offsets, bin.keys_a, bin.vals_a, radii, gx, gy, s);
+    if (int e = check_cuda("duplicate_with_keys")) return e;
+    int where = launch_radix_sort_pairs(bin.keys_a, bin.vals_a, bin.keys_b, bin.vals_b, num_rendered, end_bit,
+                                        bin.sort_temp, s);
+    if (int e = check_cuda("radix_sort")) return e;
+    const uint64_t* sorted_keys = where ? bin.keys_b : bin.keys_a;
+    point_list = where ? bin.vals_b : bin.vals_a;
+    launch_identify_tile_ranges(num_rendered, sorted_keys, img.ranges, s);
+    if (int e = check_cuda("identify_tile_ranges")) return e;
+    if (debug) if (int e = check_sync(s, "binning")) return e;
+  }
+
+  RenderFwdArgs ra;
+  ra.ranges = img.ranges; ra.point_list = point_list; ra.W = width; ra.H = height; ra.grid_x = gx; ra.grid_y = gy;
+  ra.rec = geom.rec; ra.bbox = geom.bbox; ra.bg_color = background;
+  ra.final_T = img.final_T; ra.n_contrib = img.n_contrib; ra.out_color = out_color; ra.out_others = out_others;
+  launch_render_fwd(ra, s);
+  if (int e = check_cuda("render_fwd")) return e;
+  if (debug) if (int e = check_sync(s, "render_fwd")) return e;
+  return num_rendered;
+}
+
+size_t pgs_dsr_backward_scratch_bytes(int P) { return (size_t)(P > 0 ? P : 0) * GRAD_FLOATS * sizeof(float) + 256; }
+
+int pgs_dsr_backward(int P, int D, int M, int R, const float* background, int width, int height,
+                     const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
+                     float scale_modifier, const float* rotations, const float* transMat_precomp,
+                     const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
+                     float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                     const float* dL_dpix, const float* dL_dothers, float* dL_dmean2D, float* scratch,
+                     float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh,
+                     float* dL_dscale, float* dL_drot, int debug, void* stream) {
+  (void)colors_precomp;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (P <= 0 || width <= 0 || height <= 0 || R < 0) return set_error(PGS_ERR_INVALID_ARG, "bad sizes");
+  if (!geom_buffer || !image_buffer || (R > 0 && !binning_buffer))
+    return set_error(PGS_ERR_INVALID_ARG, "null state buffer");
+  if (!dL_dpix || !dL_dothers || !scratch || !dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D ||
+      !dL_dtransMat)
+    return set_error(PGS_ERR_INVALID_ARG, "null gradient pointer");
+  if (!transMat_precomp && (!scales || !rotations || !dL_dscale || !dL_drot))
+    return set_error(PGS_ERR_INVALID_ARG, "scale/rotation path needs scales, rotations and their gradient arrays");
+  if (shs && !dL_dsh) return set_error(PGS_ERR_INVALID_ARG, "SH path needs dL_dsh");
+
+  const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+  const size_t ntiles = (size_t)gx * gy;
+  const int end_bit = 32 + (int)higher_msb(gx * gy);
+
+  GeomState geom = GeomState::from(geom_buffer, P);
+  ImageState img = ImageState::from(image_buffer, ntiles);
+  if (radii == nullptr) radii = geom.radii;
+  const uint32_t* point_list = nullptr;
+  if (R > 0) {
+    BinningState bin = BinningState::from(binning_buffer, R, end_bit);
+    point_list = (((end_bit + 7) / 8) & 1) ? bin.vals_b : bin.vals_a;
+  }
+
+  float* grad = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(scratch), 256));
+  cudaMemsetAsync(grad, 0, (size_t)P * GRAD_FLOATS * sizeof(float), s);
+
+  const float focal_y = height / (2.0f * tan_fovy);
+  const float focal_x = width / (2.0f * tan_fovx);
+
+  RenderBwdArgs rb;
+  rb.ranges = img.ranges; rb.point_list = point_list; rb.W = width; rb.H = height; rb.grid_x = gx; rb.grid_y = gy;
+  rb.rec = geom.rec; rb.bbox = geom.bbox; rb.bg_color = background; rb.final_T = img.final_T;
+  rb.n_contrib = img.n_contrib; rb.dL_dpixels = dL_dpix; rb.dL_dothers = dL_dothers; rb.grad = grad;
+  launch_render_bwd(rb, s);
+  if (int e = check_cuda("render_bwd")) return e;
+  if (debug) if (int e = check_sync(s, "render_bwd")) return e;
+
+  PreprocessBwdArgs pb;
+  pb.P = P; pb.D = D; pb.M = M; pb.means3D = means3D; pb.radii = radii; pb.shs = shs;
+  pb.scales = transMat_precomp ? nullptr : scales; pb.rotations = rotations; pb.scale_modifier = scale_modifier;
+  pb.transMat_precomp = transMat_precomp; pb.viewmatrix = viewmatrix; pb.projmatrix = projmatrix;
+  pb.focal_x = focal_x; pb.focal_y = focal_y; pb.tan_fovx = tan_fovx; pb.tan_fovy = tan_fovy; pb.cam_pos = campos;
+  pb.rec = geom.rec; pb.grad = grad;
+  pb.dL_dmean2D = dL_dmean2D; pb.dL_dcolors = dL_dcolor; pb.dL_dopacity = dL_dopacity; pb.dL_dmean3D = dL_dmean3D;
+  pb.dL_dtransMat = dL_dtransMat; pb.dL_dsh = dL_dsh; pb.dL_dscales = dL_dscale; pb.dL_drots = dL_drot;
+  launch_preprocess_bwd(pb, s);
+  if (int e = check_cuda("preprocess_bwd")) return e;
+  if (debug) if (int e = check_sync(s, "preprocess_bwd")) return e;
+  return 0;
+}
+
+int pgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     unsigned char* present, void* stream) {
+  (void)projmatrix;
+  if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return set_error(PGS_ERR_INVALID_ARG, "bad args");
+  launch_check_frustum(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+  return check_cuda("check_frustum");
+}
+
+size_t pgs_scan_temp_bytes(int n) { return scan_temp_bytes(n > 0 ? n : 0) + 256; }
+int pgs_inclusive_scan_u32(const uint32_t* in, uint32_t* out, int n, void* temp, void* stream) {
+  if (n < 0 || (n > 0 && (!in || !out || !temp))) return set_error(PGS_ERR_INVALID_ARG, "bad args");
+  void* t = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(temp), 256));
+  launch_inclusive_scan_u32(in, out, n, t, (cudaStream_t)stream);
+  return check_cuda("scan");
+}
+size_t pgs_sort_temp_bytes(int n, int end_bit) { return radix_sort_temp_bytes(n > 0 ? n : 0, end_bit) + 256; }
+int pgs_sort_pairs_u64(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int n, int end_bit,
+                       void* temp, void* stream) {
+  if (n < 0 || end_bit <= 0 || end_bit > 64 || (n > 0 && (!keys_a || !vals_a || !keys_b || !vals_b || !temp)))
+    return set_error(PGS_ERR_INVALID_ARG, "bad args");
+  void* t = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(temp), 256));
+  int where = launch_radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, n, end_bit, t, (cudaStream_t)stream);
+  if (int e = check_cuda("radix_sort")) return e;
+  return where;
+}
+int pgs_dsr_duplicate_with_keys(int P, const char* geom_buffer, int width, int height, const int* radii,
+                                uint64_t* keys, uint32_t* values, void* stream) {
+  if (P <= 0 || !geom_buffer || !keys || !values) return set_error(PGS_ERR_INVALID_ARG, "bad args");
+  const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+  char* p = const_cast<char*>(geom_buffer);
+  GeomState geom = GeomState::from(p, P);
+  if (!radii) radii = geom.radii;
+  launch_duplicate_with_keys(P, geom.rec, geom.point_offsets, keys, values, radii, gx, gy, (cudaStream_t)stream);
+  return check_cuda("duplicate_with_keys");
+}
+int pgs_identify_tile_ranges(int L, const uint64_t* sorted_keys, uint32_t* ranges, int ntiles, void* stream) {
+  if (L < 0 || ntiles <= 0 || !ranges || (L > 0 && !sorted_keys)) return set_error(PGS_ERR_INVALID_ARG, "bad args");
+  cudaMemsetAsync(ranges, 0, (size_t)ntiles * sizeof(uint2), (cudaStream_t)stream);
+  launch_identify_tile_ranges(L, sorted_keys, reinterpret_cast<uint2*>(ranges), (cudaStream_t)stream);
+  return check_cuda("identify_tile_ranges");
+}
+
+}  // extern "C"

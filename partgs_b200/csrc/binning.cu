@@ -1,0 +1,444 @@
+// Binning for the surfel rasteriser (sm_100a): prefix sum of tile counts, key
+// duplication, a hand-written onesweep LSD radix sort and tile-range detection.
+//
+// Replaces, with bit-identical results:
+//   cub::DeviceScan::InclusiveSum            rasterizer_impl.cu:278
+//   duplicateWithKeys                        rasterizer_impl.cu:70-111
+//   cub::DeviceRadixSort::SortPairs          rasterizer_impl.cu:304-309   (stable, bits [0, 32+tile_bits))
+//   identifyTileRanges                       rasterizer_impl.cu:116-138
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pgs {
+
+// =============================================================================
+// Single-pass inclusive scan (decoupled look-back), u32.
+// =============================================================================
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr unsigned long long SCAN_FLAG_AGG = 1ull << 32;
+constexpr unsigned long long SCAN_FLAG_INC = 2ull << 32;
+
+size_t scan_temp_bytes(int n) {
+  int tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  return 256 + (size_t)tiles * sizeof(unsigned long long);
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const uint32_t* __restrict__ in,
+                                                             uint32_t* __restrict__ out, int n, uint32_t* counter,
+                                                             unsigned long long* state) {
+  __shared__ uint32_t s_vals[SCAN_TILE];
+  __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+  __shared__ uint32_t s_tile;
+  __shared__ uint32_t s_excl;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_tile = atomicAdd(counter, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const int base = tile * SCAN_TILE;
+
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    int e = i * SCAN_THREADS + tid;
+    s_vals[e] = (base + e < n) ? in[base + e] : 0u;
+  }
+  __syncthreads();
+
+  uint32_t v[SCAN_ITEMS];
+  uint32_t tsum = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    tsum += s_vals[tid * SCAN_ITEMS + i];
+    v[i] = tsum;
+  }
+  // warp inclusive scan of thread sums
+  uint32_t w = tsum;
+  const unsigned lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+    if (lane >= o) w += t;
+  }
+  if (lane == 31) s_warp[wid] = w;
+  __syncthreads();
+  uint32_t warp_off = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_THREADS / 32; i++)
+    if (i < wid) warp_off += s_warp[i];
+  const uint32_t thread_excl = warp_off + w - tsum;
+
+  if (tid == SCAN_THREADS - 1) {
+    const uint32_t agg = thread_excl + tsum;  // tile aggregate
+    uint32_t excl = 0;
+    if (tile == 0) {
+      atomicExch(&state[0], SCAN_FLAG_INC | agg);
+    } else {
+      atomicExch(&state[tile], SCAN_FLAG_AGG | agg);
+      int t = (int)tile - 1;
+      while (true) {
+        unsigned long long sv = *((volatile unsigned long long*)&state[t]);
+        if ((sv >> 32) == 0) continue;
+        excl += (uint32_t)sv;
+        if ((sv >> 32) == 2) break;
+        t--;
+      }
+      atomicExch(&state[tile], SCAN_FLAG_INC | (unsigned long long)(uint32_t)(excl + agg));
+    }
+    s_excl = excl;
+  }
+  __syncthreads();
+  const uint32_t off = s_excl + thread_excl;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) s_vals[tid * SCAN_ITEMS + i] = v[i] + off;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    int e = i * SCAN_THREADS + tid;
+    if (base + e < n) out[base + e] = s_vals[e];
+  }
+}
+
+void launch_inclusive_scan_u32(const uint32_t* in, uint32_t* out, int n, void* temp, cudaStream_t s) {
+  if (n <= 0) return;
+  int tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  cudaMemsetAsync(temp, 0, scan_temp_bytes(n), s);
+  uint32_t* counter = (uint32_t*)temp;
+  unsigned long long* state = (unsigned long long*)((char*)temp + 256);
+  scan_kernel<<<tiles, SCAN_THREADS, 0, s>>>(in, out, n, counter, state);
+  count_launch();
+}
+
+// =============================================================================
+// duplicateWithKeys: key = tile_id << 32 | bits(depth), value = surfel index,
+// emitted row-major over the surfel's tile rectangle.
+// =============================================================================
+__device__ __forceinline__ void tile_rect_dup(const float2 p, int max_radius, uint2& rect_min, uint2& rect_max,
+                                              unsigned gx, unsigned gy) {
+  rect_min = {min(gx, max((int)0, (int)((p.x - max_radius) / TILE_X))),
+              min(gy, max((int)0, (int)((p.y - max_radius) / TILE_Y)))};
+  rect_max = {min(gx, max((int)0, (int)((p.x + max_radius + TILE_X - 1) / TILE_X))),
+              min(gy, max((int)0, (int)((p.y + max_radius + TILE_Y - 1) / TILE_Y)))};
+}
+
+__global__ void __launch_bounds__(256) duplicate_with_keys_kernel(int P, const float4* __restrict__ rec,
+                                                                  const uint32_t* __restrict__ offsets,
+                                                                  uint64_t* __restrict__ keys,
+                                                                  uint32_t* __restrict__ values,
+                                                                  const int* __restrict__ radii, unsigned gx,
+                                                                  unsigned gy) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const int radius = radii[idx];
+  if (radius > 0) {
+    uint32_t off = (idx == 0) ? 0 : offsets[idx - 1];
+    const float4* r = rec + (size_t)idx * REC_QUADS;
+    const float2 xy = {__ldg(&r[0]).w, __ldg(&r[1]).w};
+    const uint32_t depth_bits = __float_as_uint(__ldg(&r[3]).w);
+    uint2 rect_min, rect_max;
+    tile_rect_dup(xy, radius, rect_min, rect_max, gx, gy);
+    for (unsigned y = rect_min.y; y < rect_max.y; y++) {
+      for (unsigned x = rect_min.x; x < rect_max.x; x++) {
+        uint64_t key = y * gx + x;
+        key <<= 32;
+        key |= depth_bits;
+        keys[off] = key;
+        values[off] = idx;
+        off++;
+      }
+    }
+  }
+}
+
+void launch_duplicate_with_keys(int P, const float4* rec, const uint32_t* offsets, uint64_t* keys, uint32_t* values,
+                                const int* radii, int grid_x, int grid_y, cudaStream_t s) {
+  if (P <= 0) return;
+  duplicate_with_keys_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, rec, offsets, keys, values, radii, grid_x, grid_y);
+  count_launch();
+}
+
+// =============================================================================
+// Onesweep LSD radix sort (Adinets & Merrill 2022): one global histogram pass,
+// then one kernel per 8-bit digit that ranks a tile in shared memory, resolves its
+// global offsets by decoupled look-back over per-digit tile counts, and scatters.
+// Stable.  KeyT = uint64_t (tile|depth keys) or uint32_t (kNN cell codes).
+// =============================================================================
+constexpr int RS_BITS = 8;
+constexpr int RS_RADIX = 1 << RS_BITS;
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 12;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 3072 pairs / CTA
+constexpr int RS_MAX_PASSES = 8;
+constexpr uint32_t RS_FLAG_AGG = 1u << 30;
+constexpr uint32_t RS_FLAG_INC = 2u << 30;
+constexpr uint32_t RS_VAL_MASK = (1u << 30) - 1;
+
+static inline int rs_passes(int end_bit) { return (end_bit + RS_BITS - 1) / RS_BITS; }
+
+template <typename KeyT> static size_t rs_temp_bytes(int n, int end_bit) {
+  int passes = rs_passes(end_bit);
+  int tiles = (n + RS_TILE - 1) / RS_TILE;
+  // [hist: passes*256 u32][counters: passes u32 (padded)][lookback: passes*tiles*256 u32]
+  return (size_t)passes * RS_RADIX * 4 + 256 + (size_t)passes * tiles * RS_RADIX * 4 + 256;
+}
+size_t radix_sort_temp_bytes(int n, int end_bit) { return rs_temp_bytes<uint64_t>(n, end_bit); }
+size_t radix_sort32_temp_bytes(int n, int end_bit) { return rs_temp_bytes<uint32_t>(n, end_bit); }
+
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS) rs_histogram_kernel(const KeyT* __restrict__ keys, int n, int passes,
+                                                                   int end_bit, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_hist[RS_MAX_PASSES * RS_RADIX];
+  for (int i = threadIdx.x; i < passes * RS_RADIX; i += RS_THREADS) s_hist[i] = 0;
+  __syncthreads();
+  const int stride = gridDim.x * RS_THREADS;
+  for (int i = blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += stride) {
+    KeyT k = keys[i];
+#pragma unroll 1
+    for (int p = 0; p < passes; p++) {
+      int shift = p * RS_BITS;
+      int bits = min(RS_BITS, end_bit - shift);
+      uint32_t d = (uint32_t)(k >> shift) & ((1u << bits) - 1);
+      atomicAdd(&s_hist[p * RS_RADIX + d], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * RS_RADIX; i += RS_THREADS) {
+    uint32_t c = s_hist[i];
+    if (c) atomicAdd(&hist[i], c);
+  }
+}
+
+// exclusive scan of each pass's 256-bin histogram, in place
+__global__ void __launch_bounds__(RS_RADIX) rs_scan_hist_kernel(uint32_t* hist) {
+  __shared__ uint32_t s_warp[RS_RADIX / 32];
+  uint32_t* h = hist + blockIdx.x * RS_RADIX;
+  const int tid = threadIdx.x;
+  const unsigned lane = tid & 31, wid = tid >> 5;
+  uint32_t c = h[tid];
+  uint32_t w = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+    if (lane >= o) w += t;
+  }
+  if (lane == 31) s_warp[wid] = w;
+  __syncthreads();
+  uint32_t off = 0;
+#pragma unroll
+  for (int i = 0; i < RS_RADIX / 32; i++)
+    if (i < wid) off += s_warp[i];
+  h[tid] = off + w - c;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS)
+    rs_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                       KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift, int bits,
+                       const uint32_t* __restrict__ bin_base,  // [256] exclusive global digit offsets
+                       uint32_t* lookback,                     // [tiles][256]
+                       uint32_t* tile_counter) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  KeyT* s_keys = reinterpret_cast<KeyT*>(rs_smem);                                   // [RS_TILE]
+  uint32_t* s_vals = reinterpret_cast<uint32_t*>(rs_smem + sizeof(KeyT) * RS_TILE);  // [RS_TILE]
+  uint32_t* s_warp_hist = s_vals + RS_TILE;                                          // [RS_WARPS][256]
+  uint32_t* s_digit_start = s_warp_hist + RS_WARPS * RS_RADIX;                       // [256] block-local start
+  uint32_t* s_goff = s_digit_start + RS_RADIX;                                       // [256] global - local
+  __shared__ uint32_t s_tile;
+  __shared__ uint32_t s_scan_warp[RS_WARPS];
+
+  const int tid = threadIdx.x;
+  const unsigned lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+  for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) s_warp_hist[i] = 0;
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const int base = tile * RS_TILE;
+  const uint32_t mask = (1u << bits) - 1;
+
+  // warp-striped load: element order e = wid*ITEMS*32 + i*32 + lane
+  KeyT key[RS_ITEMS];
+  uint32_t val[RS_ITEMS];
+  uint32_t rank[RS_ITEMS];
+  const int wbase = base + wid * (RS_ITEMS * 32);
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; i++) {
+    int g = wbase + i * 32 + lane;
+    if (g < n) {
+      key[i] = keys_in[g];
+      val[i] = vals_in[g];
+    } else {
+      key[i] = ~(KeyT)0;  // sentinel: last digit, ranked after every valid element
+      val[i] = 0;
+    }
+  }
+  // rank within warp, in element order
+  uint32_t* my_hist = s_warp_hist + wid * RS_RADIX;
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; i++) {
+    uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+    unsigned peers = __match_any_sync(0xffffffffu, d);
+    unsigned leader = __ffs(peers) - 1;
+    uint32_t pre = 0;
+    if (lane == leader) {
+      pre = my_hist[d];
+      my_hist[d] = pre + __popc(peers);
+    }
+    pre = __shfl_sync(0xffffffffu, pre, leader);
+    rank[i] = pre + __popc(peers & ((1u << lane) - 1));
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // thread d owns digit d: exclusive scan across warps -> block count
+  uint32_t count = 0;
+  {
+    const int d = tid;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) {
+      uint32_t t = s_warp_hist[w * RS_RADIX + d];
+      s_warp_hist[w * RS_RADIX + d] = count;
+      count += t;
+    }
+  }
+  // publish + decoupled look-back per digit
+  uint32_t excl = 0;
+  {
+    uint32_t* lb = lookback + (size_t)tile * RS_RADIX + tid;
+    if (tile == 0) {
+      atomicExch(lb, RS_FLAG_INC | count);
+    } else {
+      atomicExch(lb, RS_FLAG_AGG | count);
+      int t = (int)tile - 1;
+      while (true) {
+        uint32_t v = *((volatile uint32_t*)(lookback + (size_t)t * RS_RADIX + tid));
+        uint32_t f = v >> 30;
+        if (f == 0) continue;
+        excl += v & RS_VAL_MASK;
+        if (f == 2) break;
+        t--;
+      }
+      atomicExch(lb, RS_FLAG_INC | ((excl + count) & RS_VAL_MASK));
+    }
+  }
+  // block-local exclusive scan over digits
+  {
+    uint32_t w = count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    if (lane == 31) s_scan_warp[wid] = w;
+    __syncthreads();
+    uint32_t off = 0;
+#pragma unroll
+    for (int i = 0; i < RS_WARPS; i++)
+      if (i < (int)wid) off += s_scan_warp[i];
+    const uint32_t start = off + w - count;
+    s_digit_start[tid] = start;
+    s_goff[tid] = bin_base[tid] + excl - start;
+  }
+  __syncthreads();
+
+  // scatter into shared memory in sorted order
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; i++) {
+    uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+    uint32_t pos = s_digit_start[d] + my_hist[d] + rank[i];
+    s_keys[pos] = key[i];
+    s_vals[pos] = val[i];
+  }
+  __syncthreads();
+
+  // coalesced write-out; sentinels occupy the tail [nvalid, RS_TILE)
+  const int nvalid = min(RS_TILE, n - base);
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; i++) {
+    int j = i * RS_THREADS + tid;
+    if (j < nvalid) {
+      KeyT k = s_keys[j];
+      uint32_t d = (uint32_t)(k >> shift) & mask;
+      uint32_t g = s_goff[d] + j;
+      keys_out[g] = k;
+      vals_out[g] = s_vals[j];
+    }
+  }
+}
+
+template <typename KeyT>
+static int rs_sort(KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, int n, int end_bit, void* temp,
+                   cudaStream_t s) {
+  if (n <= 0) return 0;
+  const int passes = rs_passes(end_bit);
+  const int tiles = (n + RS_TILE - 1) / RS_TILE;
+  cudaMemsetAsync(temp, 0, rs_temp_bytes<KeyT>(n, end_bit), s);
+  uint32_t* hist = (uint32_t*)temp;
+  uint32_t* counters = (uint32_t*)((char*)temp + (size_t)passes * RS_RADIX * 4);
+  uint32_t* lookback = (uint32_t*)((char*)counters + 256);
+
+  int hist_blocks = min(tiles, 148 * 8);
+  rs_histogram_kernel<KeyT><<<hist_blocks, RS_THREADS, 0, s>>>(keys_a, n, passes, end_bit, hist);
+  count_launch();
+  rs_scan_hist_kernel<<<passes, RS_RADIX, 0, s>>>(hist);
+  count_launch();
+
+  const size_t smem = sizeof(KeyT) * RS_TILE + 4 * RS_TILE + 4 * (RS_WARPS * RS_RADIX + 2 * RS_RADIX);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(rs_onesweep_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  KeyT* kin = keys_a;
+  uint32_t* vin = vals_a;
+  KeyT* kout = keys_b;
+  uint32_t* vout = vals_b;
+  for (int p = 0; p < passes; p++) {
+    int shift = p * RS_BITS;
+    int bits = min(RS_BITS, end_bit - shift);
+    rs_onesweep_kernel<KeyT><<<tiles, RS_THREADS, smem, s>>>(kin, vin, kout, vout, n, shift, bits,
+                                                              hist + p * RS_RADIX,
+                                                              lookback + (size_t)p * tiles * RS_RADIX, counters + p);
+    count_launch();
+    KeyT* tk = kin; kin = kout; kout = tk;
+    uint32_t* tv = vin; vin = vout; vout = tv;
+  }
+  return (passes & 1) ? 1 : 0;
+}
+
+int launch_radix_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int n, int end_bit,
+                            void* temp, cudaStream_t s) {
+  return rs_sort<uint64_t>(keys_a, vals_a, keys_b, vals_b, n, end_bit, temp, s);
+}
+int launch_radix_sort_pairs32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, int n,
+                              int end_bit, void* temp, cudaStream_t s) {
+  return rs_sort<uint32_t>(keys_a, vals_a, keys_b, vals_b, n, end_bit, temp, s);
+}
+
+// =============================================================================
+// identifyTileRanges
+// =============================================================================
+__global__ void __launch_bounds__(256) identify_tile_ranges_kernel(int L, const uint64_t* __restrict__ keys,
+                                                                   uint2* ranges) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= L) return;
+  uint32_t currtile = (uint32_t)(keys[idx] >> 32);
+  if (idx == 0)
+    ranges[currtile].x = 0;
+  else {
+    uint32_t prevtile = (uint32_t)(keys[idx - 1] >> 32);
+    if (currtile != prevtile) {
+      ranges[prevtile].y = idx;
+      ranges[currtile].x = idx;
+    }
+  }
+  if (idx == L - 1) ranges[currtile].y = L;
+}
+
+void launch_identify_tile_ranges(int L, const uint64_t* keys, uint2* ranges, cudaStream_t s) {
+  if (L <= 0) return;
+  identify_tile_ranges_kernel<<<(L + 255) / 256, 256, 0, s>>>(L, keys, ranges);
+  count_launch();
+}
+
+}  // namespace pgs

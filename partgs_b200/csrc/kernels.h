@@ -1,0 +1,119 @@
+// Internal launch interface between the C-ABI layer (api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pgs {
+
+// bookkeeping for pgs_launch_count(): every kernel launch of this library is counted
+void count_launch(int n = 1);
+
+struct PreprocessFwdArgs {
+  int P, D, M;
+  const float* means3D;
+  const float* scales;
+  float scale_modifier;
+  const float* rotations;
+  const float* opacities;
+  const float* shs;
+  const float* transMat_precomp;
+  const float* colors_precomp;
+  const float* viewmatrix;
+  const float* projmatrix;
+  const float* cam_pos;
+  int W, H;
+  int grid_x, grid_y;
+  // outputs
+  int* radii;
+  float4* rec;    // [P][REC_QUADS]
+  float4* bbox;   // [P]
+  uint32_t* tiles_touched;
+};
+void launch_preprocess_fwd(const PreprocessFwdArgs& a, cudaStream_t s);
+void launch_check_frustum(int P, const float* means3D, const float* viewmatrix, unsigned char* present,
+                          cudaStream_t s);
+
+// ---- binning ----------------------------------------------------------------
+size_t scan_temp_bytes(int n);
+// inclusive prefix sum of uint32 (reference: cub::DeviceScan::InclusiveSum, rasterizer_impl.cu:278)
+void launch_inclusive_scan_u32(const uint32_t* in, uint32_t* out, int n, void* temp, cudaStream_t s);
+
+// reference duplicateWithKeys (rasterizer_impl.cu:70-111)
+void launch_duplicate_with_keys(int P, const float4* rec, const uint32_t* offsets, uint64_t* keys, uint32_t* values,
+                                const int* radii, int grid_x, int grid_y, cudaStream_t s);
+
+// Stable LSD radix sort of (u64 key, u32 value) pairs on key bits [0, end_bit)
+// (reference: cub::DeviceRadixSort::SortPairs, rasterizer_impl.cu:304-309).
+// Buffers a/b ping-pong; returns 0 if the sorted result is in (keys_a, vals_a), 1 if in (keys_b, vals_b).
+size_t radix_sort_temp_bytes(int n, int end_bit);
+int launch_radix_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int n, int end_bit,
+                            void* temp, cudaStream_t s);
+// 32-bit key variant (distCUDA2 Morton/cell sort)
+size_t radix_sort32_temp_bytes(int n, int end_bit);
+int launch_radix_sort_pairs32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, int n,
+                              int end_bit, void* temp, cudaStream_t s);
+
+// reference identifyTileRanges (rasterizer_impl.cu:116-138); ranges must be zeroed first.
+void launch_identify_tile_ranges(int L, const uint64_t* keys, uint2* ranges, cudaStream_t s);
+
+// ---- render -----------------------------------------------------------------
+struct RenderFwdArgs {
+  const uint2* ranges;
+  const uint32_t* point_list;
+  int W, H;
+  int grid_x, grid_y;
+  const float4* rec;
+  const float4* bbox;
+  const float* bg_color;
+  // per-pixel state kept for backward, tile-major [tile][256]
+  float* final_T;     // [3][ntile*256]: T, M1, M2
+  uint32_t* n_contrib;  // [2][ntile*256]: last, median
+  float* out_color;   // [3][H][W]
+  float* out_others;  // [7][H][W]
+};
+void launch_render_fwd(const RenderFwdArgs& a, cudaStream_t s);
+
+struct RenderBwdArgs {
+  const uint2* ranges;
+  const uint32_t* point_list;
+  int W, H;
+  int grid_x, grid_y;
+  const float4* rec;
+  const float4* bbox;
+  const float* bg_color;
+  const float* final_T;
+  const uint32_t* n_contrib;
+  const float* dL_dpixels;  // [3][H][W]
+  const float* dL_dothers;  // [7][H][W]
+  float* grad;              // [P][GRAD_FLOATS], zeroed
+};
+void launch_render_bwd(const RenderBwdArgs& a, cudaStream_t s);
+
+struct PreprocessBwdArgs {
+  int P, D, M;
+  const float* means3D;
+  const int* radii;
+  const float* shs;
+  const float* scales;
+  const float* rotations;
+  float scale_modifier;
+  const float* transMat_precomp;
+  const float* viewmatrix;
+  const float* projmatrix;
+  float focal_x, focal_y, tan_fovx, tan_fovy;
+  const float* cam_pos;
+  const float4* rec;
+  const float* grad;  // [P][GRAD_FLOATS] from render bwd
+  // outputs (all written for every surfel; no pre-zeroing needed)
+  float* dL_dmean2D;    // [P][3]
+  float* dL_dcolors;    // [P][3]
+  float* dL_dopacity;   // [P]
+  float* dL_dmean3D;    // [P][3]
+  float* dL_dtransMat;  // [P][9]
+  float* dL_dsh;        // [P][M][3]
+  float* dL_dscales;    // [P][2]
+  float* dL_drots;      // [P][4]
+};
+void launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t s);
+
+}  // namespace pgs

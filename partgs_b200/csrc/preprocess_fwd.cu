@@ -1,0 +1,282 @@
+// Forward preprocess for the base surfel rasteriser (sm_100a).
+//
+// One thread per surfel: near-cull, ray-splat transform T, facing normal, 3-sigma
+// AABB -> radius / tile rectangle, SH -> RGB, packed 80-byte render record and a
+// conservative cull box for the render kernels.
+//
+// Replaces reference preprocessCUDA (cuda_rasterizer/forward.cu:148-251) and its
+// helpers compute_transmat (:75-115), compute_aabb (:119-145), computeColorFromSH
+// (:20-71), in_frustum / quat_to_rotmat / scale_to_mat / getRect
+// (cuda_rasterizer/auxiliary.h:67-77,185-235,285-292).
+//
+// Bit-exactness: radii, tile rectangles and sort keys must equal the reference's,
+// so every fp32 expression below keeps the reference's association order (GLM sums
+// are left-to-right; see linalg.cuh) and is compiled with the same nvcc defaults
+// (-fmad=true, no fast-math).
+#include "common.cuh"
+#include "linalg.cuh"
+#include "kernels.h"
+
+namespace pgs {
+
+__device__ const float kSH_C0 = 0.28209479177387814f;
+__device__ const float kSH_C1 = 0.4886025119029199f;
+__device__ const float kSH_C2[] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                   -1.0925484305920792f, 0.5462742152960396f};
+__device__ const float kSH_C3[] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                                   -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+
+__device__ __forceinline__ float3 xform_point4x3(const float3& p, const float* m) {
+  float3 t = {
+      m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
+      m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+      m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14],
+  };
+  return t;
+}
+__device__ __forceinline__ float3 xform_vec4x3(const float3& p, const float* m) {
+  float3 t = {
+      m[0] * p.x + m[4] * p.y + m[8] * p.z,
+      m[1] * p.x + m[5] * p.y + m[9] * p.z,
+      m[2] * p.x + m[6] * p.y + m[10] * p.z,
+  };
+  return t;
+}
+
+// (w,x,y,z) quaternion stored in fields (x,y,z,w); normalised here with rsqrtf.
+__device__ __forceinline__ m3 quat_to_rotmat(const v4 quat) {
+  float s = rsqrtf(quat.w * quat.w + quat.x * quat.x + quat.y * quat.y + quat.z * quat.z);
+  float w = quat.x * s;
+  float x = quat.y * s;
+  float y = quat.z * s;
+  float z = quat.w * s;
+  m3 R;
+  R[0] = v3(1.f - 2.f * (y * y + z * z), 2.f * (x * y + w * z), 2.f * (x * z - w * y));
+  R[1] = v3(2.f * (x * y - w * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z + w * x));
+  R[2] = v3(2.f * (x * z + w * y), 2.f * (y * z - w * x), 1.f - 2.f * (x * x + y * y));
+  return R;
+}
+
+__device__ __forceinline__ m3 scale_to_mat(const v2 scale, const float glob_scale) {
+  m3 S = diag3(1.f);
+  S[0][0] = glob_scale * scale.x;
+  S[1][1] = glob_scale * scale.y;
+  return S;
+}
+
+// T = transpose(splat2world) * world2ndc * ndc2pix, normal = view rotation of the
+// third rotation column.
+__device__ __forceinline__ void compute_transmat(const float3& p_orig, const v2 scale, float mod, const v4 rot,
+                                                 const float* projmatrix, const float* viewmatrix, const int W,
+                                                 const int H, m3& T, float3& normal) {
+  m3 R = quat_to_rotmat(rot);
+  m3 S = scale_to_mat(scale, mod);
+  m3 L = R * S;
+
+  m3x4 splat2world = make_m3x4(v4(L[0], 0.0f), v4(L[1], 0.0f), v4(p_orig.x, p_orig.y, p_orig.z, 1.f));
+
+  m4 world2ndc;
+  world2ndc[0] = v4(projmatrix[0], projmatrix[4], projmatrix[8], projmatrix[12]);
+  world2ndc[1] = v4(projmatrix[1], projmatrix[5], projmatrix[9], projmatrix[13]);
+  world2ndc[2] = v4(projmatrix[2], projmatrix[6], projmatrix[10], projmatrix[14]);
+  world2ndc[3] = v4(projmatrix[3], projmatrix[7], projmatrix[11], projmatrix[15]);
+
+  m3x4 ndc2pix = make_m3x4(v4((float)(float(W) / 2.0), 0.0f, 0.0f, (float)(float(W - 1) / 2.0)),
+                           v4(0.0f, (float)(float(H) / 2.0), 0.0f, (float)(float(H - 1) / 2.0)),
+                           v4(0.0f, 0.0f, 0.0f, 1.0f));
+
+  T = transpose(splat2world) * world2ndc * ndc2pix;
+  normal = xform_vec4x3({L[2].x, L[2].y, L[2].z}, viewmatrix);
+}
+
+// Bounding box of the cutoff-sigma level set in pixel space.
+__device__ __forceinline__ bool compute_aabb(m3 T, float cutoff, float2& point_image, float2& extent) {
+  v3 t = v3(cutoff * cutoff, cutoff * cutoff, -1.0f);
+  float d = dot(t, T[2] * T[2]);
+  if (d == 0.0) return false;
+  v3 f = (1 / d) * t;
+
+  v2 p = v2(dot(f, T[0] * T[2]), dot(f, T[1] * T[2]));
+  v2 h0 = p * p - v2(dot(f, T[0] * T[0]), dot(f, T[1] * T[1]));
+  v2 h = vsqrt(vmax(v2(1e-4, 1e-4), h0));
+  point_image = {p.x, p.y};
+  extent = {h.x, h.y};
+  return true;
+}
+
+__device__ __forceinline__ void tile_rect(const float2 p, int max_radius, uint2& rect_min, uint2& rect_max,
+                                          dim3 grid) {
+  rect_min = {min(grid.x, max((int)0, (int)((p.x - max_radius) / TILE_X))),
+              min(grid.y, max((int)0, (int)((p.y - max_radius) / TILE_Y)))};
+  rect_max = {min(grid.x, max((int)0, (int)((p.x + max_radius + TILE_X - 1) / TILE_X))),
+              min(grid.y, max((int)0, (int)((p.y + max_radius + TILE_Y - 1) / TILE_Y)))};
+}
+
+__device__ __forceinline__ v3 color_from_sh(int idx, int deg, int max_coeffs, const v3* means, v3 campos,
+                                            const float* shs, unsigned& clamped_mask) {
+  v3 pos = means[idx];
+  v3 dir = pos - campos;
+  dir = dir / length(dir);
+
+  const v3* sh = ((const v3*)shs) + (size_t)idx * max_coeffs;
+  v3 result = kSH_C0 * sh[0];
+
+  if (deg > 0) {
+    float x = dir.x;
+    float y = dir.y;
+    float z = dir.z;
+    result = result - kSH_C1 * y * sh[1] + kSH_C1 * z * sh[2] - kSH_C1 * x * sh[3];
+
+    if (deg > 1) {
+      float xx = x * x, yy = y * y, zz = z * z;
+      float xy = x * y, yz = y * z, xz = x * z;
+      result = result + kSH_C2[0] * xy * sh[4] + kSH_C2[1] * yz * sh[5] +
+               kSH_C2[2] * (2.0f * zz - xx - yy) * sh[6] + kSH_C2[3] * xz * sh[7] + kSH_C2[4] * (xx - yy) * sh[8];
+
+      if (deg > 2) {
+        result = result + kSH_C3[0] * y * (3.0f * xx - yy) * sh[9] + kSH_C3[1] * xy * z * sh[10] +
+                 kSH_C3[2] * y * (4.0f * zz - xx - yy) * sh[11] +
+                 kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[12] +
+                 kSH_C3[4] * x * (4.0f * zz - xx - yy) * sh[13] + kSH_C3[5] * z * (xx - yy) * sh[14] +
+                 kSH_C3[6] * x * (xx - 3.0f * yy) * sh[15];
+      }
+    }
+  }
+  result += 0.5f;
+  clamped_mask = (result.x < 0 ? 1u : 0u) | (result.y < 0 ? 2u : 0u) | (result.z < 0 ? 4u : 0u);
+  return vmax(result, 0.0f);
+}
+
+// Conservative screen-space box outside of which the reference is guaranteed to
+// skip the fragment with `alpha < 1/255`: alpha = opa*exp(-rho/2) and
+// rho = min(rho3d, rho2d), so a pixel can only pass if rho3d <= c2 or rho2d <= c2
+// with c2 = 2 ln(255 opa).  {rho3d <= c2} projects inside the c-sigma AABB of the
+// splat when the whole c-sigma disk lies in front of the camera plane;
+// {rho2d <= c2} is a disc of radius sqrt(c2/2) around the low-pass centre.
+// Evaluated in fp64 with margins; falls back to "everything" when the projected
+// conic is not an ellipse.  This is new relative to the reference (which visits
+// every pixel of every binned tile); it does not change any result.
+__device__ __forceinline__ float4 cull_box(const m3& T, float2 xy, float opa) {
+  const float BIG = 3.0e38f;
+  float4 all = {-BIG, -BIG, BIG, BIG};
+  if (!(opa > 0.f)) return make_float4(BIG, BIG, -BIG, -BIG);  // alpha <= 0 < 1/255 always
+  double c2 = 2.0 * log(255.0 * (double)opa);
+  c2 = c2 * 1.02 + 0.05;
+  if (c2 <= 0.0) return make_float4(BIG, BIG, -BIG, -BIG);
+  double ux = T[0].x, uy = T[0].y, uz = T[0].z;
+  double vx = T[1].x, vy = T[1].y, vz = T[1].z;
+  double wx = T[2].x, wy = T[2].y, wz = T[2].z;
+  double wn = c2 * (wx * wx + wy * wy);
+  // disk of radius c must be strictly in front: wz > c*|(wx,wy)| with slack
+  if (!(wz > 0.0) || !(wz * wz > wn * 1.0201)) return all;
+  double d = wn - wz * wz;  // < 0
+  double inv = 1.0 / d;
+  double cx = (c2 * (ux * wx + uy * wy) - uz * wz) * inv;
+  double cy = (c2 * (vx * wx + vy * wy) - vz * wz) * inv;
+  double hx2 = cx * cx - (c2 * (ux * ux + uy * uy) - uz * uz) * inv;
+  double hy2 = cy * cy - (c2 * (vx * vx + vy * vy) - vz * vz) * inv;
+  if (!(hx2 >= 0.0) || !(hy2 >= 0.0) || !isfinite(hx2) || !isfinite(hy2)) return all;
+  double hx = sqrt(hx2) * 1.01 + 0.5;
+  double hy = sqrt(hy2) * 1.01 + 0.5;
+  double r2 = sqrt(0.5 * c2) + 0.5;
+  double x0 = fmin(cx - hx, (double)xy.x - r2), x1 = fmax(cx + hx, (double)xy.x + r2);
+  double y0 = fmin(cy - hy, (double)xy.y - r2), y1 = fmax(cy + hy, (double)xy.y + r2);
+  if (!isfinite(x0) || !isfinite(x1) || !isfinite(y0) || !isfinite(y1)) return all;
+  return make_float4(__double2float_rd(x0), __double2float_rd(y0), __double2float_ru(x1), __double2float_ru(y1));
+}
+
+__global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessFwdArgs a) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.P) return;
+
+  // Invisible unless proven otherwise (reference forward.cu:184-185).
+  a.radii[idx] = 0;
+  a.tiles_touched[idx] = 0;
+
+  const int W = a.W, H = a.H;
+  const float* orig_points = a.means3D;
+
+  // near cull (auxiliary.h:185-210): only p_view.z <= 0.2 rejects.
+  float3 p_orig = {orig_points[3 * idx], orig_points[3 * idx + 1], orig_points[3 * idx + 2]};
+  float3 p_view = xform_point4x3(p_orig, a.viewmatrix);
+  if (p_view.z <= 0.2f) return;
+
+  m3 T;
+  float3 normal;
+  if (a.transMat_precomp == nullptr) {
+    compute_transmat(p_orig, ((const v2*)a.scales)[idx], a.scale_modifier, ((const v4*)a.rotations)[idx],
+                     a.projmatrix, a.viewmatrix, W, H, T, normal);
+  } else {
+    const v3* T_ptr = (const v3*)a.transMat_precomp;
+    T = make_m3(T_ptr[idx * 3 + 0], T_ptr[idx * 3 + 1], T_ptr[idx * 3 + 2]);
+    normal = make_float3(0.0, 0.0, 1.0);
+  }
+
+  // dual-visible: flip the normal toward the camera (forward.cu:209-214)
+  float cosv = -(p_view.x * normal.x + p_view.y * normal.y + p_view.z * normal.z);
+  if (cosv == 0) return;
+  float multiplier = cosv > 0 ? 1 : -1;
+  normal = make_float3(multiplier * normal.x, multiplier * normal.y, multiplier * normal.z);
+
+  float cutoff = 3.0f;
+  float2 point_image;
+  float radius;
+  {
+    float2 extent;
+    bool ok = compute_aabb(T, cutoff, point_image, extent);
+    if (!ok) return;
+    radius = ceil(max(max(extent.x, extent.y), cutoff * PGS_FILTER_SIZE));
+  }
+
+  dim3 grid(a.grid_x, a.grid_y, 1);
+  uint2 rect_min, rect_max;
+  tile_rect(point_image, radius, rect_min, rect_max, grid);
+  if ((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y) == 0) return;
+
+  float r, g, b;
+  unsigned clamped = 0;
+  if (a.colors_precomp == nullptr) {
+    v3 c = color_from_sh(idx, a.D, a.M, (const v3*)orig_points, *(const v3*)a.cam_pos, a.shs, clamped);
+    r = c.x; g = c.y; b = c.z;
+  } else {
+    r = a.colors_precomp[idx * 3 + 0];
+    g = a.colors_precomp[idx * 3 + 1];
+    b = a.colors_precomp[idx * 3 + 2];
+  }
+
+  const float opa = a.opacities[idx];
+  float4* rec = a.rec + (size_t)idx * REC_QUADS;
+  rec[0] = make_float4(T[0].x, T[0].y, T[0].z, point_image.x);
+  rec[1] = make_float4(T[1].x, T[1].y, T[1].z, point_image.y);
+  rec[2] = make_float4(T[2].x, T[2].y, T[2].z, opa);
+  rec[3] = make_float4(normal.x, normal.y, normal.z, p_view.z);
+  rec[4] = make_float4(r, g, b, __uint_as_float(clamped));
+  a.bbox[idx] = cull_box(T, point_image, opa);
+
+  a.radii[idx] = (int)radius;
+  a.tiles_touched[idx] = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
+}
+
+// mark_visible (reference checkFrustum, rasterizer_impl.cu:54-66)
+__global__ void __launch_bounds__(256) check_frustum_kernel(int P, const float* means3D, const float* viewmatrix,
+                                                            unsigned char* present) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  float3 p = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+  float3 pv = xform_point4x3(p, viewmatrix);
+  present[idx] = (pv.z <= 0.2f) ? 0 : 1;
+}
+
+void launch_preprocess_fwd(const PreprocessFwdArgs& a, cudaStream_t s) {
+  if (a.P <= 0) return;
+  preprocess_fwd_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a);
+  count_launch();
+}
+void launch_check_frustum(int P, const float* means3D, const float* viewmatrix, unsigned char* present,
+                          cudaStream_t s) {
+  if (P <= 0) return;
+  check_frustum_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, viewmatrix, present);
+  count_launch();
+}
+
+}  // namespace pgs

@@ -1,0 +1,85 @@
+"""Shared helpers for the parity tests (product CUDA path vs oracle)."""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+# north_star tolerances (BASELINE.json): images 1e-5 relative, gradients 1e-4 relative (fp32)
+IMG_RTOL = 1e-5
+GRAD_RTOL = 1e-4
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    """max |a-b| / max |b|  (norm-wise relative error; b is the reference)."""
+    a = a.double()
+    b = b.double()
+    if a.numel() == 0:
+        return 0.0
+    d = (a - b).abs().max().item()
+    s = b.abs().max().item()
+    return d / (s + 1e-30)
+
+
+def mismatch_frac(a: torch.Tensor, b: torch.Tensor, rtol: float) -> float:
+    """fraction of elements with |a-b| > rtol * (|b| + mean|b|)"""
+    a = a.double()
+    b = b.double()
+    if a.numel() == 0:
+        return 0.0
+    tol = rtol * (b.abs() + b.abs().mean())
+    return ((a - b).abs() > tol).double().mean().item()
+
+
+def settings_from_cam(cam, bg, sh_degree=3, scale_modifier=1.0, debug=False):
+    from partgs_b200.diff_surfel_rasterization import GaussianRasterizationSettings
+    return GaussianRasterizationSettings(
+        image_height=cam.image_height, image_width=cam.image_width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=bg,
+        scale_modifier=scale_modifier, viewmatrix=cam.viewmatrix, projmatrix=cam.projmatrix, sh_degree=sh_degree,
+        campos=cam.campos, prefiltered=False, debug=debug)
+
+
+def run_ours(scene, cam, bg, grads=None, sh_degree=3, scale_modifier=1.0, colors_precomp=None):
+    """Forward (+ backward when `grads` is given) through the public drop-in API."""
+    from partgs_b200.diff_surfel_rasterization import GaussianRasterizer, _C
+    leaf = {}
+    for k in ("means3D", "scales", "rotations", "opacities", "shs"):
+        leaf[k] = scene[k].detach().clone().requires_grad_(grads is not None)
+    means2D = torch.zeros_like(leaf["means3D"], requires_grad=grads is not None)
+    rast = GaussianRasterizer(settings_from_cam(cam, bg, sh_degree, scale_modifier))
+    kw = dict(means3D=leaf["means3D"], means2D=means2D, opacities=leaf["opacities"], scales=leaf["scales"],
+              rotations=leaf["rotations"])
+    cp = None
+    if colors_precomp is None:
+        kw["shs"] = leaf["shs"]
+    else:
+        cp = colors_precomp.detach().clone().requires_grad_(grads is not None)
+        kw["colors_precomp"] = cp
+    color, radii, allmap = rast(**kw)
+    out = dict(color=color.detach(), radii=radii, allmap=allmap.detach())
+    if grads is not None:
+        torch.autograd.backward([color, allmap], [grads["color"], grads["allmap"]])
+        out["grads"] = dict(means3D=leaf["means3D"].grad, means2D=means2D.grad, opacity=leaf["opacities"].grad,
+                            scales=leaf["scales"].grad, rotations=leaf["rotations"].grad)
+        if cp is None:
+            out["grads"]["sh"] = leaf["shs"].grad
+        else:
+            out["grads"]["colors"] = cp.grad
+    return out
+
+
+def run_ours_raw(scene, cam, bg, sh_degree=3, scale_modifier=1.0):
+    """Forward through the native entry point, returning the state buffers too."""
+    from partgs_b200.diff_surfel_rasterization import _C
+    dev = scene["means3D"].device
+    empty = torch.empty(0, device=dev)
+    R, color, others, radii, geom, binning, img = _C.rasterize_gaussians(
+        bg, scene["means3D"], empty, scene["opacities"], scene["scales"], scene["rotations"], scale_modifier, empty,
+        cam.viewmatrix, cam.projmatrix, cam.tanfovx, cam.tanfovy, cam.image_height, cam.image_width, scene["shs"],
+        sh_degree, cam.campos, False, False)
+    return dict(num_rendered=R, color=color, allmap=others, radii=radii, geom=geom, binning=binning, img=img)
