@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""bench.py — fwd+bwd frames/s of the surfel rasteriser hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C3]
+
+A "step" is one view rendered forward + backward (all 3+7 output channels receive a
+fixed synthetic upstream gradient) over the workload's resident surfel set; at N>1 every
+rank renders its own cameras (views shard by camera, surfel parameters replicated) and
+the per-step parameter gradients are all-reduced over NCCL.
+
+One JSON line on rank 0; see DESIGN.md §Measurement for how each field is derived.
+`--impl reference` times the UNMODIFIED reference CUDA rasteriser (oracle/_ref, built
+from /root/reference by oracle/Makefile) on the same tensors, same box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "fwd+bwd frames/s @1M surfels 1600x1200"
+UNIT = "frames/s"
+GRAD_BYTES_PER_SURFEL = 232  # xyz 12 + f_dc 12 + f_rest 180 + opacity 4 + scale 8 + rot 16
+
+
+# --------------------------------------------------------------------------------------
+def dist_setup(n_gpus: int):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+        local = 0
+    return world, rank, local
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(P, V, R, npix, ntile, M=16, S=0, passes=6):
+    """compulsory-traffic model of one frame."""
+    a_f = 64 * P + (12 * M + 91) * V + (104 + 24 * passes + 4 * S) * R + (60 + 4 * S) * npix + 8 * ntile
+    a_b = (304 + 4 * S) * P + (12 * M + 151) * V + (12 * M + 48) * V + (76 + 4 * S) * R + (60 + 4 * S) * npix
+    return a_f, a_b
+
+
+# --------------------------------------------------------------------------------------
+class OursArm:
+    name = "ours"
+
+    def __init__(self, scene, dev):
+        from partgs_b200 import _lib
+        from partgs_b200.diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.S = GaussianRasterizationSettings
+        self.Rz = GaussianRasterizer
+        self.dev = dev
+        self.params = {k: scene[k].clone().requires_grad_(True)
+                       for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+        self.means2D = torch.zeros_like(self.params["means3D"], requires_grad=True)
+        self.last_radii = None
+
+    def step(self, cam, bg, g, params=None, want_loss=False):
+        p = params or self.params
+        for t in p.values():
+            t.grad = None
+        self.means2D.grad = None
+        settings = self.S(image_height=cam.image_height, image_width=cam.image_width, tanfovx=cam.tanfovx,
+                          tanfovy=cam.tanfovy, bg=bg, scale_modifier=1.0, viewmatrix=cam.viewmatrix,
+                          projmatrix=cam.projmatrix, sh_degree=3, campos=cam.campos, prefiltered=False, debug=False)
+        color, radii, allmap = self.Rz(settings)(means3D=p["means3D"], means2D=self.means2D,
+                                                 opacities=p["opacities"], shs=p["shs"], scales=p["scales"],
+                                                 rotations=p["rotations"])
+        loss = None
+        if want_loss:
+            loss = (color * g["color"]).sum() + (allmap * g["allmap"]).sum()
+            loss.backward()
+        else:
+            torch.autograd.backward([color, allmap], [g["color"], g["allmap"]])
+        self.last_radii = radii
+        return loss, [p[k].grad for k in ("means3D", "shs", "opacities", "scales", "rotations")]
+
+    def launches(self):
+        return int(self.lib.pgs_launch_count())
+
+
+class ReferenceArm:
+    name = "reference"
+
+    def __init__(self, scene, dev):
+        from oracle import ref_cuda
+        self.rc = ref_cuda
+        self.C = ref_cuda.load("ref_dsr_C")
+        self.dev = dev
+        self.params = {k: scene[k].clone() for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+        self.empty = torch.empty(0, device=dev)
+        self.last_radii = None
+        self.n_launch = 0
+
+    def step(self, cam, bg, g, params=None, want_loss=False):
+        p = params or self.params
+        e = self.empty
+        R, color, others, radii, geom, binning, img = self.C.rasterize_gaussians(
+            bg, p["means3D"], e, p["opacities"], p["scales"], p["rotations"], 1.0, e, cam.viewmatrix, cam.projmatrix,
+            cam.tanfovx, cam.tanfovy, cam.image_height, cam.image_width, p["shs"], 3, cam.campos, False, False)
+        loss = (color * g["color"]).sum() + (others * g["allmap"]).sum() if want_loss else None
+        grads = self.C.rasterize_gaussians_backward(
+            bg, p["means3D"], radii, e, p["scales"], p["rotations"], 1.0, e, cam.viewmatrix, cam.projmatrix,
+            cam.tanfovx, cam.tanfovy, g["color"], g["allmap"], p["shs"], 3, cam.campos, geom, R, binning, img, False)
+        self.last_radii = radii
+        self.n_launch += 15  # preprocess, scan x2, dup, sort x8, ranges, render, bwd render, bwd preprocess
+        d2, dc, do, d3, dT, dsh, dsc, dr = grads
+        return loss, [d3, dsh, do, dsc, dr]
+
+    def launches(self):
+        return self.n_launch
+
+
+# --------------------------------------------------------------------------------------
+def run(args):
+    world, rank, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    from partgs_b200 import synth
+
+    name = args.workload
+    cfg = dict(synth.CONFIGS[name])
+    seed = synth.SEED_BASE + synth.CONFIG_INDEX[name]
+    scene = synth.make_point_scene(cfg["P"], seed, S=0, device=dev)
+    all_cams = synth.make_cameras(cfg["views"], cfg["W"], cfg["H"], seed, device=dev)
+    my_cams = all_cams[rank::world] or all_cams
+    W, H, P = cfg["W"], cfg["H"], cfg["P"]
+    bg = torch.zeros(3, device=dev)
+    g = synth.upstream_grads(W, H, synth.SEED_BASE, device=dev)
+    npix, ntile = W * H, ((W + 15) // 16) * ((H + 15) // 16)
+
+    if args.impl == "reference":
+        from oracle import ref_cuda
+        if not ref_cuda.available("ref_dsr_C"):
+            if rank == 0:
+                print(json.dumps({"impl": "reference",
+                                  "unavailable": "oracle/_ref/ref_dsr_C.so not built (needs /root/reference)"}))
+            return
+        arm = ReferenceArm(scene, dev)
+    else:
+        arm = OursArm(scene, dev)
+
+    if world > 1:
+        import torch.distributed as dist
+
+    pending = []
+
+    def allreduce_grads(grads):
+        # one async NCCL all-reduce per parameter group; waited on before the grads are replaced
+        for h in pending:
+            h.wait()
+        pending.clear()
+        if world > 1:
+            for t in grads:
+                pending.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
+
+    def one_step(i):
+        cam = my_cams[i % len(my_cams)]
+        loss, grads = arm.step(cam, bg, g)
+        allreduce_grads(grads)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ---------------------------------------------------------------------
+    for i in range(max(args.warmup, 3)):
+        one_step(i)
+    for h in pending:
+        h.wait()
+    pending.clear()
+    torch.cuda.synchronize()
+
+    # ---- timed region: inputs resident in HBM ------------------------------------------
+    if arm.name == "ours":
+        arm._lib.timing_enable(True)
+        arm._lib.timing_read(reset=True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = arm.launches()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        one_step(i)
+    for h in pending:
+        h.wait()
+    pending.clear()
+    e1.record()
+    barrier()
+    t_ms = e0.elapsed_time(e1)
+    l1 = arm.launches()
+    stage = None
+    if arm.name == "ours":
+        stage = arm._lib.timing_read(reset=True)
+        arm._lib.timing_enable(False)
+    clock_info = clocks.stop() if rank == 0 else None
+    tt = torch.tensor([t_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_ms = float(tt.item())
+    value = world * args.steps / (t_ms / 1e3)
+
+    # workload statistics of the last timed view (V, R) for the byte model
+    V = int((arm.last_radii > 0).sum().item())
+
+    # ---- end-to-end: host buffers in, loss out -------------------------------------------
+    # Every step the rasteriser inputs (surfel parameters + camera) come from pinned host
+    # memory (copied on a side stream one step ahead, so the copy overlaps the previous
+    # step's kernels) and the step's scalar loss is read back to the host.
+    host = {k: v.detach().cpu().pin_memory() for k, v in arm.params.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values()) + 2 * 64 + 12
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_host = torch.zeros(1).pin_memory()
+
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            for k, v in host.items():
+                slots[slot][k].copy_(v, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_loop(n):
+        cur = torch.cuda.current_stream(dev)
+        for s in range(2):
+            consumed[s].record(cur)
+        upload(0)
+        for i in range(n):
+            s = i & 1
+            if i + 1 < n:
+                upload(1 - s)
+            cur.wait_event(ready[s])
+            cam = my_cams[i % len(my_cams)]
+            prm = slots[s]
+            if arm.name == "ours":
+                prm = {k: v.detach().requires_grad_(True) for k, v in prm.items()}
+            loss, grads = arm.step(cam, bg, g, params=prm, want_loss=True)
+            allreduce_grads(grads)
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+            consumed[s].record(cur)
+        for h in pending:
+            h.wait()
+        pending.clear()
+        torch.cuda.synchronize()
+        return float(loss_host.item())
+
+    e2e_loop(2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(args.steps)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / float(te.item())
+
+    if rank != 0:
+        return
+
+    # ---- R of the last view (needed by the byte model); taken outside the timed region --
+    cam = my_cams[(args.steps - 1) % len(my_cams)]
+    if arm.name == "ours":
+        from partgs_b200.diff_surfel_rasterization import _C
+        e = torch.empty(0, device=dev)
+        R = _C.rasterize_gaussians(bg, scene["means3D"], e, scene["opacities"], scene["scales"], scene["rotations"],
+                                   1.0, e, cam.viewmatrix, cam.projmatrix, cam.tanfovx, cam.tanfovy, H, W,
+                                   scene["shs"], 3, cam.campos, False, False)[0]
+    else:
+        R = arm.rc.forward(scene, cam, bg)["num_rendered"]
+    a_f, a_b = algorithmic_bytes(P, V, R, npix, ntile)
+    peak, peak_src = measured_peak()
+
+    out = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(t_ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{name}: {P} surfels, {W}x{H}, fwd+bwd, all 10 output channels get gradient",
+                   "views": cfg["views"], "views_per_rank": len(my_cams), "sharding": "by camera",
+                   "collective": "nccl all-reduce of 232 B/surfel parameter gradients per step" if world > 1 else "none",
+                   "l2": "inputs (232 MB parameters + per-view state) exceed the 126 MB L2; views cycle every step",
+                   "V_visible": V, "R_instances": int(R)},
+        "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": int(l1 - l0),
+        "clocks": clock_info,
+        "frame_roofline": {"algorithmic_bytes": int(a_f + a_b), "achieved_gbs": round((a_f + a_b) / (t_ms / args.steps * 1e-3) / 1e9, 1),
+                           "peak_gbs": peak, "frac": round((a_f + a_b) / (t_ms / args.steps * 1e-3) / 1e9 / peak, 4)},
+    }
+    if args.impl == "reference":
+        out["impl"] = "reference"
+    if stage is not None:
+        # dominant kernel: backward render.  algorithmic bytes per launch = 76 B per surfel-tile
+        # instance gathered + 60 B per pixel of upstream gradients and saved state (SURVEY §8(d) A_b terms)
+        ms, n = stage["render_bwd"]
+        per_launch_s = ms / max(n, 1) * 1e-3
+        alg = 76 * R + 60 * npix
+        traffic = None
+        tp = ROOT / "profiles" / "traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get("render_bwd_kernel", {}).get(name)
+            except Exception:
+                traffic = None
+        ach = alg / per_launch_s / 1e9
+        out["roofline"] = {"bound": "hbm", "kernel": "render_bwd_kernel", "achieved": round(ach, 1), "peak": peak,
+                           "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic,
+                           "peak_source": peak_src, "avg_launch_ms": round(ms / max(n, 1), 4)}
+        out["stage_ms_per_step"] = {k: round(v[0] / args.steps, 4) for k, v in stage.items() if v[1]}
+
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample ------------------
+    if world == 1 and args.impl != "reference" and not args.no_cpu:
+        from oracle import cpu_oracle
+        cpu_scene = {k: v.cpu() for k, v in scene.items()}
+        camc = my_cams[0].to("cpu")
+        gc = {k: v.cpu() for k, v in g.items()}
+        t0 = time.perf_counter()
+        f = cpu_oracle.forward_scene(cpu_scene, camc, keep_state=True)
+        cpu_oracle.backward(f, gc["color"], gc["allmap"])
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": round(1.0 / dt, 4), "unit": UNIT, "cores": cpu_oracle.load().oracle_num_threads(),
+                               "kind": "port", "sample": f"1 frame (view 0) of {name} fwd+bwd, oracle/surfel_oracle.c + OpenMP"}
+    if args.impl == "reference":
+        out["cpu_baseline"] = {"value": out["value"], "unit": UNIT, "cores": 0, "kind": "reference",
+                               "sample": "unmodified reference CUDA rasteriser (oracle/_ref) on the same GPU, same steps"}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    run(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,17 @@ int pgs_version(void);
 /* Number of kernels launched by this library in the calling process so far. */
 unsigned long long pgs_launch_count(void);
 
+/* ---- per-stage device timing (CUDA events recorded on the caller's stream around each
+ * kernel group); off by default.  pgs_timing_read synchronises the recorded events and
+ * returns accumulated milliseconds / launch counts per stage. */
+enum {
+  PGS_STAGE_PREPROCESS_FWD = 0, PGS_STAGE_SCAN, PGS_STAGE_DUP_KEYS, PGS_STAGE_SORT, PGS_STAGE_TILE_RANGES,
+  PGS_STAGE_RENDER_FWD, PGS_STAGE_RENDER_BWD, PGS_STAGE_PREPROCESS_BWD, PGS_STAGE_KNN, PGS_STAGE_SQ_FWD,
+  PGS_STAGE_SQ_BWD, PGS_NUM_STAGES
+};
+void pgs_timing_enable(int on);
+int pgs_timing_read(double* ms, unsigned long long* counts, int reset);
+
 /* ---- base rasteriser ----------------------------------------------------------
  * Replaces CudaRasterizer::Rasterizer::forward (DSR/cuda_rasterizer/rasterizer.h:31-61,
  * rasterizer_impl.cu:198-342).  Same argument meaning; optional inputs are NULL

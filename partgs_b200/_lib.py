@@ -32,6 +32,8 @@ SIGNATURES = {
     "pgs_last_error": (C.c_char_p, []),
     "pgs_version": (C.c_int, []),
     "pgs_launch_count": (C.c_ulonglong, []),
+    "pgs_timing_enable": (None, [C.c_int]),
+    "pgs_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), C.c_int]),
     "pgs_dsr_forward": (C.c_int, [ALLOC_FN, _vp, ALLOC_FN, _vp, ALLOC_FN, _vp, C.c_int, C.c_int, C.c_int,
                                   _f32p, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, _f32p,
                                   _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_int, _f32p, _f32p, _vp,
@@ -123,3 +125,20 @@ def require_cuda_float(t: torch.Tensor, name: str) -> torch.Tensor:
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
+
+
+STAGES = ("preprocess_fwd", "scan", "dup_keys", "sort", "tile_ranges", "render_fwd", "render_bwd", "preprocess_bwd",
+          "knn", "sq_fwd", "sq_bwd")
+
+
+def timing_enable(on: bool = True):
+    load().pgs_timing_enable(1 if on else 0)
+
+
+def timing_read(reset: bool = True):
+    """{stage: (total_ms, launches)} accumulated since the last reset."""
+    n = len(STAGES)
+    ms = (C.c_double * n)()
+    cnt = (C.c_ulonglong * n)()
+    check(load().pgs_timing_read(ms, cnt, 1 if reset else 0), "pgs_timing_read")
+    return {STAGES[i]: (ms[i], int(cnt[i])) for i in range(n)}

@@ -3,6 +3,8 @@
 // Mirrors the call order of reference CudaRasterizer::Rasterizer::forward/backward
 // (cuda_rasterizer/rasterizer_impl.cu:198-342, 346-448).
 #include <atomic>
+#include <mutex>
+#include <vector>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -35,6 +37,27 @@ int check_sync(cudaStream_t s, const char* what) {
   if (e != cudaSuccess) return set_error(PGS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return 0;
 }
+
+// ---- optional per-stage device timing (CUDA events on the launching stream) ------
+// bench.py uses it to time the dominant kernel live inside its timed region.
+struct StageSpan { int stage; cudaEvent_t a, b; };
+static std::atomic<int> g_timing{0};
+static std::mutex g_timing_mu;
+static std::vector<StageSpan> g_spans;
+static std::vector<cudaEvent_t> g_event_pool;
+static cudaEvent_t get_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct StageTimer {
+  bool on; int stage; cudaStream_t s; cudaEvent_t a, b;
+  StageTimer(int stage_, cudaStream_t s_) : on(g_timing.load() != 0), stage(stage_), s(s_) {
+    if (on) { std::lock_guard<std::mutex> lk(g_timing_mu); a = get_event(); b = get_event(); cudaEventRecord(a, s); }
+  }
+  ~StageTimer() {
+    if (on) { cudaEventRecord(b, s); std::lock_guard<std::mutex> lk(g_timing_mu); g_spans.push_back({stage, a, b}); }
+  }
+};
 
 // reference getHigherMsb (rasterizer_impl.cu:35-50)
 static uint32_t higher_msb(uint32_t n) {
@@ -114,6 +137,29 @@ int pgs_version(void) { return 100; }
 unsigned long long pgs_launch_count(void) { return g_launches.load(); }
 uint32_t pgs_higher_msb(uint32_t n) { return higher_msb(n); }
 
+void pgs_timing_enable(int on) { g_timing.store(on ? 1 : 0); }
+int pgs_timing_read(double* ms, unsigned long long* counts, int reset) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  static double acc_ms[PGS_NUM_STAGES];
+  static unsigned long long acc_n[PGS_NUM_STAGES];
+  for (auto& sp : g_spans) {
+    cudaError_t e = cudaEventSynchronize(sp.b);
+    float t = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, sp.a, sp.b);
+    if (e != cudaSuccess) return set_error(PGS_ERR_CUDA, "timing: %s", cudaGetErrorString(e));
+    if (sp.stage >= 0 && sp.stage < PGS_NUM_STAGES) { acc_ms[sp.stage] += t; acc_n[sp.stage]++; }
+    g_event_pool.push_back(sp.a);
+    g_event_pool.push_back(sp.b);
+  }
+  g_spans.clear();
+  for (int i = 0; i < PGS_NUM_STAGES; i++) {
+    if (ms) ms[i] = acc_ms[i];
+    if (counts) counts[i] = acc_n[i];
+    if (reset) { acc_ms[i] = 0; acc_n[i] = 0; }
+  }
+  return 0;
+}
+
 int pgs_dsr_get_layout(int P, int width, int height, int R, pgs_dsr_layout* out) {
   if (!out || P < 0 || width <= 0 || height <= 0 || R < 0) return set_error(PGS_ERR_INVALID_ARG, "bad layout query");
   const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
@@ -192,11 +238,11 @@ int pgs_dsr_forward(pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_alloc
   pa.colors_precomp = colors_precomp; pa.viewmatrix = viewmatrix; pa.projmatrix = projmatrix; pa.cam_pos = cam_pos;
   pa.W = width; pa.H = height; pa.grid_x = gx; pa.grid_y = gy;
   pa.radii = radii; pa.rec = geom.rec; pa.bbox = geom.bbox; pa.tiles_touched = geom.tiles_touched;
-  launch_preprocess_fwd(pa, s);
+  { StageTimer t(PGS_STAGE_PREPROCESS_FWD, s); launch_preprocess_fwd(pa, s); }
   if (int e = check_cuda("preprocess_fwd")) return e;
   if (debug) if (int e = check_sync(s, "preprocess_fwd")) return e;
 
-  launch_inclusive_scan_u32(geom.tiles_touched, geom.point_offsets, P, geom.scan_temp, s);
+  { StageTimer t(PGS_STAGE_SCAN, s); launch_inclusive_scan_u32(geom.tiles_touched, geom.point_offsets, P, geom.scan_temp, s); }
   if (int e = check_cuda("scan")) return e;
 
   // number of surfel x tile instances; sizes the binning buffer (reference: rasterizer_impl.cu:282)
@@ -215,14 +261,17 @@ int pgs_dsr_forward(pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_alloc
   cudaMemsetAsync(img.ranges, 0, ntiles * sizeof(uint2), s);
   const uint32_t* point_list = bin.vals_a;
   if (num_rendered > 0) {
-    launch_duplicate_with_keys(P, geom.rec, geom.point_offsets, bin.keys_a, bin.vals_a, radii, gx, gy, s);
+    { StageTimer t(PGS_STAGE_DUP_KEYS, s);
+      launch_duplicate_with_keys(P, geom.rec, geom.point_offsets, bin.keys_a, bin.vals_a, radii, gx, gy, s); }
     if (int e = check_cuda("duplicate_with_keys")) return e;
-    int where = launch_radix_sort_pairs(bin.keys_a, bin.vals_a, bin.keys_b, bin.vals_b, num_rendered, end_bit,
-                                        bin.sort_temp, s);
+    int where;
+    { StageTimer t(PGS_STAGE_SORT, s);
+      where = launch_radix_sort_pairs(bin.keys_a, bin.vals_a, bin.keys_b, bin.vals_b, num_rendered, end_bit,
+                                      bin.sort_temp, s); }
     if (int e = check_cuda("radix_sort")) return e;
     const uint64_t* sorted_keys = where ? bin.keys_b : bin.keys_a;
     point_list = where ? bin.vals_b : bin.vals_a;
-    launch_identify_tile_ranges(num_rendered, sorted_keys, img.ranges, s);
+    { StageTimer t(PGS_STAGE_TILE_RANGES, s); launch_identify_tile_ranges(num_rendered, sorted_keys, img.ranges, s); }
     if (int e = check_cuda("identify_tile_ranges")) return e;
     if (debug) if (int e = check_sync(s, "binning")) return e;
   }
@@ -231,7 +280,7 @@ int pgs_dsr_forward(pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_alloc
   ra.ranges = img.ranges; ra.point_list = point_list; ra.W = width; ra.H = height; ra.grid_x = gx; ra.grid_y = gy;
   ra.rec = geom.rec; ra.bbox = geom.bbox; ra.bg_color = background;
   ra.final_T = img.final_T; ra.n_contrib = img.n_contrib; ra.out_color = out_color; ra.out_others = out_others;
-  launch_render_fwd(ra, s);
+  { StageTimer t(PGS_STAGE_RENDER_FWD, s); launch_render_fwd(ra, s); }
   if (int e = check_cuda("render_fwd")) return e;
   if (debug) if (int e = check_sync(s, "render_fwd")) return e;
   return num_rendered;
@@ -282,7 +331,7 @@ int pgs_dsr_backward(int P, int D, int M, int R, const float* background, int wi
   rb.ranges = img.ranges; rb.point_list = point_list; rb.W = width; rb.H = height; rb.grid_x = gx; rb.grid_y = gy;
   rb.rec = geom.rec; rb.bbox = geom.bbox; rb.bg_color = background; rb.final_T = img.final_T;
   rb.n_contrib = img.n_contrib; rb.dL_dpixels = dL_dpix; rb.dL_dothers = dL_dothers; rb.grad = grad;
-  launch_render_bwd(rb, s);
+  { StageTimer t(PGS_STAGE_RENDER_BWD, s); launch_render_bwd(rb, s); }
   if (int e = check_cuda("render_bwd")) return e;
   if (debug) if (int e = check_sync(s, "render_bwd")) return e;
 
@@ -294,7 +343,7 @@ int pgs_dsr_backward(int P, int D, int M, int R, const float* background, int wi
   pb.rec = geom.rec; pb.grad = grad;
   pb.dL_dmean2D = dL_dmean2D; pb.dL_dcolors = dL_dcolor; pb.dL_dopacity = dL_dopacity; pb.dL_dmean3D = dL_dmean3D;
   pb.dL_dtransMat = dL_dtransMat; pb.dL_dsh = dL_dsh; pb.dL_dscales = dL_dscale; pb.dL_drots = dL_drot;
-  launch_preprocess_bwd(pb, s);
+  { StageTimer t(PGS_STAGE_PREPROCESS_BWD, s); launch_preprocess_bwd(pb, s); }
   if (int e = check_cuda("preprocess_bwd")) return e;
   if (debug) if (int e = check_sync(s, "preprocess_bwd")) return e;
   return 0;

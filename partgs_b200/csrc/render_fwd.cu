@@ -179,7 +179,10 @@ __global__ void __launch_bounds__(TILE_PIX) render_fwd_kernel(RenderFwdArgs a) {
   a.final_T[sidx + npt] = M1;
   a.final_T[sidx + 2 * npt] = M2;
   a.n_contrib[sidx] = last_contributor;
-  a.n_contrib[sidx + npt] = (uint32_t)median_contributor;
+  // The reference converts its float -1 sentinel to uint32 (undefined in C++, garbage in
+  // practice) for pixels nothing was blended into; those pixels have n_contrib == 0 and the
+  // value is never consulted.  Store a defined 0 instead.
+  a.n_contrib[sidx + npt] = median_contributor < 0.f ? 0u : (uint32_t)median_contributor;
 
   if (inside) {
     const size_t HW = (size_t)a.H * a.W;

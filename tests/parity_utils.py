@@ -36,6 +36,20 @@ def mismatch_frac(a: torch.Tensor, b: torch.Tensor, rtol: float) -> float:
     return ((a - b).abs() > tol).double().mean().item()
 
 
+def robust_close(a, b, atol_frac=1e-4, max_frac=2e-3):
+    """Comparison against the CPU restatement, which rounds differently from the GPU (no FMA
+    contraction): a few fragments sit on the other side of the alpha >= 1/255 or T < 1e-4
+    tests, which moves single pixels / surfels by up to ~4e-3.  Require that all but
+    `max_frac` of the elements agree to atol_frac * max|b| and that the mean error is tiny."""
+    a = torch.as_tensor(a).double().flatten()
+    b = torch.as_tensor(b).double().flatten()
+    scale = b.abs().max().item() + 1e-30
+    d = (a - b).abs()
+    frac_bad = (d > atol_frac * scale).double().mean().item()
+    mean_err = d.mean().item() / scale
+    return frac_bad <= max_frac and mean_err <= atol_frac, (frac_bad, mean_err)
+
+
 def settings_from_cam(cam, bg, sh_degree=3, scale_modifier=1.0, debug=False):
     from partgs_b200.diff_surfel_rasterization import GaussianRasterizationSettings
     return GaussianRasterizationSettings(
