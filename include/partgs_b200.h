@@ -88,6 +88,39 @@ int pgs_dsr_backward(int P, int D, int M, int R, const float* background, int wi
 int pgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                      unsigned char* present, void* stream);
 
+/* ---- superquadric -> surfel parameterisation ------------------------------------------
+ * Replaces BlockGaussianModel.get_verts / prepare_scaling_rot / get_opacity
+ * (games/block_mesh_splatting/scene/block_gaussian_model.py:189-256, 106-109) and the autograd
+ * graph PyTorch builds for them.  B superquadrics, Vt icosphere vertices, F faces, K surfels per
+ * face; surfel index = (b*F + f)*K + k.  All arrays float32 device memory except faces (int32).
+ *   in : sq_r[B,4] sq_s[B,3] sq_t[B,3] sq_eps[B,2] sq_occ[B] (raw, pre-activation),
+ *        eta[B,Vt] omega[B,Vt], faces[B,F,3], alpha[B*F,K,3] (normalised barycentrics, BGM:178-186),
+ *        scale_raw[B,F*K] (BGM `_scale`), ratio (ratio_block_scene), scale_min (scale_block_min)
+ *   out: vertices[B,Vt,3], xyz[P,3], scaling[P,2] (log space, BGM `_scaling`), rotation[P,4]
+ *        (w,x,y,z, real part >= 0, BGM `_rotation`), opacity[P] = sigmoid(sq_occ) per block. */
+int pgs_sq2surfel_forward(int B, int Vt, int F, int K, const float* sq_r, const float* sq_s, const float* sq_t,
+                          const float* sq_eps, const float* sq_occ, const float* eta, const float* omega,
+                          const int* faces, const float* alpha, const float* scale_raw, float ratio, float scale_min,
+                          float* vertices, float* xyz, float* scaling, float* rotation, float* opacity, void* stream);
+size_t pgs_sq2surfel_backward_scratch_bytes(int B, int Vt);
+/* Gradients of the five block parameters (always) and of alpha / scale_raw (when non-NULL) given
+ * gradients of the forward outputs; d_opacity and d_vertices_in may be NULL. */
+int pgs_sq2surfel_backward(int B, int Vt, int F, int K, const float* sq_r, const float* sq_s, const float* sq_t,
+                           const float* sq_eps, const float* sq_occ, const float* eta, const float* omega,
+                           const int* faces, const float* alpha, const float* scale_raw, float ratio, float scale_min,
+                           const float* vertices, const float* d_xyz, const float* d_scaling, const float* d_rotation,
+                           const float* d_opacity, const float* d_vertices_in, float* d_sq_r, float* d_sq_s,
+                           float* d_sq_t, float* d_sq_eps, float* d_sq_occ, float* d_alpha, float* d_scale_raw,
+                           void* scratch, void* stream);
+
+/* ---- simple-knn ------------------------------------------------------------------
+ * Replaces distCUDA2 / SimpleKNN::knn (KNN/spatial.cu:15-25, KNN/simple_knn.cu:185-221):
+ * mean squared distance of every point to its 3 nearest neighbours (exact).
+ * points [P,3] float32 device, mean_dist2 [P] float32 device, temp >= pgs_knn_temp_bytes(P).
+ * Synchronises the stream once (bounding-box read-back). */
+size_t pgs_knn_temp_bytes(int P);
+int pgs_knn_dist2(int P, const float* points, float* mean_dist2, void* temp, void* stream);
+
 /* ---- binning stages, individually callable (parity tests compare each stage) ---- */
 /* cub::DeviceScan::InclusiveSum, rasterizer_impl.cu:278 */
 size_t pgs_scan_temp_bytes(int n);

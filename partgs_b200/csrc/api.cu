@@ -357,6 +357,87 @@ int pgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const
   return check_cuda("check_frustum");
 }
 
+static int sq_fill(SqArgs& a, int B, int Vt, int F, int K, const float* sq_r, const float* sq_s, const float* sq_t,
+                   const float* sq_eps, const float* sq_occ, const float* eta, const float* omega, const int* faces,
+                   const float* alpha, const float* scale_raw, float ratio, float scale_min) {
+  if (B <= 0 || Vt <= 0 || F <= 0 || K <= 0) return set_error(PGS_ERR_INVALID_ARG, "B, Vt, F, K must be positive");
+  if ((long long)B * F * K > 0x7fffffffLL) return set_error(PGS_ERR_UNSUPPORTED, "too many surfels");
+  if (!sq_r || !sq_s || !sq_t || !sq_eps || !sq_occ || !eta || !omega || !faces || !alpha || !scale_raw)
+    return set_error(PGS_ERR_INVALID_ARG, "null superquadric input");
+  a.B = B; a.Vt = Vt; a.F = F; a.K = K; a.sq_r = sq_r; a.sq_s = sq_s; a.sq_t = sq_t; a.sq_eps = sq_eps;
+  a.sq_occ = sq_occ; a.eta = eta; a.omega = omega; a.faces = faces; a.alpha = alpha; a.scale_raw = scale_raw;
+  a.ratio = ratio; a.scale_min = scale_min;
+  return 0;
+}
+
+int pgs_sq2surfel_forward(int B, int Vt, int F, int K, const float* sq_r, const float* sq_s, const float* sq_t,
+                          const float* sq_eps, const float* sq_occ, const float* eta, const float* omega,
+                          const int* faces, const float* alpha, const float* scale_raw, float ratio, float scale_min,
+                          float* vertices, float* xyz, float* scaling, float* rotation, float* opacity, void* stream) {
+  SqArgs a;
+  if (int e = sq_fill(a, B, Vt, F, K, sq_r, sq_s, sq_t, sq_eps, sq_occ, eta, omega, faces, alpha, scale_raw, ratio,
+                      scale_min))
+    return e;
+  if (!vertices || !xyz || !scaling || !rotation || !opacity) return set_error(PGS_ERR_INVALID_ARG, "null output");
+  cudaStream_t s = (cudaStream_t)stream;
+  {
+    StageTimer t(PGS_STAGE_SQ_FWD, s);
+    launch_sq_forward(a, vertices, xyz, scaling, rotation, opacity, s);
+  }
+  return check_cuda("sq2surfel_forward");
+}
+
+size_t pgs_sq2surfel_backward_scratch_bytes(int B, int Vt) {
+  return (size_t)(B > 0 ? B : 0) * ((size_t)(Vt > 0 ? Vt : 0) * 3 + 1) * sizeof(float) + 512;
+}
+
+int pgs_sq2surfel_backward(int B, int Vt, int F, int K, const float* sq_r, const float* sq_s, const float* sq_t,
+                           const float* sq_eps, const float* sq_occ, const float* eta, const float* omega,
+                           const int* faces, const float* alpha, const float* scale_raw, float ratio, float scale_min,
+                           const float* vertices, const float* d_xyz, const float* d_scaling, const float* d_rotation,
+                           const float* d_opacity, const float* d_vertices_in, float* d_sq_r, float* d_sq_s,
+                           float* d_sq_t, float* d_sq_eps, float* d_sq_occ, float* d_alpha, float* d_scale_raw,
+                           void* scratch, void* stream) {
+  SqArgs a;
+  if (int e = sq_fill(a, B, Vt, F, K, sq_r, sq_s, sq_t, sq_eps, sq_occ, eta, omega, faces, alpha, scale_raw, ratio,
+                      scale_min))
+    return e;
+  if (!vertices || !d_xyz || !d_scaling || !d_rotation || !d_sq_r || !d_sq_s || !d_sq_t || !d_sq_eps || !d_sq_occ ||
+      !scratch)
+    return set_error(PGS_ERR_INVALID_ARG, "null gradient pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* d_vertices = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(scratch), 256));
+  float* d_occ_acc = d_vertices + (size_t)B * Vt * 3;
+  const size_t nv = (size_t)B * Vt * 3 * sizeof(float);
+  if (d_vertices_in)
+    cudaMemcpyAsync(d_vertices, d_vertices_in, nv, cudaMemcpyDeviceToDevice, s);
+  else
+    cudaMemsetAsync(d_vertices, 0, nv, s);
+  cudaMemsetAsync(d_occ_acc, 0, (size_t)B * sizeof(float), s);
+  {
+    StageTimer t(PGS_STAGE_SQ_BWD, s);
+    launch_sq_backward(a, vertices, d_xyz, d_scaling, d_rotation, d_opacity, d_vertices, d_occ_acc, d_alpha,
+                       d_scale_raw, d_sq_r, d_sq_s, d_sq_t, d_sq_eps, d_sq_occ, s);
+  }
+  return check_cuda("sq2surfel_backward");
+}
+
+size_t pgs_knn_temp_bytes(int P) { return knn_temp_bytes(P > 0 ? P : 0) + 256; }
+int pgs_knn_dist2(int P, const float* points, float* mean_dist2, void* temp, void* stream) {
+  if (P < 0 || (P > 0 && (!points || !mean_dist2 || !temp))) return set_error(PGS_ERR_INVALID_ARG, "bad args");
+  if (P == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  void* t = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(temp), 256));
+  char msg[256] = "";
+  int rc;
+  {
+    StageTimer tm(PGS_STAGE_KNN, s);
+    rc = launch_knn_dist2(P, points, mean_dist2, t, s, msg, sizeof(msg));
+  }
+  if (rc < 0) return set_error(rc == -1 ? PGS_ERR_ALLOC : PGS_ERR_CUDA, "%s", msg);
+  return check_cuda("knn");
+}
+
 size_t pgs_scan_temp_bytes(int n) { return scan_temp_bytes(n > 0 ? n : 0) + 256; }
 int pgs_inclusive_scan_u32(const uint32_t* in, uint32_t* out, int n, void* temp, void* stream) {
   if (n < 0 || (n > 0 && (!in || !out || !temp))) return set_error(PGS_ERR_INVALID_ARG, "bad args");

@@ -116,4 +116,31 @@ struct PreprocessBwdArgs {
 };
 void launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t s);
 
+// ---- superquadric -> surfel parameterisation (games/block_mesh_splatting) ------------
+struct SqArgs {
+  int B, Vt, F, K;
+  const float* sq_r;       // [B,4] raw quaternion (w,x,y,z)
+  const float* sq_s;       // [B,3] raw log-scale
+  const float* sq_t;       // [B,3]
+  const float* sq_eps;     // [B,2] raw
+  const float* sq_occ;     // [B,1] raw
+  const float* eta;        // [B,Vt]
+  const float* omega;      // [B,Vt]
+  const int* faces;        // [B,F,3] int32
+  const float* alpha;      // [B*F,K,3] normalised barycentrics
+  const float* scale_raw;  // [B,F*K]
+  float ratio, scale_min;
+};
+void launch_sq_forward(const SqArgs& a, float* vertices, float* xyz, float* scaling, float* rotation, float* opacity,
+                       cudaStream_t s);
+void launch_sq_backward(const SqArgs& a, const float* vertices, const float* d_xyz, const float* d_scaling,
+                        const float* d_rotation, const float* d_opacity, float* d_vertices, float* d_occ_acc,
+                        float* d_alpha, float* d_scale_raw, float* d_sq_r, float* d_sq_s, float* d_sq_t,
+                        float* d_sq_eps, float* d_sq_occ, cudaStream_t s);
+
+// ---- distCUDA2 (simple-knn) ---------------------------------------------------
+size_t knn_temp_bytes(int P);
+// returns 0, or <0 with a message in err (does one stream sync for the bounding box)
+int launch_knn_dist2(int P, const float* points, float* out, void* temp, cudaStream_t s, char* err, size_t errlen);
+
 }  // namespace pgs

@@ -15,6 +15,9 @@
 // One host sync (bounding box read-back) instead of the reference's two + mallocs; all
 // scratch comes from the caller.
 #include <cfloat>
+#include <climits>
+#include <cstdio>
+#include <cstring>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -176,10 +179,9 @@ __global__ void __launch_bounds__(128) knn_search_kernel(int P, KnnGrid g, const
 }
 
 size_t knn_temp_bytes(int P) {
-  size_t cells = (size_t)KNN_MAX_RES * KNN_MAX_RES * KNN_MAX_RES;
-  size_t cap = 64;
-  while (cap < (size_t)P * 2 && cap < cells) cap *= 2;  // cells actually used <= ~8 P, see knn_dist2
-  size_t ncell = cap * 8 < cells ? cap * 8 : cells;
+  int res = 8;  // same rule as launch_knn_dist2
+  while (res < KNN_MAX_RES && (double)res * res * res < (double)P) res *= 2;
+  size_t ncell = (size_t)res * res * res;
   return 256 + align_up((size_t)P * 4, 256) + 2 * align_up(ncell * 4, 256) + align_up((size_t)P * 16, 256) +
          scan_temp_bytes((int)ncell) + 1024;
 }

@@ -228,7 +228,9 @@ def test_vs_cpu_oracle_small():
     ok, info = pu.robust_close(o["color"].cpu(), f["color"])
     assert ok, ("color", info)
     for ch in range(7):
-        ok, info = pu.robust_close(o["allmap"][ch].cpu(), f["allmap"][ch])
+        # channel 6 (distortion) is a cancellation-heavy sum (m^2 A + M2 - 2 m M1): with and without
+        # FMA contraction it agrees to ~1e-3 of its range only
+        ok, info = pu.robust_close(o["allmap"][ch].cpu(), f["allmap"][ch], atol_frac=5e-3 if ch == 6 else 1e-4)
         assert ok, (f"allmap[{ch}]", info)
     for k in ("means3D", "opacity", "scales", "rotations", "sh"):
         ok, info = pu.robust_close(o["grads"][k].cpu(), gr[k], atol_frac=1e-3, max_frac=5e-3)
