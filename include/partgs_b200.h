@@ -83,6 +83,31 @@ int pgs_dsr_backward(int P, int D, int M, int R, const float* background, int wi
                      float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh,
                      float* dL_dscale, float* dL_drot, int debug, void* stream);
 
+/* ---- `_part` rasteriser (part / semantic maps) ------------------------------------
+ * Replaces CudaRasterizer::Rasterizer::forward / backward of the fork
+ * (DSRP/cuda_rasterizer/rasterizer.h, rasterizer_impl.cu:198-350 / :352-460): same as the base
+ * pair plus `semantics` [P,S] in, `out_semantic` [S,H,W] out, an 8-channel aux map
+ * (out_others [8,H,W]) and `dL_dsemantics` [P,S] (fully written).  S = semantic_types must be
+ * <= 16 (the reference overflows a fixed 16-entry array silently; here it is an error).
+ * transMat_precomp must be NULL (that path is unusable in the reference fork). */
+int pgs_dsrp_forward(pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_alloc_fn binning_buffer,
+                     void* binning_user, pgs_alloc_fn image_buffer, void* image_user, int P, int D, int M,
+                     const float* background, int width, int height, int semantic_types, const float* means3D,
+                     const float* shs, const float* colors_precomp, const float* semantics, const float* opacities,
+                     const float* scales, float scale_modifier, const float* rotations, const float* transMat_precomp,
+                     const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                     float tan_fovy, int prefiltered, float* out_color, float* out_semantic, float* out_others,
+                     int* radii, int debug, void* stream);
+int pgs_dsrp_backward(int P, int D, int M, int R, const float* background, int width, int height, int semantic_types,
+                      const float* means3D, const float* shs, const float* colors_precomp, const float* semantics,
+                      const float* scales, float scale_modifier, const float* rotations,
+                      const float* transMat_precomp, const float* viewmatrix, const float* projmatrix,
+                      const float* campos, float tan_fovx, float tan_fovy, const int* radii, char* geom_buffer,
+                      char* binning_buffer, char* image_buffer, const float* dL_dpix, const float* dL_dsemantic_pix,
+                      const float* dL_dothers, float* dL_dmean2D, float* scratch, float* dL_dopacity, float* dL_dcolor,
+                      float* dL_dsemantics, float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh, float* dL_dscale,
+                      float* dL_drot, int debug, void* stream);
+
 /* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:24-29, rasterizer_impl.cu:141-153).
  * present: one byte per point (bool). */
 int pgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

@@ -128,3 +128,30 @@ def backward(fwd, scene, cam, bg, dL_dcolor, dL_dallmap, sh_degree=3, scale_modi
             fwd["geom"], fwd["num_rendered"], fwd["binning"], fwd["img"], False)
     names = ("means2D", "colors", "opacity", "means3D", "transMat", "sh", "scales", "rotations")
     return dict(zip(names, C.rasterize_gaussians_backward(*args)))
+
+
+# ---- `_part` fork (ref_dsrp_C) ------------------------------------------------------
+def forward_part(scene, cam, bg, sh_degree=3, scale_modifier=1.0):
+    """_C.rasterize_gaussians of the fork (DSRP/rasterize_points.cu:39-146)."""
+    C = load("ref_dsrp_C")
+    dev = scene["means3D"].device
+    e = torch.empty(0, device=dev)
+    args = (bg, scene["means3D"], e, scene["opacities"], scene["semantics"], scene["scales"], scene["rotations"],
+            scale_modifier, e, cam.viewmatrix, cam.projmatrix, cam.tanfovx, cam.tanfovy, cam.image_height,
+            cam.image_width, scene["shs"], sh_degree, cam.campos, False, False)
+    R, color, semantic, others, radii, geom, binning, img = C.rasterize_gaussians(*args)
+    return dict(num_rendered=R, color=color, semantic=semantic, allmap=others, radii=radii, geom=geom,
+                binning=binning, img=img)
+
+
+def backward_part(fwd, scene, cam, bg, dL_dcolor, dL_dsemantic, dL_dallmap, sh_degree=3, scale_modifier=1.0):
+    """_C.rasterize_gaussians_backward of the fork (DSRP/rasterize_points.cu:148-252)."""
+    C = load("ref_dsrp_C")
+    dev = scene["means3D"].device
+    e = torch.empty(0, device=dev)
+    args = (bg, scene["means3D"], fwd["radii"], e, scene["semantics"], scene["scales"], scene["rotations"],
+            scale_modifier, e, cam.viewmatrix, cam.projmatrix, cam.tanfovx, cam.tanfovy, dL_dcolor, dL_dsemantic,
+            dL_dallmap, scene["shs"], sh_degree, cam.campos, fwd["geom"], fwd["num_rendered"], fwd["binning"],
+            fwd["img"], False)
+    names = ("means2D", "colors", "semantics", "opacity", "means3D", "transMat", "sh", "scales", "rotations")
+    return dict(zip(names, C.rasterize_gaussians_backward(*args)))

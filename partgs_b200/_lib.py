@@ -43,6 +43,14 @@ SIGNATURES = {
                                    _f32p, _f32p, C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float,
                                    C.c_float, _vp, _vp, _vp, _vp, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
                                    _f32p, _f32p, _f32p, _f32p, C.c_int, _vp]),
+    "pgs_dsrp_forward": (C.c_int, [ALLOC_FN, _vp, ALLOC_FN, _vp, ALLOC_FN, _vp, C.c_int, C.c_int, C.c_int,
+                                   _f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
+                                   C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_int,
+                                   _f32p, _f32p, _f32p, _vp, C.c_int, _vp]),
+    "pgs_dsrp_backward": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, _f32p,
+                                    _f32p, _f32p, _f32p, _f32p, C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p,
+                                    C.c_float, C.c_float, _vp, _vp, _vp, _vp, _f32p, _f32p, _f32p, _f32p, _f32p,
+                                    _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _vp]),
     "pgs_mark_visible": (C.c_int, [C.c_int, _f32p, _f32p, _f32p, _vp, _vp]),
     "pgs_sq2surfel_forward": (C.c_int, [C.c_int] * 4 + [_f32p] * 7 + [_vp, _f32p, _f32p, C.c_float, C.c_float] +
                               [_f32p] * 5 + [_vp]),

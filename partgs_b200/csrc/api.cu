@@ -96,11 +96,13 @@ struct ImageState {
   float* final_T;
   uint32_t* n_contrib;
   uint2* ranges;
+  uint32_t* tile_order;
   static ImageState from(char*& p, size_t ntiles) {
     ImageState s;
     carve(p, s.final_T, 3 * ntiles * TILE_PIX);
     carve(p, s.n_contrib, 2 * ntiles * TILE_PIX);
     carve(p, s.ranges, ntiles);
+    carve(p, s.tile_order, ntiles);
     return s;
   }
 };
@@ -110,7 +112,11 @@ struct BinningState {
   uint32_t* vals_a;
   uint32_t* vals_b;
   char* sort_temp;
-  static BinningState from(char*& p, size_t R, int end_bit) {
+  // The arena is laid out for R rounded up to 512 Ki instances: the request the caller's
+  // allocator sees then takes only a handful of distinct sizes across views, so a caching
+  // allocator (torch) reuses blocks instead of growing / fragmenting every frame.
+  static BinningState from(char*& p, size_t R_exact, int end_bit) {
+    const size_t R = align_up(R_exact > 0 ? R_exact : 1, (size_t)1 << 19);
     BinningState b;
     carve(p, b.keys_a, R);
     carve(p, b.keys_b, R);
@@ -197,14 +203,26 @@ int pgs_dsr_get_layout(int P, int width, int height, int R, pgs_dsr_layout* out)
   return 0;
 }
 
-int pgs_dsr_forward(pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_alloc_fn binning_buffer,
-                    void* binning_user, pgs_alloc_fn image_buffer, void* image_user, int P, int D, int M,
-                    const float* background, int width, int height, const float* means3D, const float* shs,
-                    const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,
-                    const float* rotations, const float* transMat_precomp, const float* viewmatrix,
-                    const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered,
-                    float* out_color, float* out_others, int* radii, int debug, void* stream) {
+}  // extern "C"
+
+// Shared host sequence of both forks (part == true: diff-surfel-rasterization_part).
+static int forward_impl(bool part, int S, const float* semantics, float* out_semantic,
+                        pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_alloc_fn binning_buffer,
+                        void* binning_user, pgs_alloc_fn image_buffer, void* image_user, int P, int D, int M,
+                        const float* background, int width, int height, const float* means3D, const float* shs,
+                        const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,
+                        const float* rotations, const float* transMat_precomp, const float* viewmatrix,
+                        const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered,
+                        float* out_color, float* out_others, int* radii, int debug, void* stream) {
   (void)prefiltered;
+  if (part) {
+    if (S < 0 || S > MAX_SEMANTIC)
+      return set_error(PGS_ERR_UNSUPPORTED, "semantic channels must be in [0, %d] (got %d)", MAX_SEMANTIC, S);
+    if (S > 0 && (!semantics || !out_semantic)) return set_error(PGS_ERR_INVALID_ARG, "null semantics pointer");
+    if (transMat_precomp)
+      return set_error(PGS_ERR_UNSUPPORTED, "transMat_precomp is not usable in the _part fork (reference reads "
+                                            "scales unconditionally and leaves the normal uninitialised)");
+  }
   cudaStream_t s = (cudaStream_t)stream;
   if (P <= 0 || width <= 0 || height <= 0) return set_error(PGS_ERR_INVALID_ARG, "P, width, height must be positive");
   if (!geometry_buffer || !binning_buffer || !image_buffer) return set_error(PGS_ERR_INVALID_ARG, "null allocator");
@@ -238,7 +256,12 @@ int pgs_dsr_forward(pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_alloc
   pa.colors_precomp = colors_precomp; pa.viewmatrix = viewmatrix; pa.projmatrix = projmatrix; pa.cam_pos = cam_pos;
   pa.W = width; pa.H = height; pa.grid_x = gx; pa.grid_y = gy;
   pa.radii = radii; pa.rec = geom.rec; pa.bbox = geom.bbox; pa.tiles_touched = geom.tiles_touched;
-  { StageTimer t(PGS_STAGE_PREPROCESS_FWD, s); launch_preprocess_fwd(pa, s); }
+  pa.focal_y = height / (2.0f * tan_fovy);
+  pa.focal_x = width / (2.0f * tan_fovx);
+  {
+    StageTimer t(PGS_STAGE_PREPROCESS_FWD, s);
+    if (part) launch_preprocess_fwd_part(pa, s); else launch_preprocess_fwd(pa, s);
+  }
   if (int e = check_cuda("preprocess_fwd")) return e;
   if (debug) if (int e = check_sync(s, "preprocess_fwd")) return e;
 
@@ -276,27 +299,73 @@ int pgs_dsr_forward(pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_alloc
     if (debug) if (int e = check_sync(s, "binning")) return e;
   }
 
+  launch_tile_order(img.ranges, (int)ntiles, img.tile_order, s);
+  if (int e = check_cuda("tile_order")) return e;
+
   RenderFwdArgs ra;
-  ra.ranges = img.ranges; ra.point_list = point_list; ra.W = width; ra.H = height; ra.grid_x = gx; ra.grid_y = gy;
+  ra.ranges = img.ranges; ra.tile_order = img.tile_order; ra.point_list = point_list; ra.W = width; ra.H = height; ra.grid_x = gx; ra.grid_y = gy;
   ra.rec = geom.rec; ra.bbox = geom.bbox; ra.bg_color = background;
   ra.final_T = img.final_T; ra.n_contrib = img.n_contrib; ra.out_color = out_color; ra.out_others = out_others;
-  { StageTimer t(PGS_STAGE_RENDER_FWD, s); launch_render_fwd(ra, s); }
+  ra.S = S; ra.semantics = semantics; ra.out_semantic = out_semantic;
+  {
+    StageTimer t(PGS_STAGE_RENDER_FWD, s);
+    if (part) launch_render_fwd_part(ra, s); else launch_render_fwd(ra, s);
+  }
   if (int e = check_cuda("render_fwd")) return e;
   if (debug) if (int e = check_sync(s, "render_fwd")) return e;
   return num_rendered;
 }
 
+extern "C" {
+
+int pgs_dsr_forward(pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_alloc_fn binning_buffer,
+                    void* binning_user, pgs_alloc_fn image_buffer, void* image_user, int P, int D, int M,
+                    const float* background, int width, int height, const float* means3D, const float* shs,
+                    const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,
+                    const float* rotations, const float* transMat_precomp, const float* viewmatrix,
+                    const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered,
+                    float* out_color, float* out_others, int* radii, int debug, void* stream) {
+  return forward_impl(false, 0, nullptr, nullptr, geometry_buffer, geometry_user, binning_buffer, binning_user,
+                      image_buffer, image_user, P, D, M, background, width, height, means3D, shs, colors_precomp,
+                      opacities, scales, scale_modifier, rotations, transMat_precomp, viewmatrix, projmatrix, cam_pos,
+                      tan_fovx, tan_fovy, prefiltered, out_color, out_others, radii, debug, stream);
+}
+
+int pgs_dsrp_forward(pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_alloc_fn binning_buffer,
+                     void* binning_user, pgs_alloc_fn image_buffer, void* image_user, int P, int D, int M,
+                     const float* background, int width, int height, int semantic_types, const float* means3D,
+                     const float* shs, const float* colors_precomp, const float* semantics, const float* opacities,
+                     const float* scales, float scale_modifier, const float* rotations, const float* transMat_precomp,
+                     const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                     float tan_fovy, int prefiltered, float* out_color, float* out_semantic, float* out_others,
+                     int* radii, int debug, void* stream) {
+  return forward_impl(true, semantic_types, semantics, out_semantic, geometry_buffer, geometry_user, binning_buffer,
+                      binning_user, image_buffer, image_user, P, D, M, background, width, height, means3D, shs,
+                      colors_precomp, opacities, scales, scale_modifier, rotations, transMat_precomp, viewmatrix,
+                      projmatrix, cam_pos, tan_fovx, tan_fovy, prefiltered, out_color, out_others, radii, debug, stream);
+}
+
 size_t pgs_dsr_backward_scratch_bytes(int P) { return (size_t)(P > 0 ? P : 0) * GRAD_FLOATS * sizeof(float) + 256; }
 
-int pgs_dsr_backward(int P, int D, int M, int R, const float* background, int width, int height,
-                     const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
-                     float scale_modifier, const float* rotations, const float* transMat_precomp,
-                     const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
-                     float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
-                     const float* dL_dpix, const float* dL_dothers, float* dL_dmean2D, float* scratch,
-                     float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh,
-                     float* dL_dscale, float* dL_drot, int debug, void* stream) {
+}  // extern "C"
+
+static int backward_impl(bool part, int S, const float* semantics, const float* dL_dsemantic_pix, float* dL_dsemantics,
+                         int P, int D, int M, int R, const float* background, int width, int height,
+                         const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
+                         float scale_modifier, const float* rotations, const float* transMat_precomp,
+                         const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
+                         float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                         const float* dL_dpix, const float* dL_dothers, float* dL_dmean2D, float* scratch,
+                         float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh,
+                         float* dL_dscale, float* dL_drot, int debug, void* stream) {
   (void)colors_precomp;
+  if (part) {
+    if (S < 0 || S > MAX_SEMANTIC)
+      return set_error(PGS_ERR_UNSUPPORTED, "semantic channels must be in [0, %d] (got %d)", MAX_SEMANTIC, S);
+    if (S > 0 && (!semantics || !dL_dsemantic_pix || !dL_dsemantics))
+      return set_error(PGS_ERR_INVALID_ARG, "null semantics pointer");
+    if (transMat_precomp) return set_error(PGS_ERR_UNSUPPORTED, "transMat_precomp is not usable in the _part fork");
+  }
   cudaStream_t s = (cudaStream_t)stream;
   if (P <= 0 || width <= 0 || height <= 0 || R < 0) return set_error(PGS_ERR_INVALID_ARG, "bad sizes");
   if (!geom_buffer || !image_buffer || (R > 0 && !binning_buffer))
@@ -328,10 +397,15 @@ int pgs_dsr_backward(int P, int D, int M, int R, const float* background, int wi
   const float focal_x = width / (2.0f * tan_fovx);
 
   RenderBwdArgs rb;
-  rb.ranges = img.ranges; rb.point_list = point_list; rb.W = width; rb.H = height; rb.grid_x = gx; rb.grid_y = gy;
+  rb.ranges = img.ranges; rb.tile_order = img.tile_order; rb.point_list = point_list; rb.W = width; rb.H = height; rb.grid_x = gx; rb.grid_y = gy;
   rb.rec = geom.rec; rb.bbox = geom.bbox; rb.bg_color = background; rb.final_T = img.final_T;
   rb.n_contrib = img.n_contrib; rb.dL_dpixels = dL_dpix; rb.dL_dothers = dL_dothers; rb.grad = grad;
-  { StageTimer t(PGS_STAGE_RENDER_BWD, s); launch_render_bwd(rb, s); }
+  rb.S = S; rb.semantics = semantics; rb.dL_dsemantic = dL_dsemantic_pix; rb.grad_semantics = dL_dsemantics;
+  if (part && S > 0) cudaMemsetAsync(dL_dsemantics, 0, (size_t)P * S * sizeof(float), s);
+  {
+    StageTimer t(PGS_STAGE_RENDER_BWD, s);
+    if (part) launch_render_bwd_part(rb, s); else launch_render_bwd(rb, s);
+  }
   if (int e = check_cuda("render_bwd")) return e;
   if (debug) if (int e = check_sync(s, "render_bwd")) return e;
 
@@ -343,10 +417,46 @@ int pgs_dsr_backward(int P, int D, int M, int R, const float* background, int wi
   pb.rec = geom.rec; pb.grad = grad;
   pb.dL_dmean2D = dL_dmean2D; pb.dL_dcolors = dL_dcolor; pb.dL_dopacity = dL_dopacity; pb.dL_dmean3D = dL_dmean3D;
   pb.dL_dtransMat = dL_dtransMat; pb.dL_dsh = dL_dsh; pb.dL_dscales = dL_dscale; pb.dL_drots = dL_drot;
-  { StageTimer t(PGS_STAGE_PREPROCESS_BWD, s); launch_preprocess_bwd(pb, s); }
+  {
+    StageTimer t(PGS_STAGE_PREPROCESS_BWD, s);
+    if (part) launch_preprocess_bwd_part(pb, s); else launch_preprocess_bwd(pb, s);
+  }
   if (int e = check_cuda("preprocess_bwd")) return e;
   if (debug) if (int e = check_sync(s, "preprocess_bwd")) return e;
   return 0;
+}
+
+extern "C" {
+
+int pgs_dsr_backward(int P, int D, int M, int R, const float* background, int width, int height,
+                     const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
+                     float scale_modifier, const float* rotations, const float* transMat_precomp,
+                     const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
+                     float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                     const float* dL_dpix, const float* dL_dothers, float* dL_dmean2D, float* scratch,
+                     float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh,
+                     float* dL_dscale, float* dL_drot, int debug, void* stream) {
+  return backward_impl(false, 0, nullptr, nullptr, nullptr, P, D, M, R, background, width, height, means3D, shs,
+                       colors_precomp, scales, scale_modifier, rotations, transMat_precomp, viewmatrix, projmatrix,
+                       campos, tan_fovx, tan_fovy, radii, geom_buffer, binning_buffer, image_buffer, dL_dpix,
+                       dL_dothers, dL_dmean2D, scratch, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dtransMat, dL_dsh,
+                       dL_dscale, dL_drot, debug, stream);
+}
+
+int pgs_dsrp_backward(int P, int D, int M, int R, const float* background, int width, int height, int semantic_types,
+                      const float* means3D, const float* shs, const float* colors_precomp, const float* semantics,
+                      const float* scales, float scale_modifier, const float* rotations,
+                      const float* transMat_precomp, const float* viewmatrix, const float* projmatrix,
+                      const float* campos, float tan_fovx, float tan_fovy, const int* radii, char* geom_buffer,
+                      char* binning_buffer, char* image_buffer, const float* dL_dpix, const float* dL_dsemantic_pix,
+                      const float* dL_dothers, float* dL_dmean2D, float* scratch, float* dL_dopacity, float* dL_dcolor,
+                      float* dL_dsemantics, float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh, float* dL_dscale,
+                      float* dL_drot, int debug, void* stream) {
+  return backward_impl(true, semantic_types, semantics, dL_dsemantic_pix, dL_dsemantics, P, D, M, R, background,
+                       width, height, means3D, shs, colors_precomp, scales, scale_modifier, rotations,
+                       transMat_precomp, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, radii, geom_buffer,
+                       binning_buffer, image_buffer, dL_dpix, dL_dothers, dL_dmean2D, scratch, dL_dopacity, dL_dcolor,
+                       dL_dmean3D, dL_dtransMat, dL_dsh, dL_dscale, dL_drot, debug, stream);
 }
 
 int pgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

@@ -1,0 +1,64 @@
+// Per-fragment (pixel x surfel) arithmetic shared by the four render kernels, with every
+// rounding step pinned.
+//
+// The reference writes this math as plain C (cuda_rasterizer/forward.cu:344-387,
+// backward.cu:282-313 and the `_part` twins) and lets nvcc/ptxas contract a*b+c into FMAs.
+// Which products get fused decides single bits of rho/alpha, and a fragment sitting on the
+// `alpha < 1/255` or `T(1-alpha) < 1e-4` threshold then flips between blended and skipped.
+// To stay bit-identical to the reference build *independently of how the surrounding kernel
+// is restructured*, the contraction pattern observed in the reference SASS (sm_100a, nvcc
+// 12.9) is written out here with explicit __fmaf_rn / __fmul_rn / __fadd_rn:
+//   k.c   = fma(px, Tw.c, -Tu.c)                 l.c = fma(py, Tw.c, -Tv.c)
+//   p     = k x l with  a*b - c*d -> fma(a, b, -(c*d))
+//   s     = p.xy / p.z (IEEE division)
+//   rho3d = fma(s.x, s.x, s.y*s.y)
+//   rho2d = 2 * fma(d.y, d.y, d.x*d.x)                        (base fork)
+//         = float(double(fma(d.x, d.x, d.y*d.y)) * (1/0.7071067811865476^2))   (`_part` fork)
+//   depth = Tw.z + fma(Tw.x, s.x, Tw.y*s.y)   when rho3d <= rho2d, else Tw.z
+// Forward and backward use the same routine, so the backward replay takes exactly the
+// forward's decisions.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pgs {
+
+struct FragGeom {
+  float3 k, l, p;
+  float2 s, d;
+  float rho3d, rho2d, depth;
+};
+
+// Returns false when the two pixel planes do not intersect the splat plane in a point
+// (p.z == 0; the reference `continue`s).
+template <bool PART>
+__device__ __forceinline__ bool frag_geometry(const float2 pixf, const float3 Tu, const float3 Tv, const float3 Tw,
+                                              const float2 xy, FragGeom& f) {
+  f.k = make_float3(__fmaf_rn(pixf.x, Tw.x, -Tu.x), __fmaf_rn(pixf.x, Tw.y, -Tu.y), __fmaf_rn(pixf.x, Tw.z, -Tu.z));
+  f.l = make_float3(__fmaf_rn(pixf.y, Tw.x, -Tv.x), __fmaf_rn(pixf.y, Tw.y, -Tv.y), __fmaf_rn(pixf.y, Tw.z, -Tv.z));
+  f.p.x = __fmaf_rn(f.k.y, f.l.z, -__fmul_rn(f.k.z, f.l.y));
+  f.p.y = __fmaf_rn(f.k.z, f.l.x, -__fmul_rn(f.k.x, f.l.z));
+  f.p.z = __fmaf_rn(f.k.x, f.l.y, -__fmul_rn(f.k.y, f.l.x));
+  if (f.p.z == 0.0f) return false;
+  f.s = make_float2(__fdiv_rn(f.p.x, f.p.z), __fdiv_rn(f.p.y, f.p.z));
+  f.rho3d = __fmaf_rn(f.s.x, f.s.x, __fmul_rn(f.s.y, f.s.y));
+  f.d = make_float2(__fsub_rn(xy.x, pixf.x), __fsub_rn(xy.y, pixf.y));
+  if (PART) {
+    const float dd = __fmaf_rn(f.d.x, f.d.x, __fmul_rn(f.d.y, f.d.y));
+    f.rho2d = (float)((double)dd * (1 / (0.7071067811865476 * 0.7071067811865476)));
+  } else {
+    const float dd = __fmaf_rn(f.d.y, f.d.y, __fmul_rn(f.d.x, f.d.x));
+    f.rho2d = __fadd_rn(dd, dd);  // FilterInvSquare = 2
+  }
+  f.depth = (f.rho3d <= f.rho2d) ? __fadd_rn(Tw.z, __fmaf_rn(Tw.x, f.s.x, __fmul_rn(Tw.y, f.s.y))) : Tw.z;
+  return true;
+}
+
+// alpha of a fragment: min(0.99, opacity * exp(-rho/2)).  `G` returns the Gaussian weight.
+__device__ __forceinline__ float frag_alpha(float rho3d, float rho2d, float opa, float& power, float& G) {
+  const float rho = fminf(rho3d, rho2d);
+  power = __fmul_rn(-0.5f, rho);
+  G = expf(power);
+  return fminf(0.99f, __fmul_rn(opa, G));
+}
+
+}  // namespace pgs

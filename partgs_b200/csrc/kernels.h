@@ -23,6 +23,7 @@ struct PreprocessFwdArgs {
   const float* cam_pos;
   int W, H;
   int grid_x, grid_y;
+  float focal_x, focal_y;  // `_part` fork only
   // outputs
   int* radii;
   float4* rec;    // [P][REC_QUADS]
@@ -30,6 +31,7 @@ struct PreprocessFwdArgs {
   uint32_t* tiles_touched;
 };
 void launch_preprocess_fwd(const PreprocessFwdArgs& a, cudaStream_t s);
+void launch_preprocess_fwd_part(const PreprocessFwdArgs& a, cudaStream_t s);
 void launch_check_frustum(int P, const float* means3D, const float* viewmatrix, unsigned char* present,
                           cudaStream_t s);
 
@@ -57,8 +59,12 @@ int launch_radix_sort_pairs32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys
 void launch_identify_tile_ranges(int L, const uint64_t* keys, uint2* ranges, cudaStream_t s);
 
 // ---- render -----------------------------------------------------------------
+// tile ids sorted longest-list-first (launch order of the render kernels)
+void launch_tile_order(const uint2* ranges, int ntiles, uint32_t* order, cudaStream_t s);
+
 struct RenderFwdArgs {
   const uint2* ranges;
+  const uint32_t* tile_order;  // [ntiles] or nullptr (identity)
   const uint32_t* point_list;
   int W, H;
   int grid_x, grid_y;
@@ -69,12 +75,19 @@ struct RenderFwdArgs {
   float* final_T;     // [3][ntile*256]: T, M1, M2
   uint32_t* n_contrib;  // [2][ntile*256]: last, median
   float* out_color;   // [3][H][W]
-  float* out_others;  // [7][H][W]
+  float* out_others;  // [7][H][W] (base) / [8][H][W] (`_part`)
+  // `_part` fork only
+  int S;                   // semantic channels (<= MAX_SEMANTIC)
+  const float* semantics;  // [P][S]
+  float* out_semantic;     // [S][H][W]
 };
+constexpr int MAX_SEMANTIC = 16;  // DSRP/cuda_rasterizer/forward.cu:317 (fixed register array in the reference)
 void launch_render_fwd(const RenderFwdArgs& a, cudaStream_t s);
+void launch_render_fwd_part(const RenderFwdArgs& a, cudaStream_t s);
 
 struct RenderBwdArgs {
   const uint2* ranges;
+  const uint32_t* tile_order;  // [ntiles] or nullptr (identity)
   const uint32_t* point_list;
   int W, H;
   int grid_x, grid_y;
@@ -86,8 +99,14 @@ struct RenderBwdArgs {
   const float* dL_dpixels;  // [3][H][W]
   const float* dL_dothers;  // [7][H][W]
   float* grad;              // [P][GRAD_FLOATS], zeroed
+  // `_part` fork only
+  int S;
+  const float* semantics;       // [P][S]
+  const float* dL_dsemantic;    // [S][H][W]
+  float* grad_semantics;        // [P][S], zeroed
 };
 void launch_render_bwd(const RenderBwdArgs& a, cudaStream_t s);
+void launch_render_bwd_part(const RenderBwdArgs& a, cudaStream_t s);
 
 struct PreprocessBwdArgs {
   int P, D, M;
@@ -115,6 +134,7 @@ struct PreprocessBwdArgs {
   float* dL_drots;      // [P][4]
 };
 void launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t s);
+void launch_preprocess_bwd_part(const PreprocessBwdArgs& a, cudaStream_t s);
 
 // ---- superquadric -> surfel parameterisation (games/block_mesh_splatting) ------------
 struct SqArgs {

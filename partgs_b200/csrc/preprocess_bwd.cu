@@ -60,6 +60,88 @@ __device__ __forceinline__ v4 quat_to_rotmat_vjp(const v4 quat, const m3 v_R) {
   return v_quat;
 }
 
+// SH -> RGB backward (reference backward.cu:20-139): writes dL/dsh[M] and returns the mean3D
+// gradient that flows through the view direction.
+__device__ __forceinline__ v3 sh_backward(int idx, int deg, int M, const v3* means, v3 campos, const float* shs,
+                                          unsigned clamped, v3 dL_dcolor, v3* dL_dsh_out) {
+  v3 pos = means[idx];
+  v3 dir_orig = pos - campos;
+  v3 dir = dir_orig / length(dir_orig);
+  const v3* sh = ((const v3*)shs) + (size_t)idx * M;
+
+  v3 dL_dRGB = dL_dcolor;
+  dL_dRGB.x *= (clamped & 1u) ? 0 : 1;
+  dL_dRGB.y *= (clamped & 2u) ? 0 : 1;
+  dL_dRGB.z *= (clamped & 4u) ? 0 : 1;
+
+  v3 dRGBdx(0, 0, 0), dRGBdy(0, 0, 0), dRGBdz(0, 0, 0);
+  float x = dir.x, y = dir.y, z = dir.z;
+  v3* dL_dsh = dL_dsh_out;
+  for (int i = 0; i < M; i++) dL_dsh[i] = v3(0.f, 0.f, 0.f);
+
+  float dRGBdsh0 = bSH_C0;
+  dL_dsh[0] = dRGBdsh0 * dL_dRGB;
+  if (deg > 0) {
+    float dRGBdsh1 = -bSH_C1 * y;
+    float dRGBdsh2 = bSH_C1 * z;
+    float dRGBdsh3 = -bSH_C1 * x;
+    dL_dsh[1] = dRGBdsh1 * dL_dRGB;
+    dL_dsh[2] = dRGBdsh2 * dL_dRGB;
+    dL_dsh[3] = dRGBdsh3 * dL_dRGB;
+    dRGBdx = -bSH_C1 * sh[3];
+    dRGBdy = -bSH_C1 * sh[1];
+    dRGBdz = bSH_C1 * sh[2];
+    if (deg > 1) {
+      float xx = x * x, yy = y * y, zz = z * z;
+      float xy = x * y, yz = y * z, xz = x * z;
+      float dRGBdsh4 = bSH_C2[0] * xy;
+      float dRGBdsh5 = bSH_C2[1] * yz;
+      float dRGBdsh6 = bSH_C2[2] * (2.f * zz - xx - yy);
+      float dRGBdsh7 = bSH_C2[3] * xz;
+      float dRGBdsh8 = bSH_C2[4] * (xx - yy);
+      dL_dsh[4] = dRGBdsh4 * dL_dRGB;
+      dL_dsh[5] = dRGBdsh5 * dL_dRGB;
+      dL_dsh[6] = dRGBdsh6 * dL_dRGB;
+      dL_dsh[7] = dRGBdsh7 * dL_dRGB;
+      dL_dsh[8] = dRGBdsh8 * dL_dRGB;
+      dRGBdx += bSH_C2[0] * y * sh[4] + bSH_C2[2] * 2.f * -x * sh[6] + bSH_C2[3] * z * sh[7] +
+                bSH_C2[4] * 2.f * x * sh[8];
+      dRGBdy += bSH_C2[0] * x * sh[4] + bSH_C2[1] * z * sh[5] + bSH_C2[2] * 2.f * -y * sh[6] +
+                bSH_C2[4] * 2.f * -y * sh[8];
+      dRGBdz += bSH_C2[1] * y * sh[5] + bSH_C2[2] * 2.f * 2.f * z * sh[6] + bSH_C2[3] * x * sh[7];
+      if (deg > 2) {
+        float dRGBdsh9 = bSH_C3[0] * y * (3.f * xx - yy);
+        float dRGBdsh10 = bSH_C3[1] * xy * z;
+        float dRGBdsh11 = bSH_C3[2] * y * (4.f * zz - xx - yy);
+        float dRGBdsh12 = bSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+        float dRGBdsh13 = bSH_C3[4] * x * (4.f * zz - xx - yy);
+        float dRGBdsh14 = bSH_C3[5] * z * (xx - yy);
+        float dRGBdsh15 = bSH_C3[6] * x * (xx - 3.f * yy);
+        dL_dsh[9] = dRGBdsh9 * dL_dRGB;
+        dL_dsh[10] = dRGBdsh10 * dL_dRGB;
+        dL_dsh[11] = dRGBdsh11 * dL_dRGB;
+        dL_dsh[12] = dRGBdsh12 * dL_dRGB;
+        dL_dsh[13] = dRGBdsh13 * dL_dRGB;
+        dL_dsh[14] = dRGBdsh14 * dL_dRGB;
+        dL_dsh[15] = dRGBdsh15 * dL_dRGB;
+        dRGBdx += (bSH_C3[0] * sh[9] * 3.f * 2.f * xy + bSH_C3[1] * sh[10] * yz + bSH_C3[2] * sh[11] * -2.f * xy +
+                   bSH_C3[3] * sh[12] * -3.f * 2.f * xz + bSH_C3[4] * sh[13] * (-3.f * xx + 4.f * zz - yy) +
+                   bSH_C3[5] * sh[14] * 2.f * xz + bSH_C3[6] * sh[15] * 3.f * (xx - yy));
+        dRGBdy += (bSH_C3[0] * sh[9] * 3.f * (xx - yy) + bSH_C3[1] * sh[10] * xz +
+                   bSH_C3[2] * sh[11] * (-3.f * yy + 4.f * zz - xx) + bSH_C3[3] * sh[12] * -3.f * 2.f * yz +
+                   bSH_C3[4] * sh[13] * -2.f * xy + bSH_C3[5] * sh[14] * -2.f * yz +
+                   bSH_C3[6] * sh[15] * -3.f * 2.f * xy);
+        dRGBdz += (bSH_C3[1] * sh[10] * xy + bSH_C3[2] * sh[11] * 4.f * 2.f * yz +
+                   bSH_C3[3] * sh[12] * 3.f * (2.f * zz - xx - yy) + bSH_C3[4] * sh[13] * 4.f * 2.f * xz +
+                   bSH_C3[5] * sh[14] * (xx - yy));
+      }
+    }
+  }
+  v3 dL_ddir(dot(dRGBdx, dL_dRGB), dot(dRGBdy, dL_dRGB), dot(dRGBdz, dL_dRGB));
+  float3 dL_dmean = dnormvdv3(float3{dir_orig.x, dir_orig.y, dir_orig.z}, float3{dL_ddir.x, dL_ddir.y, dL_ddir.z});
+  return v3(dL_dmean.x, dL_dmean.y, dL_dmean.z);
+}
+
 __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.P) return;
@@ -209,86 +291,8 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
 
   // SH backward (backward.cu:20-139), incl. view-direction -> mean3D path
   if (a.shs) {
-    const int deg = a.D;
-    const unsigned clamped = __float_as_uint(q4.w);
-    const v3* means = (const v3*)a.means3D;
-    v3 pos = means[idx];
-    v3 campos = *(const v3*)a.cam_pos;
-    v3 dir_orig = pos - campos;
-    v3 dir = dir_orig / length(dir_orig);
-    const v3* sh = ((const v3*)a.shs) + (size_t)idx * M;
-
-    v3 dL_dRGB = dL_dcolor;
-    dL_dRGB.x *= (clamped & 1u) ? 0 : 1;
-    dL_dRGB.y *= (clamped & 2u) ? 0 : 1;
-    dL_dRGB.z *= (clamped & 4u) ? 0 : 1;
-
-    v3 dRGBdx(0, 0, 0), dRGBdy(0, 0, 0), dRGBdz(0, 0, 0);
-    float x = dir.x, y = dir.y, z = dir.z;
-    v3* dL_dsh = (v3*)o_sh;
-    for (int i = 0; i < M; i++) dL_dsh[i] = v3(0.f, 0.f, 0.f);
-
-    float dRGBdsh0 = bSH_C0;
-    dL_dsh[0] = dRGBdsh0 * dL_dRGB;
-    if (deg > 0) {
-      float dRGBdsh1 = -bSH_C1 * y;
-      float dRGBdsh2 = bSH_C1 * z;
-      float dRGBdsh3 = -bSH_C1 * x;
-      dL_dsh[1] = dRGBdsh1 * dL_dRGB;
-      dL_dsh[2] = dRGBdsh2 * dL_dRGB;
-      dL_dsh[3] = dRGBdsh3 * dL_dRGB;
-      dRGBdx = -bSH_C1 * sh[3];
-      dRGBdy = -bSH_C1 * sh[1];
-      dRGBdz = bSH_C1 * sh[2];
-      if (deg > 1) {
-        float xx = x * x, yy = y * y, zz = z * z;
-        float xy = x * y, yz = y * z, xz = x * z;
-        float dRGBdsh4 = bSH_C2[0] * xy;
-        float dRGBdsh5 = bSH_C2[1] * yz;
-        float dRGBdsh6 = bSH_C2[2] * (2.f * zz - xx - yy);
-        float dRGBdsh7 = bSH_C2[3] * xz;
-        float dRGBdsh8 = bSH_C2[4] * (xx - yy);
-        dL_dsh[4] = dRGBdsh4 * dL_dRGB;
-        dL_dsh[5] = dRGBdsh5 * dL_dRGB;
-        dL_dsh[6] = dRGBdsh6 * dL_dRGB;
-        dL_dsh[7] = dRGBdsh7 * dL_dRGB;
-        dL_dsh[8] = dRGBdsh8 * dL_dRGB;
-        dRGBdx += bSH_C2[0] * y * sh[4] + bSH_C2[2] * 2.f * -x * sh[6] + bSH_C2[3] * z * sh[7] +
-                  bSH_C2[4] * 2.f * x * sh[8];
-        dRGBdy += bSH_C2[0] * x * sh[4] + bSH_C2[1] * z * sh[5] + bSH_C2[2] * 2.f * -y * sh[6] +
-                  bSH_C2[4] * 2.f * -y * sh[8];
-        dRGBdz += bSH_C2[1] * y * sh[5] + bSH_C2[2] * 2.f * 2.f * z * sh[6] + bSH_C2[3] * x * sh[7];
-        if (deg > 2) {
-          float dRGBdsh9 = bSH_C3[0] * y * (3.f * xx - yy);
-          float dRGBdsh10 = bSH_C3[1] * xy * z;
-          float dRGBdsh11 = bSH_C3[2] * y * (4.f * zz - xx - yy);
-          float dRGBdsh12 = bSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
-          float dRGBdsh13 = bSH_C3[4] * x * (4.f * zz - xx - yy);
-          float dRGBdsh14 = bSH_C3[5] * z * (xx - yy);
-          float dRGBdsh15 = bSH_C3[6] * x * (xx - 3.f * yy);
-          dL_dsh[9] = dRGBdsh9 * dL_dRGB;
-          dL_dsh[10] = dRGBdsh10 * dL_dRGB;
-          dL_dsh[11] = dRGBdsh11 * dL_dRGB;
-          dL_dsh[12] = dRGBdsh12 * dL_dRGB;
-          dL_dsh[13] = dRGBdsh13 * dL_dRGB;
-          dL_dsh[14] = dRGBdsh14 * dL_dRGB;
-          dL_dsh[15] = dRGBdsh15 * dL_dRGB;
-          dRGBdx += (bSH_C3[0] * sh[9] * 3.f * 2.f * xy + bSH_C3[1] * sh[10] * yz + bSH_C3[2] * sh[11] * -2.f * xy +
-                     bSH_C3[3] * sh[12] * -3.f * 2.f * xz + bSH_C3[4] * sh[13] * (-3.f * xx + 4.f * zz - yy) +
-                     bSH_C3[5] * sh[14] * 2.f * xz + bSH_C3[6] * sh[15] * 3.f * (xx - yy));
-          dRGBdy += (bSH_C3[0] * sh[9] * 3.f * (xx - yy) + bSH_C3[1] * sh[10] * xz +
-                     bSH_C3[2] * sh[11] * (-3.f * yy + 4.f * zz - xx) + bSH_C3[3] * sh[12] * -3.f * 2.f * yz +
-                     bSH_C3[4] * sh[13] * -2.f * xy + bSH_C3[5] * sh[14] * -2.f * yz +
-                     bSH_C3[6] * sh[15] * -3.f * 2.f * xy);
-          dRGBdz += (bSH_C3[1] * sh[10] * xy + bSH_C3[2] * sh[11] * 4.f * 2.f * yz +
-                     bSH_C3[3] * sh[12] * 3.f * (2.f * zz - xx - yy) + bSH_C3[4] * sh[13] * 4.f * 2.f * xz +
-                     bSH_C3[5] * sh[14] * (xx - yy));
-        }
-      }
-    }
-    v3 dL_ddir(dot(dRGBdx, dL_dRGB), dot(dRGBdy, dL_dRGB), dot(dRGBdz, dL_dRGB));
-    float3 dL_dmean = dnormvdv3(float3{dir_orig.x, dir_orig.y, dir_orig.z}, float3{dL_ddir.x, dL_ddir.y, dL_ddir.z});
-    dmean += v3(dL_dmean.x, dL_dmean.y, dL_dmean.z);
+    dmean += sh_backward(idx, a.D, M, (const v3*)a.means3D, *(const v3*)a.cam_pos, a.shs, __float_as_uint(q4.w),
+                         dL_dcolor, (v3*)o_sh);
   } else if (o_sh) {
     for (int i = 0; i < M * 3; i++) o_sh[i] = 0.f;
   }
@@ -299,6 +303,134 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
   o_m2d[0] = hack_x;
   o_m2d[1] = hack_y;
   o_m2d[2] = 0.f;
+}
+
+// =============================================================================
+// `_part` fork: computeAABB backward (DSRP/cuda_rasterizer/backward.cu:621-671) fused with
+// preprocessCUDA backward (:555-619) and the computeTransMat VJP (:473-551).  Quirks kept:
+// the AABB-centre term is always added (no dL_dmean2D != 0 test), dL_dtransMat returned to
+// the caller includes it, mean2D hack = dL_dT[2|5] * z * {fx*tanx | fy*tany}.
+// =============================================================================
+__global__ void __launch_bounds__(256) preprocess_bwd_part_kernel(PreprocessBwdArgs a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.P) return;
+  const int M = a.M;
+  float* o_m2d = a.dL_dmean2D + (size_t)idx * 3;
+  float* o_col = a.dL_dcolors + (size_t)idx * 3;
+  float* o_m3d = a.dL_dmean3D + (size_t)idx * 3;
+  float* o_T = a.dL_dtransMat + (size_t)idx * 9;
+  float* o_sh = a.dL_dsh ? a.dL_dsh + (size_t)idx * M * 3 : nullptr;
+  if (!(a.radii[idx] > 0)) {
+    o_m2d[0] = o_m2d[1] = o_m2d[2] = 0.f;
+    o_col[0] = o_col[1] = o_col[2] = 0.f;
+    a.dL_dopacity[idx] = 0.f;
+    o_m3d[0] = o_m3d[1] = o_m3d[2] = 0.f;
+    for (int i = 0; i < 9; i++) o_T[i] = 0.f;
+    if (o_sh)
+      for (int i = 0; i < M * 3; i++) o_sh[i] = 0.f;
+    a.dL_dscales[idx * 2] = 0.f; a.dL_dscales[idx * 2 + 1] = 0.f;
+    for (int i = 0; i < 4; i++) a.dL_drots[idx * 4 + i] = 0.f;
+    return;
+  }
+  const float4* gq = reinterpret_cast<const float4*>(a.grad + (size_t)idx * GRAD_FLOATS);
+  const float4 g0 = gq[0], g1 = gq[1], g2 = gq[2], g3 = gq[3], g4 = gq[4];
+  float gT[9] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x};
+  const float3 dL_dmean2D = {g2.y, g2.z, 0.f};
+  const float g_opacity = g2.w;
+  const float dL_dnormal3D[3] = {g3.x, g3.y, g3.z};
+  v3 dL_dcolor = v3(g4.x, g4.y, g4.z);
+
+  const float4* rec = a.rec + (size_t)idx * REC_QUADS;
+  const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q4 = rec[4];
+
+  // ---- computeAABB backward ----
+  {
+    m4x3 T;
+    T[0] = v3(q0.x, q0.y, q0.z); T[1] = v3(q1.x, q1.y, q1.z); T[2] = v3(q2.x, q2.y, q2.z); T[3] = T[2];
+    float d = dot(v3(1.0f, 1.0f, -1.0f), T[3] * T[3]);
+    v3 f = v3(1.0f, 1.0f, -1.0f) * (1.0f / d);
+    v3 dL_dT0 = dL_dmean2D.x * f * T[3];
+    v3 dL_dT1 = dL_dmean2D.y * f * T[3];
+    v3 dL_dT3 = dL_dmean2D.x * f * T[0] + dL_dmean2D.y * f * T[1];
+    v3 dL_df = (dL_dmean2D.x * T[0] * T[3]) + (dL_dmean2D.y * T[1] * T[3]);
+    float dL_dd = dot(dL_df, f) * (-1.0 / d);
+    v3 dd_dT3 = v3(1.0f, 1.0f, -1.0f) * T[3] * 2.0f;
+    dL_dT3 += dL_dd * dd_dT3;
+    gT[0] += dL_dT0.x; gT[1] += dL_dT0.y; gT[2] += dL_dT0.z;
+    gT[3] += dL_dT1.x; gT[4] += dL_dT1.y; gT[5] += dL_dT1.z;
+    gT[6] += dL_dT3.x; gT[7] += dL_dT3.y; gT[8] += dL_dT3.z;
+  }
+  for (int i = 0; i < 9; i++) o_T[i] = gT[i];
+  const float Wh = a.focal_x * a.tan_fovx, Hh = a.focal_y * a.tan_fovy;
+  const float z = q2.z;
+  o_m2d[0] = gT[2] * z * Wh;
+  o_m2d[1] = gT[5] * z * Hh;
+  o_m2d[2] = 0.f;
+
+  // ---- computeTransMat VJP ----
+  const float* viewmat = a.viewmatrix;
+  const float4 intrins = {a.focal_x, a.focal_y, a.focal_x * a.tan_fovx, a.focal_y * a.tan_fovy};
+  m3 W;
+  W[0] = v3(viewmat[0], viewmat[1], viewmat[2]);
+  W[1] = v3(viewmat[4], viewmat[5], viewmat[6]);
+  W[2] = v3(viewmat[8], viewmat[9], viewmat[10]);
+  const v3 cam_pos = v3(viewmat[12], viewmat[13], viewmat[14]);
+  m4 Pm;
+  Pm[0] = v4(intrins.x, 0.0f, 0.0f, 0.0f);
+  Pm[1] = v4(0.0f, intrins.y, 0.0f, 0.0f);
+  Pm[2] = v4(intrins.z, intrins.w, 1.0f, 1.0f);
+  Pm[3] = v4(0.0f, 0.0f, 0.0f, 0.0f);
+  const v3 p_world = v3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
+  const v4 quat = ((const v4*)a.rotations)[idx];
+  const v2 scale = ((const v2*)a.scales)[idx];
+  m3 S = diag3(1.f);
+  S[0][0] = 1.0f * scale.x; S[1][1] = 1.0f * scale.y; S[2][2] = 1.0f;
+  m3 R = quat_to_rotmat_b(quat);
+  m3 RS = R * S;
+  v3 p_view = W * p_world + cam_pos;
+  m3 Mm = make_m3(W * RS[0], W * RS[1], p_view);
+
+  m4x3 dL_dT;
+  dL_dT[0] = v3(gT[0], gT[1], gT[2]);
+  dL_dT[1] = v3(gT[3], gT[4], gT[5]);
+  dL_dT[2] = v3(gT[6], gT[7], gT[8]);
+  dL_dT[3] = v3(0.0f, 0.0f, 0.0f);
+  m3x4 dL_dM_aug = transpose(Pm) * transpose(dL_dT);
+  m3 dL_dM = make_m3(xyz(dL_dM_aug[0]), xyz(dL_dM_aug[1]), xyz(dL_dM_aug[2]));
+  m3 W_t = transpose(W);
+  m3 dL_dRS = W_t * dL_dM;
+  v3 dL_dRS0 = dL_dRS[0];
+  v3 dL_dRS1 = dL_dRS[1];
+  v3 dL_dpw = dL_dRS[2];
+  v3 dL_dtn = W_t * v3(dL_dnormal3D[0], dL_dnormal3D[1], dL_dnormal3D[2]);
+  v3 tn = W * R[2];
+  float cosv = dot(-tn, Mm[2]);
+  float multiplier = cosv > 0 ? 1 : -1;
+  dL_dtn *= multiplier;
+  m3 dL_dR = make_m3(dL_dRS0 * v3(scale.x, scale.x, scale.x), dL_dRS1 * v3(scale.y, scale.y, scale.y), dL_dtn);
+  v4 dq = quat_to_rotmat_vjp(quat, dL_dR);
+  a.dL_drots[idx * 4 + 0] = dq.x; a.dL_drots[idx * 4 + 1] = dq.y;
+  a.dL_drots[idx * 4 + 2] = dq.z; a.dL_drots[idx * 4 + 3] = dq.w;
+  a.dL_dscales[idx * 2 + 0] = (float)dot(dL_dRS0, R[0]);
+  a.dL_dscales[idx * 2 + 1] = (float)dot(dL_dRS1, R[1]);
+  v3 dmean = dL_dpw;
+
+  if (a.shs) {
+    v3 extra = sh_backward(idx, a.D, M, (const v3*)a.means3D, *(const v3*)a.cam_pos, a.shs, __float_as_uint(q4.w),
+                           dL_dcolor, (v3*)o_sh);
+    dmean += extra;
+  } else if (o_sh) {
+    for (int i = 0; i < M * 3; i++) o_sh[i] = 0.f;
+  }
+  o_m3d[0] = dmean.x; o_m3d[1] = dmean.y; o_m3d[2] = dmean.z;
+  o_col[0] = dL_dcolor.x; o_col[1] = dL_dcolor.y; o_col[2] = dL_dcolor.z;
+  a.dL_dopacity[idx] = g_opacity;
+}
+
+void launch_preprocess_bwd_part(const PreprocessBwdArgs& a, cudaStream_t s) {
+  if (a.P <= 0) return;
+  preprocess_bwd_part_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a);
+  count_launch();
 }
 
 void launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t s) {

@@ -257,6 +257,119 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessFwdArgs a
   a.tiles_touched[idx] = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
 }
 
+// =============================================================================
+// `_part` fork (submodules/diff-surfel-rasterization_part): older 2DGS math.
+//   computeTransMat   DSRP/cuda_rasterizer/forward.cu:75-128  (view matrix + intrinsics
+//                     {fx, fy, W/2, H/2}; scale_modifier ignored; normal flipped inside)
+//   computeAABB       :133-163 (1-sigma box, h = sqrt(max(0,h0)))
+//   preprocessCUDA    :166-260 (radius = ceil(3 * max(ext, 0.7071067811865476)) in double)
+// =============================================================================
+__device__ __forceinline__ bool part_transmat(const v3& p_world, const v4& quat, const v2& scale,
+                                              const float* viewmat, const float4& intrins, m3& Tout,
+                                              float3& normal) {
+  m3 W;
+  W[0] = v3(viewmat[0], viewmat[1], viewmat[2]);
+  W[1] = v3(viewmat[4], viewmat[5], viewmat[6]);
+  W[2] = v3(viewmat[8], viewmat[9], viewmat[10]);
+  const v3 cam_pos = v3(viewmat[12], viewmat[13], viewmat[14]);
+  m4 Pm;
+  Pm[0] = v4(intrins.x, 0.0f, 0.0f, 0.0f);
+  Pm[1] = v4(0.0f, intrins.y, 0.0f, 0.0f);
+  Pm[2] = v4(intrins.z, intrins.w, 1.0f, 1.0f);
+  Pm[3] = v4(0.0f, 0.0f, 0.0f, 0.0f);
+
+  v3 p_view = W * p_world + cam_pos;
+  m3 S = diag3(1.f);
+  S[0][0] = 1.0f * scale.x;
+  S[1][1] = 1.0f * scale.y;
+  S[2][2] = 1.0f * 1.0f;
+  m3 R = quat_to_rotmat(quat) * S;
+  m3 M = make_m3(W * R[0], W * R[1], p_view);
+  v3 tn = W * R[2];
+  float cosv = dot(-tn, p_view);
+  if (cosv == 0.0f) return false;
+  float multiplier = cosv > 0 ? 1 : -1;
+  tn *= multiplier;
+  m4x3 T = transpose(Pm * make_m3x4(v4(M[0], 0.0f), v4(M[1], 0.0f), v4(M[2], 1.0f)));
+  Tout[0] = T[0];
+  Tout[1] = T[1];
+  Tout[2] = T[2];
+  normal = {tn.x, tn.y, tn.z};
+  return true;
+}
+
+__device__ __forceinline__ bool part_aabb(const m3& T3, float2& center, float2& extent) {
+  m4x3 T;
+  T[0] = T3[0]; T[1] = T3[1]; T[2] = T3[2]; T[3] = T3[2];
+  float d = dot(v3(1.0f, 1.0f, -1.0f), T[3] * T[3]);
+  if (d == 0.0f) return false;
+  v3 f = v3(1.0f, 1.0f, -1.0f) * (1.0f / d);
+  v3 p = v3(dot(f, T[0] * T[3]), dot(f, T[1] * T[3]), dot(f, T[2] * T[3]));
+  v3 h0 = p * p - v3(dot(f, T[0] * T[0]), dot(f, T[1] * T[1]), dot(f, T[2] * T[2]));
+  v3 h = vsqrt(vmax(v3(0.0f, 0.0f, 0.0f), h0)) + v3(0.0f, 0.0f, (float)1e-2);
+  center = {p.x, p.y};
+  extent = {h.x, h.y};
+  return true;
+}
+
+__global__ void __launch_bounds__(256) preprocess_fwd_part_kernel(PreprocessFwdArgs a) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.P) return;
+  a.radii[idx] = 0;
+  a.tiles_touched[idx] = 0;
+
+  const int W = a.W, H = a.H;
+  const float* orig_points = a.means3D;
+  v3 p_world = v3(orig_points[3 * idx], orig_points[3 * idx + 1], orig_points[3 * idx + 2]);
+  float3 p_orig = {p_world.x, p_world.y, p_world.z};
+  float3 p_view = xform_point4x3(p_orig, a.viewmatrix);
+  if (p_view.z <= 0.2f) return;
+
+  float4 intrins = {a.focal_x, a.focal_y, (float)(float(W) / 2.0), (float)(float(H) / 2.0)};
+  v2 scale = ((const v2*)a.scales)[idx];
+  v4 quat = ((const v4*)a.rotations)[idx];
+  m3 T;
+  float3 normal;
+  if (!part_transmat(p_world, quat, scale, a.viewmatrix, intrins, T, normal)) return;
+
+  float2 center, extent;
+  if (!part_aabb(T, center, extent)) return;
+  float truncated_R = 3.f;
+  float radius = ceil(truncated_R * max(max(extent.x, extent.y), 0.7071067811865476));
+
+  dim3 grid(a.grid_x, a.grid_y, 1);
+  uint2 rect_min, rect_max;
+  tile_rect(center, radius, rect_min, rect_max, grid);
+  if ((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y) == 0) return;
+
+  float r, g, b;
+  unsigned clamped = 0;
+  if (a.colors_precomp == nullptr) {
+    v3 c = color_from_sh(idx, a.D, a.M, (const v3*)orig_points, *(const v3*)a.cam_pos, a.shs, clamped);
+    r = c.x; g = c.y; b = c.z;
+  } else {
+    r = a.colors_precomp[idx * 3 + 0];
+    g = a.colors_precomp[idx * 3 + 1];
+    b = a.colors_precomp[idx * 3 + 2];
+  }
+  const float opa = a.opacities[idx];
+  float4* rec = a.rec + (size_t)idx * REC_QUADS;
+  rec[0] = make_float4(T[0].x, T[0].y, T[0].z, center.x);
+  rec[1] = make_float4(T[1].x, T[1].y, T[1].z, center.y);
+  rec[2] = make_float4(T[2].x, T[2].y, T[2].z, opa);
+  rec[3] = make_float4(normal.x, normal.y, normal.z, p_view.z);
+  rec[4] = make_float4(r, g, b, __uint_as_float(clamped));
+  a.bbox[idx] = cull_box(T, center, opa);
+  a.radii[idx] = (int)radius;
+  a.tiles_touched[idx] = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
+}
+
+void launch_preprocess_fwd_part(const PreprocessFwdArgs& a, cudaStream_t s) {
+  if (a.P <= 0) return;
+  preprocess_fwd_part_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a);
+  count_launch();
+}
+
 // mark_visible (reference checkFrustum, rasterizer_impl.cu:54-66)
 __global__ void __launch_bounds__(256) check_frustum_kernel(int P, const float* means3D, const float* viewmatrix,
                                                             unsigned char* present) {

@@ -1,0 +1,598 @@
+// Per-tile alpha blending of 2D-Gaussian surfels, forward and backward, for both forks
+// (sm_100a).
+//
+// Replaces reference renderCUDA forward (cuda_rasterizer/forward.cu:256-441; `_part` fork
+// DSRP/cuda_rasterizer/forward.cu:265-474) and backward (backward.cu:143-440; `_part`
+// :143-471).  The reference runs one 16x16 CTA per tile in lock-step rounds of 256 surfels
+// (three __syncthreads per round, every pixel visits every surfel binned to the tile) and
+// issues 16 global float atomics per pixel x surfel fragment in the backward pass.
+//
+// B200 design:
+//   * a tile is still one 256-thread CTA, but its 8 warps are independent streams: each warp
+//     owns an 8x4 pixel footprint and walks the tile's depth-sorted list on its own, 32
+//     candidates per step — one candidate per lane: fetch id (coalesced) and the surfel's
+//     16-byte cull box, test the box against the warp's footprint, ballot-compact the
+//     survivors and stage only their 80-byte records into the warp's private shared-memory
+//     ring with 128-bit cp.async (LDGSTS); ids / boxes of the next step are prefetched while
+//     the current survivors are blended.  No __syncthreads anywhere in the loop, so a warp
+//     never waits for a sibling with more work, and a surfel costs ALU time only in the
+//     warps whose footprint its cull box touches;
+//   * tiles are issued longest-list-first (tile_order, built by tile_order_kernel) so the
+//     heavy tiles do not form the tail of the launch;
+//   * warp-level early termination (all 32 pixels saturated) in forward; in backward each
+//     warp starts at its own deepest contributing fragment (max n_contrib over its pixels);
+//   * backward: the 16+3(+S) per-fragment gradient components are reduced over the 32 pixels
+//     with a transposed butterfly (16 shuffles for 16 values instead of 80); 16 lanes then
+//     hold one finished component each and issue one coalesced red.global.add.f32 into the
+//     surfel's 80-byte gradient record.
+// The per-fragment arithmetic is pinned in frag_math.cuh; accumulations below use the
+// reference's rounding sequence (explicit fma/mul), so images are bit-identical.
+#include "common.cuh"
+#include "frag_math.cuh"
+#include "kernels.h"
+
+namespace pgs {
+
+constexpr unsigned RFULL = 0xffffffffu;
+constexpr int NWARP = TILE_PIX / 32;
+constexpr int CHUNK = 32;  // candidates per warp step (one per lane)
+
+struct __align__(16) WarpStage {
+  float4 rec[CHUNK][REC_QUADS];  // 32 x 80 B
+  uint32_t pos[CHUNK];           // list position of the staged surfel
+  uint32_t id[CHUNK];            // surfel index (backward only)
+};
+
+__device__ __forceinline__ bool box_hits(const float4 b, float x0, float y0, float x1, float y1) {
+  return !(b.x > x1 || b.z < x0 || b.y > y1 || b.w < y0);
+}
+
+// =============================================================================
+// tile order: longest list first (approximate LPT by counting sort on len/16)
+// =============================================================================
+constexpr int TO_BUCKETS = 1024;
+__global__ void __launch_bounds__(1024) tile_order_kernel(const uint2* __restrict__ ranges, int ntiles,
+                                                          uint32_t* __restrict__ order) {
+  __shared__ uint32_t s_cnt[TO_BUCKETS];
+  __shared__ uint32_t s_warp[32];
+  const int tid = threadIdx.x;
+  s_cnt[tid] = 0;
+  __syncthreads();
+  for (int t = tid; t < ntiles; t += blockDim.x) {
+    const uint2 r = ranges[t];
+    const uint32_t b = TO_BUCKETS - 1 - min((r.y - r.x) >> 4, (uint32_t)(TO_BUCKETS - 1));  // long lists -> small bucket
+    atomicAdd(&s_cnt[b], 1u);
+  }
+  __syncthreads();
+  // exclusive scan of the 1024 bucket counts
+  const uint32_t c = s_cnt[tid];
+  uint32_t w = c;
+  const unsigned lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(RFULL, w, o);
+    if (lane >= (unsigned)o) w += t;
+  }
+  if (lane == 31) s_warp[wid] = w;
+  __syncthreads();
+  uint32_t off = 0;
+  for (int i = 0; i < 32; i++)
+    if (i < (int)wid) off += s_warp[i];
+  __syncthreads();
+  s_cnt[tid] = off + w - c;
+  __syncthreads();
+  for (int t = tid; t < ntiles; t += blockDim.x) {
+    const uint2 r = ranges[t];
+    const uint32_t b = TO_BUCKETS - 1 - min((r.y - r.x) >> 4, (uint32_t)(TO_BUCKETS - 1));
+    order[atomicAdd(&s_cnt[b], 1u)] = (uint32_t)t;
+  }
+}
+
+void launch_tile_order(const uint2* ranges, int ntiles, uint32_t* order, cudaStream_t s) {
+  if (ntiles <= 0) return;
+  tile_order_kernel<<<1, 1024, 0, s>>>(ranges, ntiles, order);
+  count_launch();
+}
+
+// =============================================================================
+// forward
+// =============================================================================
+template <bool PART>
+__global__ void __launch_bounds__(TILE_PIX) render_fwd_kernel(RenderFwdArgs a) {
+  __shared__ WarpStage s_stage[NWARP];
+  extern __shared__ float s_sem_dyn[];  // PART: [NWARP][CHUNK][MAX_SEMANTIC]
+
+  const int S = PART ? a.S : 0;
+  const int tid = threadIdx.x;
+  const unsigned lane = tid & 31, wid = tid >> 5;
+  const int tile_id = a.tile_order ? (int)a.tile_order[blockIdx.x] : (int)blockIdx.x;
+  const int tile_x = tile_id % a.grid_x, tile_y = tile_id / a.grid_x;
+  const int fx0 = tile_x * TILE_X + (wid & 1) * WARP_FX;
+  const int fy0 = tile_y * TILE_Y + (wid >> 1) * WARP_FY;
+  const uint2 pix = {(unsigned)(fx0 + (lane & 7)), (unsigned)(fy0 + (lane >> 3))};
+  const float poff = PART ? 0.5f : 0.0f;  // pixel centres: integer (base) / +0.5 (`_part`)
+  const float2 pixf = {(float)pix.x + poff, (float)pix.y + poff};
+  const bool inside = pix.x < (unsigned)a.W && pix.y < (unsigned)a.H;
+  bool done = !inside;
+  const float wx0 = (float)fx0 + poff, wy0 = (float)fy0 + poff;
+  const float wx1 = wx0 + (float)(WARP_FX - 1), wy1 = wy0 + (float)(WARP_FY - 1);
+
+  WarpStage& st = s_stage[wid];
+  float* sem_stage = PART ? (s_sem_dyn + (size_t)wid * CHUNK * MAX_SEMANTIC) : nullptr;
+
+  const uint2 range = a.ranges[tile_id];
+  const int total = (int)(range.y - range.x);
+  const uint32_t* __restrict__ list = a.point_list + range.x;
+
+  float T = 1.0f;
+  uint32_t last_contributor = 0;
+  float C[3] = {0.f, 0.f, 0.f};
+  float N[3] = {0.f, 0.f, 0.f};
+  float D = 0.f, M1 = 0.f, M2 = 0.f, distortion = 0.f, median_depth = 0.f, median_weight = 0.f;
+  float median_contributor = -1.f;
+  float Sem[MAX_SEMANTIC];
+  if (PART) {
+#pragma unroll
+    for (int i = 0; i < MAX_SEMANTIC; i++) Sem[i] = 0.f;
+  }
+
+  // software pipeline: ids two steps ahead, cull boxes one step ahead
+  const float4 nobox = make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);
+  uint32_t id_cur = 0, id_nxt = 0;
+  float4 box_cur = nobox;
+  if ((int)lane < total) id_cur = list[lane];
+  if ((int)lane + CHUNK < total) id_nxt = list[lane + CHUNK];
+  if ((int)lane < total) box_cur = __ldg(&a.bbox[id_cur]);
+
+  for (int base = 0; base < total; base += CHUNK) {
+    if (__all_sync(RFULL, done)) break;
+    // prefetch for the following steps
+    uint32_t id_n2 = 0;
+    if (base + 2 * CHUNK + (int)lane < total) id_n2 = list[base + 2 * CHUNK + lane];
+    float4 box_nxt = nobox;
+    if (base + CHUNK + (int)lane < total) box_nxt = __ldg(&a.bbox[id_nxt]);
+
+    const bool hit = box_hits(box_cur, wx0, wy0, wx1, wy1);  // lanes past the end carry `nobox`
+    const unsigned m = __ballot_sync(RFULL, hit);
+    const int n = __popc(m);
+    if (n > 0) {
+      if (hit) {
+        const int slot = __popc(m & ((1u << lane) - 1));
+        const float4* src = a.rec + (size_t)id_cur * REC_QUADS;
+#pragma unroll
+        for (int q = 0; q < REC_QUADS; q++) cp_async16(&st.rec[slot][q], src + q);
+        st.pos[slot] = (uint32_t)(base + lane + 1);
+        if (PART) {
+          const float* sem = a.semantics + (size_t)id_cur * S;
+          for (int ch = 0; ch < S; ch++) sem_stage[slot * MAX_SEMANTIC + ch] = __ldg(sem + ch);
+        }
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncwarp();
+
+      for (int j = 0; j < n; j++) {
+        if (done) continue;
+        const float4 q0 = st.rec[j][0];
+        const float4 q1 = st.rec[j][1];
+        const float4 q2 = st.rec[j][2];
+        const float3 Tu = {q0.x, q0.y, q0.z};
+        const float3 Tv = {q1.x, q1.y, q1.z};
+        const float3 Tw = {q2.x, q2.y, q2.z};
+        FragGeom f;
+        if (!frag_geometry<PART>(pixf, Tu, Tv, Tw, make_float2(q0.w, q1.w), f)) continue;
+        const float depth = f.depth;
+        if (PART) {
+          if ((double)depth < 0.2) continue;
+        } else {
+          if (depth < PGS_NEAR_N) continue;
+        }
+        float power, G;
+        const float alpha = frag_alpha(f.rho3d, f.rho2d, q2.w, power, G);
+        if (power > 0.0f) continue;
+        if (alpha < 1.0f / 255.0f) continue;
+        const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+        if (test_T < 0.0001f) {
+          done = true;
+          continue;
+        }
+        const float4 q3 = st.rec[j][3];
+        const float4 q4 = st.rec[j][4];
+        const uint32_t contributor = st.pos[j];
+        const float A = __fsub_rn(1.0f, T);
+        if (!PART) {
+          const float w = __fmul_rn(alpha, T);
+          const float mm = __fmul_rn(__fadd_rn(__fdiv_rn(-PGS_NEAR_N, depth), 1.0f),
+                                     PGS_FAR_N / (PGS_FAR_N - PGS_NEAR_N));
+          const float mm2 = __fmul_rn(mm, mm);
+          const float err = __fmaf_rn(-M1, __fadd_rn(mm, mm), __fmaf_rn(A, mm2, M2));
+          distortion = __fmaf_rn(err, w, distortion);
+          D = __fmaf_rn(depth, w, D);
+          M1 = __fmaf_rn(mm, w, M1);
+          M2 = __fmaf_rn(mm2, w, M2);
+          if (T > 0.5f) {
+            median_depth = depth;
+            median_contributor = (float)contributor;
+          }
+          N[0] = __fmaf_rn(q3.x, w, N[0]);
+          N[1] = __fmaf_rn(q3.y, w, N[1]);
+          N[2] = __fmaf_rn(q3.z, w, N[2]);
+          C[0] = __fmaf_rn(q4.x, w, C[0]);
+          C[1] = __fmaf_rn(q4.y, w, C[1]);
+          C[2] = __fmaf_rn(q4.z, w, C[2]);
+        } else {
+          // `_part`: mapped depth in double, every accumulation is fma(T, x*alpha, acc)
+          const double dd = (double)depth;
+          const float md = (float)__ddiv_rn(__fma_rn(dd, 100.0, -20.0), __dmul_rn(dd, 100.0 - 0.2));
+          const float md2 = __fmul_rn(md, md);
+          const float err = __fmaf_rn(-M1, __fadd_rn(md, md), __fmaf_rn(A, md2, M2));
+          distortion = __fmaf_rn(T, __fmul_rn(err, alpha), distortion);
+          if (T > 0.5f) {
+            median_depth = depth;
+            median_weight = __fmul_rn(alpha, T);
+            median_contributor = (float)contributor;
+          }
+          N[0] = __fmaf_rn(T, __fmul_rn(q3.x, alpha), N[0]);
+          N[1] = __fmaf_rn(T, __fmul_rn(q3.y, alpha), N[1]);
+          N[2] = __fmaf_rn(T, __fmul_rn(q3.z, alpha), N[2]);
+          D = __fmaf_rn(T, __fmul_rn(depth, alpha), D);
+          M1 = __fmaf_rn(T, __fmul_rn(md, alpha), M1);
+          M2 = __fmaf_rn(T, __fmul_rn(md2, alpha), M2);
+          C[0] = __fmaf_rn(T, __fmul_rn(q4.x, alpha), C[0]);
+          C[1] = __fmaf_rn(T, __fmul_rn(q4.y, alpha), C[1]);
+          C[2] = __fmaf_rn(T, __fmul_rn(q4.z, alpha), C[2]);
+#pragma unroll
+          for (int ch = 0; ch < MAX_SEMANTIC; ch++)
+            if (ch < S) Sem[ch] = __fmaf_rn(T, __fmul_rn(sem_stage[j * MAX_SEMANTIC + ch], alpha), Sem[ch]);
+        }
+        T = test_T;
+        last_contributor = contributor;
+      }
+      __syncwarp();  // the ring is rewritten in the next step
+    }
+    id_cur = id_nxt;
+    id_nxt = id_n2;
+    box_cur = box_nxt;
+  }
+
+  // per-pixel state for backward, tile-major so that a warp writes 128 contiguous bytes
+  const size_t npt = (size_t)a.grid_x * a.grid_y * TILE_PIX;
+  const size_t sidx = (size_t)tile_id * TILE_PIX + tid;
+  a.final_T[sidx] = T;
+  a.final_T[sidx + npt] = M1;
+  a.final_T[sidx + 2 * npt] = M2;
+  a.n_contrib[sidx] = last_contributor;
+  // The reference converts its float -1 sentinel to uint32 (undefined in C++, garbage in
+  // practice) for pixels nothing was blended into; those have n_contrib == 0 and the value is
+  // never consulted.  Store a defined 0.
+  a.n_contrib[sidx + npt] = median_contributor < 0.f ? 0u : (uint32_t)median_contributor;
+
+  if (inside) {
+    const size_t HW = (size_t)a.H * a.W;
+    const size_t pix_id = (size_t)a.W * pix.y + pix.x;
+    for (int ch = 0; ch < 3; ch++) a.out_color[ch * HW + pix_id] = __fmaf_rn(T, a.bg_color[ch], C[ch]);
+    a.out_others[pix_id + DEPTH_OFFSET * HW] = D;
+    a.out_others[pix_id + ALPHA_OFFSET * HW] = 1 - T;
+    for (int ch = 0; ch < 3; ch++) a.out_others[pix_id + (NORMAL_OFFSET + ch) * HW] = N[ch];
+    a.out_others[pix_id + MIDDEPTH_OFFSET * HW] = median_depth;
+    a.out_others[pix_id + DISTORTION_OFFSET * HW] = distortion;
+    if (PART) {
+      a.out_others[pix_id + MEDIAN_WEIGHT_OFFSET * HW] = median_weight;
+#pragma unroll
+      for (int ch = 0; ch < MAX_SEMANTIC; ch++)
+        if (ch < S) a.out_semantic[ch * HW + pix_id] = Sem[ch];
+    }
+  }
+}
+
+// =============================================================================
+// backward
+// =============================================================================
+// Sum v[0..15] over the warp; every lane returns component (lane >> 1).
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], unsigned lane) {
+#pragma unroll
+  for (int step = 0; step < 4; step++) {
+    const int half = 8 >> step;
+    const unsigned bit = 16u >> step;
+    const bool hi = lane & bit;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (i < half) {
+        const float keep = hi ? v[i + half] : v[i];
+        const float send = hi ? v[i] : v[i + half];
+        v[i] = keep + __shfl_xor_sync(RFULL, send, bit);
+      }
+    }
+  }
+  v[0] += __shfl_xor_sync(RFULL, v[0], 1);
+  return v[0];
+}
+// Sum c[0..3] over the warp; every lane returns component (lane >> 3).
+__device__ __forceinline__ float warp_reduce4(float (&c)[4], unsigned lane) {
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const float keep = hi ? c[i + 2] : c[i];
+      const float send = hi ? c[i] : c[i + 2];
+      c[i] = keep + __shfl_xor_sync(RFULL, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
+    const float keep = hi ? c[1] : c[0];
+    const float send = hi ? c[0] : c[1];
+    c[0] = keep + __shfl_xor_sync(RFULL, send, 8);
+  }
+  c[0] += __shfl_xor_sync(RFULL, c[0], 4);
+  c[0] += __shfl_xor_sync(RFULL, c[0], 2);
+  c[0] += __shfl_xor_sync(RFULL, c[0], 1);
+  return c[0];
+}
+
+template <bool PART>
+__global__ void __launch_bounds__(TILE_PIX) render_bwd_kernel(RenderBwdArgs a) {
+  __shared__ WarpStage s_stage[NWARP];
+
+  const int S = PART ? a.S : 0;
+  const int tid = threadIdx.x;
+  const unsigned lane = tid & 31, wid = tid >> 5;
+  const int tile_id = a.tile_order ? (int)a.tile_order[blockIdx.x] : (int)blockIdx.x;
+  const int tile_x = tile_id % a.grid_x, tile_y = tile_id / a.grid_x;
+  const int fx0 = tile_x * TILE_X + (wid & 1) * WARP_FX;
+  const int fy0 = tile_y * TILE_Y + (wid >> 1) * WARP_FY;
+  const uint2 pix = {(unsigned)(fx0 + (lane & 7)), (unsigned)(fy0 + (lane >> 3))};
+  const float poff = PART ? 0.5f : 0.0f;
+  const float2 pixf = {(float)pix.x + poff, (float)pix.y + poff};
+  const bool inside = pix.x < (unsigned)a.W && pix.y < (unsigned)a.H;
+  const float wx0 = (float)fx0 + poff, wy0 = (float)fy0 + poff;
+  const float wx1 = wx0 + (float)(WARP_FX - 1), wy1 = wy0 + (float)(WARP_FY - 1);
+
+  WarpStage& st = s_stage[wid];
+  const uint2 range = a.ranges[tile_id];
+  const uint32_t* __restrict__ list = a.point_list + range.x;
+
+  const size_t npt = (size_t)a.grid_x * a.grid_y * TILE_PIX;
+  const size_t sidx = (size_t)tile_id * TILE_PIX + tid;
+  const size_t HW = (size_t)a.H * a.W;
+  const size_t pix_id = (size_t)a.W * pix.y + pix.x;
+
+  const float T_final = inside ? a.final_T[sidx] : 0;
+  float T = T_final;
+  const uint32_t last_contributor = inside ? a.n_contrib[sidx] : 0;
+  const uint32_t median_contributor = inside ? a.n_contrib[sidx + npt] : 0;
+  const float final_D = inside ? a.final_T[sidx + npt] : 0;
+  const float final_D2 = inside ? a.final_T[sidx + 2 * npt] : 0;
+  const float final_A = 1 - T_final;
+
+  float dL_dpixel[3] = {0.f, 0.f, 0.f};
+  float dL_dreg = 0.f, dL_ddepth = 0.f, dL_daccum = 0.f, dL_dmedian_depth = 0.f, dL_dmax_dweight = 0.f;
+  float dL_dnormal2D[3] = {0.f, 0.f, 0.f};
+  float dL_dsem[MAX_SEMANTIC];
+  if (PART) {
+#pragma unroll
+    for (int i = 0; i < MAX_SEMANTIC; i++) dL_dsem[i] = 0.f;
+  }
+  if (inside) {
+    for (int i = 0; i < 3; i++) dL_dpixel[i] = a.dL_dpixels[i * HW + pix_id];
+    dL_ddepth = a.dL_dothers[DEPTH_OFFSET * HW + pix_id];
+    dL_daccum = a.dL_dothers[ALPHA_OFFSET * HW + pix_id];
+    dL_dreg = a.dL_dothers[DISTORTION_OFFSET * HW + pix_id];
+    for (int i = 0; i < 3; i++) dL_dnormal2D[i] = a.dL_dothers[(NORMAL_OFFSET + i) * HW + pix_id];
+    dL_dmedian_depth = a.dL_dothers[MIDDEPTH_OFFSET * HW + pix_id];
+    if (PART) {
+      dL_dmax_dweight = a.dL_dothers[MEDIAN_WEIGHT_OFFSET * HW + pix_id];
+#pragma unroll
+      for (int i = 0; i < MAX_SEMANTIC; i++)
+        if (i < S) dL_dsem[i] = a.dL_dsemantic[i * HW + pix_id];
+    }
+  }
+  float bg_dot_dpixel = 0;
+  for (int i = 0; i < 3; i++) bg_dot_dpixel += a.bg_color[i] * dL_dpixel[i];
+
+  float accum_rec[3] = {0.f, 0.f, 0.f};
+  float last_color[3] = {0.f, 0.f, 0.f};
+  float last_alpha = 0;
+  float last_depth = 0;
+  float last_normal[3] = {0.f, 0.f, 0.f};
+  float accum_depth_rec = 0;
+  float accum_alpha_rec = 0;
+  float accum_normal_rec[3] = {0.f, 0.f, 0.f};
+  float last_dL_dT = 0;
+
+  // deepest contributing fragment over the warp's 32 pixels: positions [0, top) matter
+  uint32_t top = last_contributor;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) top = max(top, __shfl_xor_sync(RFULL, top, o));
+  const int total = (int)top;
+
+  const float4 nobox = make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);
+  // candidate c of step `base` sits at list position total-1-(base+lane)  (back to front)
+  uint32_t id_cur = 0, id_nxt = 0;
+  float4 box_cur = nobox;
+  if ((int)lane < total) id_cur = list[total - 1 - lane];
+  if ((int)lane + CHUNK < total) id_nxt = list[total - 1 - lane - CHUNK];
+  if ((int)lane < total) box_cur = __ldg(&a.bbox[id_cur]);
+
+  for (int base = 0; base < total; base += CHUNK) {
+    uint32_t id_n2 = 0;
+    if (base + 2 * CHUNK + (int)lane < total) id_n2 = list[total - 1 - (base + 2 * CHUNK + lane)];
+    float4 box_nxt = nobox;
+    if (base + CHUNK + (int)lane < total) box_nxt = __ldg(&a.bbox[id_nxt]);
+
+    const bool hit = box_hits(box_cur, wx0, wy0, wx1, wy1);
+    const unsigned m = __ballot_sync(RFULL, hit);
+    const int n = __popc(m);
+    if (n > 0) {
+      if (hit) {
+        const int slot = __popc(m & ((1u << lane) - 1));
+        const float4* src = a.rec + (size_t)id_cur * REC_QUADS;
+#pragma unroll
+        for (int q = 0; q < REC_QUADS; q++) cp_async16(&st.rec[slot][q], src + q);
+        st.pos[slot] = (uint32_t)(total - 1 - (base + (int)lane));
+        st.id[slot] = id_cur;
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncwarp();
+
+      for (int j = 0; j < n; j++) {
+        const uint32_t contributor = st.pos[j];
+        const float4 q0 = st.rec[j][0];
+        const float4 q1 = st.rec[j][1];
+        const float4 q2 = st.rec[j][2];
+        const float3 Tu = {q0.x, q0.y, q0.z};
+        const float3 Tv = {q1.x, q1.y, q1.z};
+        const float3 Tw = {q2.x, q2.y, q2.z};
+        const float opa = q2.w;
+
+        // replay the forward decision sequence bit-identically
+        FragGeom f;
+        bool valid = contributor < last_contributor;
+        valid = frag_geometry<PART>(pixf, Tu, Tv, Tw, make_float2(q0.w, q1.w), f) && valid;
+        const float c_d = f.depth;
+        if (PART) valid = valid && !((double)c_d < 0.2);
+        else valid = valid && !(c_d < PGS_NEAR_N);
+        float power, G;
+        const float alpha = frag_alpha(f.rho3d, f.rho2d, opa, power, G);
+        valid = valid && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+
+        if (!__any_sync(RFULL, valid)) continue;
+
+        float g[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) g[i] = 0.f;
+        float gc[4] = {0.f, 0.f, 0.f, 0.f};
+        float w_sem = 0.f;
+
+        if (valid) {
+          const float4 q3 = st.rec[j][3];
+          const float4 q4 = st.rec[j][4];
+          const float normal[3] = {q3.x, q3.y, q3.z};
+          const float col[3] = {q4.x, q4.y, q4.z};
+          const float3 k = f.k, l = f.l, p = f.p;
+          const float2 s = f.s, d = f.d;
+
+          T = __fdiv_rn(T, __fsub_rn(1.f, alpha));
+          const float dchannel_dcolor = alpha * T;
+          w_sem = dchannel_dcolor;
+          float dL_dalpha = 0.0f;
+#pragma unroll
+          for (int ch = 0; ch < 3; ch++) {
+            const float c = col[ch];
+            accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+            last_color[ch] = c;
+            const float dL_dchannel = dL_dpixel[ch];
+            dL_dalpha += (c - accum_rec[ch]) * dL_dchannel;
+            gc[ch] = dchannel_dcolor * dL_dchannel;
+          }
+
+          float dL_dz = 0.0f;
+          float dL_dweight = 0;
+          float m_d, dmd_dd;
+          if (PART) {
+            m_d = (100.0 * c_d - 100.0 * 0.2) / ((100.0 - 0.2) * c_d);
+            dmd_dd = (100.0 * 0.2) / ((100.0 - 0.2) * c_d * c_d);
+          } else {
+            m_d = PGS_FAR_N / (PGS_FAR_N - PGS_NEAR_N) * (1 - PGS_NEAR_N / c_d);
+            dmd_dd = (PGS_FAR_N * PGS_NEAR_N) / ((PGS_FAR_N - PGS_NEAR_N) * c_d * c_d);
+          }
+          if (contributor == median_contributor - 1) {
+            dL_dz += dL_dmedian_depth;
+            if (PART) dL_dweight += dL_dmax_dweight;
+          }
+          dL_dweight += (final_D2 + m_d * m_d * final_A - 2 * m_d * final_D) * dL_dreg;
+          dL_dalpha += dL_dweight - last_dL_dT;
+          last_dL_dT = dL_dweight * alpha + (1 - alpha) * last_dL_dT;
+          const float dL_dmd = 2.0f * (T * alpha) * (m_d * final_A - final_D) * dL_dreg;
+          dL_dz += dL_dmd * dmd_dd;
+
+          accum_depth_rec = last_alpha * last_depth + (1.f - last_alpha) * accum_depth_rec;
+          last_depth = c_d;
+          dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
+          accum_alpha_rec = last_alpha * 1.0f + (1.f - last_alpha) * accum_alpha_rec;
+          dL_dalpha += (1 - accum_alpha_rec) * dL_daccum;
+
+#pragma unroll
+          for (int ch = 0; ch < 3; ch++) {
+            accum_normal_rec[ch] = last_alpha * last_normal[ch] + (1.f - last_alpha) * accum_normal_rec[ch];
+            last_normal[ch] = normal[ch];
+            dL_dalpha += (normal[ch] - accum_normal_rec[ch]) * dL_dnormal2D[ch];
+            g[12 + ch] = alpha * T * dL_dnormal2D[ch];
+          }
+
+          dL_dalpha *= T;
+          last_alpha = alpha;
+          dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+
+          const float dL_dG = opa * dL_dalpha;
+          dL_dz += alpha * T * dL_ddepth;
+
+          if (f.rho3d <= f.rho2d) {
+            const float2 dL_ds = {dL_dG * -G * s.x + dL_dz * Tw.x, dL_dG * -G * s.y + dL_dz * Tw.y};
+            const float dsx_pz = dL_ds.x / p.z;
+            const float dsy_pz = dL_ds.y / p.z;
+            const float3 dL_dp = {dsx_pz, dsy_pz, -(dsx_pz * s.x + dsy_pz * s.y)};
+            const float3 dL_dk = {l.y * dL_dp.z - l.z * dL_dp.y, l.z * dL_dp.x - l.x * dL_dp.z,
+                                  l.x * dL_dp.y - l.y * dL_dp.x};
+            const float3 dL_dl = {dL_dp.y * k.z - dL_dp.z * k.y, dL_dp.z * k.x - dL_dp.x * k.z,
+                                  dL_dp.x * k.y - dL_dp.y * k.x};
+            g[0] = -dL_dk.x; g[1] = -dL_dk.y; g[2] = -dL_dk.z;
+            g[3] = -dL_dl.x; g[4] = -dL_dl.y; g[5] = -dL_dl.z;
+            g[6] = pixf.x * dL_dk.x + pixf.y * dL_dl.x + dL_dz * s.x;
+            g[7] = pixf.x * dL_dk.y + pixf.y * dL_dl.y + dL_dz * s.y;
+            g[8] = pixf.x * dL_dk.z + pixf.y * dL_dl.z + dL_dz;
+          } else {
+            const float fis = PART ? (float)(1 / (0.7071067811865476 * 0.7071067811865476)) : PGS_FILTER_INV_SQUARE;
+            g[9] = dL_dG * (-G * fis * d.x);
+            g[10] = dL_dG * (-G * fis * d.y);
+            g[8] = dL_dz;
+          }
+          g[11] = G * dL_dalpha;
+        }
+
+        const float r16 = warp_reduce16(g, lane);
+        const float r4 = warp_reduce4(gc, lane);
+        const uint32_t gid = st.id[j];
+        float* dst = a.grad + (size_t)gid * GRAD_FLOATS;
+        if ((lane & 1) == 0 && (lane >> 1) != 15) atomicAdd(dst + (lane >> 1), r16);
+        if ((lane & 7) == 0 && (lane >> 3) != 3) atomicAdd(dst + 16 + (lane >> 3), r4);
+        if (PART && S > 0) {
+          // dL/dsem[ch] = sum_pixels alpha*T * dL/dpixel_sem[ch]  (no alpha gradient in the reference fork)
+          float gs[16];
+#pragma unroll
+          for (int i = 0; i < 16; i++) gs[i] = w_sem * dL_dsem[i];
+          const float rs = warp_reduce16(gs, lane);
+          const int ch = lane >> 1;
+          if ((lane & 1) == 0 && ch < S) atomicAdd(a.grad_semantics + (size_t)gid * S + ch, rs);
+        }
+      }
+      __syncwarp();
+    }
+    id_cur = id_nxt;
+    id_nxt = id_n2;
+    box_cur = box_nxt;
+  }
+}
+
+// =============================================================================
+// launchers
+// =============================================================================
+template <bool PART> static void launch_fwd(const RenderFwdArgs& a, cudaStream_t s) {
+  const int ntiles = a.grid_x * a.grid_y;
+  const size_t dyn = PART ? (size_t)NWARP * CHUNK * MAX_SEMANTIC * sizeof(float) : 0;
+  render_fwd_kernel<PART><<<ntiles, TILE_PIX, dyn, s>>>(a);
+  count_launch();
+}
+void launch_render_fwd(const RenderFwdArgs& a, cudaStream_t s) { launch_fwd<false>(a, s); }
+void launch_render_fwd_part(const RenderFwdArgs& a, cudaStream_t s) { launch_fwd<true>(a, s); }
+
+template <bool PART> static void launch_bwd(const RenderBwdArgs& a, cudaStream_t s) {
+  const int ntiles = a.grid_x * a.grid_y;
+  render_bwd_kernel<PART><<<ntiles, TILE_PIX, 0, s>>>(a);
+  count_launch();
+}
+void launch_render_bwd(const RenderBwdArgs& a, cudaStream_t s) { launch_bwd<false>(a, s); }
+void launch_render_bwd_part(const RenderBwdArgs& a, cudaStream_t s) { launch_bwd<true>(a, s); }
+
+}  // namespace pgs
