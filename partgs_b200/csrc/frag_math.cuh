@@ -38,7 +38,7 @@ __device__ __forceinline__ bool frag_geometry(const float2 pixf, const float3 Tu
   f.p.x = __fmaf_rn(f.k.y, f.l.z, -__fmul_rn(f.k.z, f.l.y));
   f.p.y = __fmaf_rn(f.k.z, f.l.x, -__fmul_rn(f.k.x, f.l.z));
   f.p.z = __fmaf_rn(f.k.x, f.l.y, -__fmul_rn(f.k.y, f.l.x));
-  if (f.p.z == 0.0f) return false;
+  const bool ok = !(f.p.z == 0.0f);  // branch-free: a zero p.z only produces inf/nan that the caller discards
   f.s = make_float2(__fdiv_rn(f.p.x, f.p.z), __fdiv_rn(f.p.y, f.p.z));
   f.rho3d = __fmaf_rn(f.s.x, f.s.x, __fmul_rn(f.s.y, f.s.y));
   f.d = make_float2(__fsub_rn(xy.x, pixf.x), __fsub_rn(xy.y, pixf.y));
@@ -50,7 +50,7 @@ __device__ __forceinline__ bool frag_geometry(const float2 pixf, const float3 Tu
     f.rho2d = __fadd_rn(dd, dd);  // FilterInvSquare = 2
   }
   f.depth = (f.rho3d <= f.rho2d) ? __fadd_rn(Tw.z, __fmaf_rn(Tw.x, f.s.x, __fmul_rn(Tw.y, f.s.y))) : Tw.z;
-  return true;
+  return ok;
 }
 
 // alpha of a fragment: min(0.99, opacity * exp(-rho/2)).  `G` returns the Gaussian weight.
@@ -59,6 +59,23 @@ __device__ __forceinline__ float frag_alpha(float rho3d, float rho2d, float opa,
   power = __fmul_rn(-0.5f, rho);
   G = expf(power);
   return fminf(0.99f, __fmul_rn(opa, G));
+}
+
+// Forward-side evaluation of one fragment up to the `alpha < 1/255` test: true when the
+// reference would go on to the transmittance test / blending (forward.cu:350-383).  Does not
+// depend on the pixel's running state, so several fragments can be evaluated ahead of the blend.
+template <bool PART>
+__device__ __forceinline__ bool frag_eval(const float2 pixf, const float4 q0, const float4 q1, const float4 q2,
+                                          float& alpha, float& depth) {
+  FragGeom f;
+  bool ok = frag_geometry<PART>(pixf, make_float3(q0.x, q0.y, q0.z), make_float3(q1.x, q1.y, q1.z),
+                                make_float3(q2.x, q2.y, q2.z), make_float2(q0.w, q1.w), f);
+  depth = f.depth;
+  if (PART) ok = ok && !((double)depth < 0.2);
+  else ok = ok && !(depth < 0.2f);
+  float power, G;
+  alpha = frag_alpha(f.rho3d, f.rho2d, q2.w, power, G);
+  return ok && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
 }
 
 }  // namespace pgs

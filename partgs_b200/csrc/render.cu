@@ -171,30 +171,14 @@ __global__ void __launch_bounds__(TILE_PIX) render_fwd_kernel(RenderFwdArgs a) {
       cp_async_wait<0>();
       __syncwarp();
 
-      for (int j = 0; j < n; j++) {
-        if (done) continue;
-        const float4 q0 = st.rec[j][0];
-        const float4 q1 = st.rec[j][1];
-        const float4 q2 = st.rec[j][2];
-        const float3 Tu = {q0.x, q0.y, q0.z};
-        const float3 Tv = {q1.x, q1.y, q1.z};
-        const float3 Tw = {q2.x, q2.y, q2.z};
-        FragGeom f;
-        if (!frag_geometry<PART>(pixf, Tu, Tv, Tw, make_float2(q0.w, q1.w), f)) continue;
-        const float depth = f.depth;
-        if (PART) {
-          if ((double)depth < 0.2) continue;
-        } else {
-          if (depth < PGS_NEAR_N) continue;
-        }
-        float power, G;
-        const float alpha = frag_alpha(f.rho3d, f.rho2d, q2.w, power, G);
-        if (power > 0.0f) continue;
-        if (alpha < 1.0f / 255.0f) continue;
+      // Two fragments are evaluated (geometry, alpha: independent of the pixel's running state)
+      // before they are blended in order: doubles the ILP of the per-pixel dependency chain,
+      // which is what bounds the deepest tiles (thousands of fragments on the same pixels).
+      auto blend = [&](const int j, const float alpha, const float depth) {
         const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
         if (test_T < 0.0001f) {
           done = true;
-          continue;
+          return;
         }
         const float4 q3 = st.rec[j][3];
         const float4 q4 = st.rec[j][4];
@@ -247,6 +231,14 @@ __global__ void __launch_bounds__(TILE_PIX) render_fwd_kernel(RenderFwdArgs a) {
         }
         T = test_T;
         last_contributor = contributor;
+      };
+      for (int j = 0; j < n; j += 2) {
+        float alpha0, depth0, alpha1 = 0.f, depth1 = 0.f;
+        const bool ok0 = frag_eval<PART>(pixf, st.rec[j][0], st.rec[j][1], st.rec[j][2], alpha0, depth0);
+        bool ok1 = false;
+        if (j + 1 < n) ok1 = frag_eval<PART>(pixf, st.rec[j + 1][0], st.rec[j + 1][1], st.rec[j + 1][2], alpha1, depth1);
+        if (ok0 && !done) blend(j, alpha0, depth0);
+        if (ok1 && !done) blend(j + 1, alpha1, depth1);
       }
       __syncwarp();  // the ring is rewritten in the next step
     }
@@ -331,7 +323,7 @@ __device__ __forceinline__ float warp_reduce4(float (&c)[4], unsigned lane) {
 }
 
 template <bool PART>
-__global__ void __launch_bounds__(TILE_PIX) render_bwd_kernel(RenderBwdArgs a) {
+__global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(RenderBwdArgs a) {
   __shared__ WarpStage s_stage[NWARP];
 
   const int S = PART ? a.S : 0;
@@ -466,37 +458,42 @@ __global__ void __launch_bounds__(TILE_PIX) render_bwd_kernel(RenderBwdArgs a) {
         float w_sem = 0.f;
 
         if (valid) {
+          // Gradient arithmetic (not part of the replayed decisions): approximate reciprocals
+          // (MUFU.RCP, ~1 ulp) instead of IEEE divisions, both branches of the rho3d/rho2d
+          // choice evaluated and selected.  Gradients are gated at 1e-4 relative.
           const float4 q3 = st.rec[j][3];
           const float4 q4 = st.rec[j][4];
           const float normal[3] = {q3.x, q3.y, q3.z};
           const float col[3] = {q4.x, q4.y, q4.z};
-          const float3 k = f.k, l = f.l, p = f.p;
+          const float3 k = f.k, l = f.l;
           const float2 s = f.s, d = f.d;
 
-          T = __fdiv_rn(T, __fsub_rn(1.f, alpha));
-          const float dchannel_dcolor = alpha * T;
-          w_sem = dchannel_dcolor;
+          const float inv_1ma = __frcp_rn(1.f - alpha);
+          T = T * inv_1ma;
+          const float w = alpha * T;
+          w_sem = w;
+          const float one_m_la = 1.f - last_alpha;
           float dL_dalpha = 0.0f;
 #pragma unroll
           for (int ch = 0; ch < 3; ch++) {
             const float c = col[ch];
-            accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+            accum_rec[ch] = last_alpha * last_color[ch] + one_m_la * accum_rec[ch];
             last_color[ch] = c;
-            const float dL_dchannel = dL_dpixel[ch];
-            dL_dalpha += (c - accum_rec[ch]) * dL_dchannel;
-            gc[ch] = dchannel_dcolor * dL_dchannel;
+            dL_dalpha += (c - accum_rec[ch]) * dL_dpixel[ch];
+            gc[ch] = w * dL_dpixel[ch];
           }
 
-          float dL_dz = 0.0f;
-          float dL_dweight = 0;
+          const float inv_cd = __frcp_rn(c_d);
           float m_d, dmd_dd;
           if (PART) {
-            m_d = (100.0 * c_d - 100.0 * 0.2) / ((100.0 - 0.2) * c_d);
-            dmd_dd = (100.0 * 0.2) / ((100.0 - 0.2) * c_d * c_d);
+            m_d = (float)(100.0 / (100.0 - 0.2)) * (1.f - 0.2f * inv_cd);
+            dmd_dd = (float)(100.0 * 0.2 / (100.0 - 0.2)) * inv_cd * inv_cd;
           } else {
-            m_d = PGS_FAR_N / (PGS_FAR_N - PGS_NEAR_N) * (1 - PGS_NEAR_N / c_d);
-            dmd_dd = (PGS_FAR_N * PGS_NEAR_N) / ((PGS_FAR_N - PGS_NEAR_N) * c_d * c_d);
+            m_d = (PGS_FAR_N / (PGS_FAR_N - PGS_NEAR_N)) * (1.f - PGS_NEAR_N * inv_cd);
+            dmd_dd = ((PGS_FAR_N * PGS_NEAR_N) / (PGS_FAR_N - PGS_NEAR_N)) * inv_cd * inv_cd;
           }
+          float dL_dz = 0.0f;
+          float dL_dweight = 0;
           if (contributor == median_contributor - 1) {
             dL_dz += dL_dmedian_depth;
             if (PART) dL_dweight += dL_dmax_dweight;
@@ -504,51 +501,56 @@ __global__ void __launch_bounds__(TILE_PIX) render_bwd_kernel(RenderBwdArgs a) {
           dL_dweight += (final_D2 + m_d * m_d * final_A - 2 * m_d * final_D) * dL_dreg;
           dL_dalpha += dL_dweight - last_dL_dT;
           last_dL_dT = dL_dweight * alpha + (1 - alpha) * last_dL_dT;
-          const float dL_dmd = 2.0f * (T * alpha) * (m_d * final_A - final_D) * dL_dreg;
+          const float dL_dmd = 2.0f * w * (m_d * final_A - final_D) * dL_dreg;
           dL_dz += dL_dmd * dmd_dd;
 
-          accum_depth_rec = last_alpha * last_depth + (1.f - last_alpha) * accum_depth_rec;
+          accum_depth_rec = last_alpha * last_depth + one_m_la * accum_depth_rec;
           last_depth = c_d;
           dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
-          accum_alpha_rec = last_alpha * 1.0f + (1.f - last_alpha) * accum_alpha_rec;
+          accum_alpha_rec = last_alpha + one_m_la * accum_alpha_rec;
           dL_dalpha += (1 - accum_alpha_rec) * dL_daccum;
 
 #pragma unroll
           for (int ch = 0; ch < 3; ch++) {
-            accum_normal_rec[ch] = last_alpha * last_normal[ch] + (1.f - last_alpha) * accum_normal_rec[ch];
+            accum_normal_rec[ch] = last_alpha * last_normal[ch] + one_m_la * accum_normal_rec[ch];
             last_normal[ch] = normal[ch];
             dL_dalpha += (normal[ch] - accum_normal_rec[ch]) * dL_dnormal2D[ch];
-            g[12 + ch] = alpha * T * dL_dnormal2D[ch];
+            g[12 + ch] = w * dL_dnormal2D[ch];
           }
 
           dL_dalpha *= T;
           last_alpha = alpha;
-          dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+          dL_dalpha -= T_final * inv_1ma * bg_dot_dpixel;
 
           const float dL_dG = opa * dL_dalpha;
-          dL_dz += alpha * T * dL_ddepth;
-
-          if (f.rho3d <= f.rho2d) {
-            const float2 dL_ds = {dL_dG * -G * s.x + dL_dz * Tw.x, dL_dG * -G * s.y + dL_dz * Tw.y};
-            const float dsx_pz = dL_ds.x / p.z;
-            const float dsy_pz = dL_ds.y / p.z;
-            const float3 dL_dp = {dsx_pz, dsy_pz, -(dsx_pz * s.x + dsy_pz * s.y)};
-            const float3 dL_dk = {l.y * dL_dp.z - l.z * dL_dp.y, l.z * dL_dp.x - l.x * dL_dp.z,
-                                  l.x * dL_dp.y - l.y * dL_dp.x};
-            const float3 dL_dl = {dL_dp.y * k.z - dL_dp.z * k.y, dL_dp.z * k.x - dL_dp.x * k.z,
-                                  dL_dp.x * k.y - dL_dp.y * k.x};
-            g[0] = -dL_dk.x; g[1] = -dL_dk.y; g[2] = -dL_dk.z;
-            g[3] = -dL_dl.x; g[4] = -dL_dl.y; g[5] = -dL_dl.z;
-            g[6] = pixf.x * dL_dk.x + pixf.y * dL_dl.x + dL_dz * s.x;
-            g[7] = pixf.x * dL_dk.y + pixf.y * dL_dl.y + dL_dz * s.y;
-            g[8] = pixf.x * dL_dk.z + pixf.y * dL_dl.z + dL_dz;
-          } else {
-            const float fis = PART ? (float)(1 / (0.7071067811865476 * 0.7071067811865476)) : PGS_FILTER_INV_SQUARE;
-            g[9] = dL_dG * (-G * fis * d.x);
-            g[10] = dL_dG * (-G * fis * d.y);
-            g[8] = dL_dz;
-          }
+          dL_dz += w * dL_ddepth;
           g[11] = G * dL_dalpha;
+
+          const bool use3d = f.rho3d <= f.rho2d;
+          // ray-splat branch: gradient w.r.t. the 3x3 transform through s = p.xy / p.z
+          const float mGG = -G * dL_dG;
+          const float inv_pz = __frcp_rn(f.p.z);
+          const float dsx_pz = (mGG * s.x + dL_dz * Tw.x) * inv_pz;
+          const float dsy_pz = (mGG * s.y + dL_dz * Tw.y) * inv_pz;
+          const float3 dL_dp = {dsx_pz, dsy_pz, -(dsx_pz * s.x + dsy_pz * s.y)};
+          const float3 dL_dk = {l.y * dL_dp.z - l.z * dL_dp.y, l.z * dL_dp.x - l.x * dL_dp.z,
+                                l.x * dL_dp.y - l.y * dL_dp.x};
+          const float3 dL_dl = {dL_dp.y * k.z - dL_dp.z * k.y, dL_dp.z * k.x - dL_dp.x * k.z,
+                                dL_dp.x * k.y - dL_dp.y * k.x};
+          // low-pass branch: gradient w.r.t. the screen-space centre
+          const float fis = PART ? (float)(1 / (0.7071067811865476 * 0.7071067811865476)) : PGS_FILTER_INV_SQUARE;
+          const float mGGf = mGG * fis;
+          g[0] = use3d ? -dL_dk.x : 0.f;
+          g[1] = use3d ? -dL_dk.y : 0.f;
+          g[2] = use3d ? -dL_dk.z : 0.f;
+          g[3] = use3d ? -dL_dl.x : 0.f;
+          g[4] = use3d ? -dL_dl.y : 0.f;
+          g[5] = use3d ? -dL_dl.z : 0.f;
+          g[6] = use3d ? pixf.x * dL_dk.x + pixf.y * dL_dl.x + dL_dz * s.x : 0.f;
+          g[7] = use3d ? pixf.x * dL_dk.y + pixf.y * dL_dl.y + dL_dz * s.y : 0.f;
+          g[8] = use3d ? pixf.x * dL_dk.z + pixf.y * dL_dl.z + dL_dz : dL_dz;
+          g[9] = use3d ? 0.f : mGGf * d.x;
+          g[10] = use3d ? 0.f : mGGf * d.y;
         }
 
         const float r16 = warp_reduce16(g, lane);
