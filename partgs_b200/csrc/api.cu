@@ -84,7 +84,7 @@ struct GeomState {
   static GeomState from(char*& p, size_t P) {
     GeomState g;
     carve(p, g.rec, P * REC_QUADS);
-    carve(p, g.bbox, P);
+    carve(p, g.bbox, P * CULL_QUADS);
     carve(p, g.radii, P);
     carve(p, g.tiles_touched, P);
     carve(p, g.point_offsets, P);

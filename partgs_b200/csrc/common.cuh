@@ -40,6 +40,14 @@ constexpr int MEDIAN_WEIGHT_OFFSET = 7;  // _part fork only
 constexpr int REC_QUADS = 5;
 constexpr int REC_FLOATS = REC_QUADS * 4;
 
+// Per-surfel cull record (3 x float4 = 48 B), written by preprocess, read by the render kernels:
+//   c0 = conservative screen box {x0, y0, x1, y1} outside of which no pixel can pass alpha >= 1/255
+//   c1 = {a, b, c, d}, c2 = {e, g, cx, cy}: the conic  f(X,Y) = aX^2 + 2bXY + cY^2 + 2dX + 2eY + g
+//        (X = x - cx, Y = y - cy) whose non-positive set is exactly {rho3d <= c^2}; a pixel can
+//        only be blended if f <= 0 there or it lies within LOWPASS_RADIUS of (cx, cy).
+constexpr int CULL_QUADS = 3;
+#define PGS_LOWPASS_RADIUS 2.9f
+
 // Per-surfel gradient accumulator filled by the backward render kernel.
 //   [0..8] dL/dT (Tu,Tv,Tw)  [9,10] dL/dmean2D.xy  [11] dL/dopacity(G*dL_dalpha)
 //   [12..14] dL/dnormal(view) [15] pad  [16..18] dL/dcolor [19] pad

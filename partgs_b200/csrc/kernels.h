@@ -27,7 +27,7 @@ struct PreprocessFwdArgs {
   // outputs
   int* radii;
   float4* rec;    // [P][REC_QUADS]
-  float4* bbox;   // [P]
+  float4* bbox;   // [P][CULL_QUADS] cull records (box + conic)
   uint32_t* tiles_touched;
 };
 void launch_preprocess_fwd(const PreprocessFwdArgs& a, cudaStream_t s);

@@ -112,6 +112,9 @@ __device__ __forceinline__ void tile_rect(const float2 p, int max_radius, uint2&
               min(grid.y, max((int)0, (int)((p.y + max_radius + TILE_Y - 1) / TILE_Y)))};
 }
 
+// NOTE: keep this function exactly in this shape — its FMA contraction (decided by nvcc from the
+// expression tree and its surroundings) is what makes `rgb` bit-identical to the reference build;
+// a variant that first copied the coefficients to registers with 128-bit loads changed it.
 __device__ __forceinline__ v3 color_from_sh(int idx, int deg, int max_coeffs, const v3* means, v3 campos,
                                             const float* shs, unsigned& clamped_mask) {
   v3 pos = means[idx];
@@ -156,33 +159,65 @@ __device__ __forceinline__ v3 color_from_sh(int idx, int deg, int max_coeffs, co
 // Evaluated in fp64 with margins; falls back to "everything" when the projected
 // conic is not an ellipse.  This is new relative to the reference (which visits
 // every pixel of every binned tile); it does not change any result.
-__device__ __forceinline__ float4 cull_box(const m3& T, float2 xy, float opa) {
+__device__ __forceinline__ void cull_record(const m3& T, float2 xy, float opa, float4* out) {
   const float BIG = 3.0e38f;
-  float4 all = {-BIG, -BIG, BIG, BIG};
-  if (!(opa > 0.f)) return make_float4(BIG, BIG, -BIG, -BIG);  // alpha <= 0 < 1/255 always
+  const float4 none = make_float4(BIG, BIG, -BIG, -BIG);
+  const float4 all = make_float4(-BIG, -BIG, BIG, BIG);
+  // conic "always passes" (g = -BIG) unless computed below
+  out[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  out[2] = make_float4(0.f, -BIG, xy.x, xy.y);
+  if (!(opa > 0.f)) { out[0] = none; return; }  // alpha <= 0 < 1/255 always
   double c2 = 2.0 * log(255.0 * (double)opa);
   c2 = c2 * 1.02 + 0.05;
-  if (c2 <= 0.0) return make_float4(BIG, BIG, -BIG, -BIG);
-  double ux = T[0].x, uy = T[0].y, uz = T[0].z;
-  double vx = T[1].x, vy = T[1].y, vz = T[1].z;
-  double wx = T[2].x, wy = T[2].y, wz = T[2].z;
-  double wn = c2 * (wx * wx + wy * wy);
-  // disk of radius c must be strictly in front: wz > c*|(wx,wy)| with slack
-  if (!(wz > 0.0) || !(wz * wz > wn * 1.0201)) return all;
-  double d = wn - wz * wz;  // < 0
-  double inv = 1.0 / d;
-  double cx = (c2 * (ux * wx + uy * wy) - uz * wz) * inv;
-  double cy = (c2 * (vx * wx + vy * wy) - vz * wz) * inv;
-  double hx2 = cx * cx - (c2 * (ux * ux + uy * uy) - uz * uz) * inv;
-  double hy2 = cy * cy - (c2 * (vx * vx + vy * vy) - vz * vz) * inv;
-  if (!(hx2 >= 0.0) || !(hy2 >= 0.0) || !isfinite(hx2) || !isfinite(hy2)) return all;
-  double hx = sqrt(hx2) * 1.01 + 0.5;
-  double hy = sqrt(hy2) * 1.01 + 0.5;
-  double r2 = sqrt(0.5 * c2) + 0.5;
-  double x0 = fmin(cx - hx, (double)xy.x - r2), x1 = fmax(cx + hx, (double)xy.x + r2);
-  double y0 = fmin(cy - hy, (double)xy.y - r2), y1 = fmax(cy + hy, (double)xy.y + r2);
-  if (!isfinite(x0) || !isfinite(x1) || !isfinite(y0) || !isfinite(y1)) return all;
-  return make_float4(__double2float_rd(x0), __double2float_rd(y0), __double2float_ru(x1), __double2float_ru(y1));
+  if (c2 <= 0.0) { out[0] = none; return; }
+  const double ux = T[0].x, uy = T[0].y, uz = T[0].z;
+  const double vx = T[1].x, vy = T[1].y, vz = T[1].z;
+  const double wx = T[2].x, wy = T[2].y, wz = T[2].z;
+
+  // ---- conic: p(x,y) = x*(Tv x Tw) + y*(Tw x Tu) + (Tu x Tv);  rho3d <= c2  <=>  p.x^2 + p.y^2 - c2 p.z^2 <= 0
+  // (holds for every conic type, no front-facing assumption).  Centred on the low-pass centre and
+  // normalised; only used when opa <= 1 so that the fixed low-pass radius bound is valid.
+  if (opa <= 1.0f) {
+    const double a1x = vy * wz - vz * wy, a1y = vz * wx - vx * wz, a1z = vx * wy - vy * wx;
+    const double a2x = wy * uz - wz * uy, a2y = wz * ux - wx * uz, a2z = wx * uy - wy * ux;
+    const double a0x = uy * vz - uz * vy, a0y = uz * vx - ux * vz, a0z = ux * vy - uy * vx;
+    const double cx = xy.x, cy = xy.y;
+    // p at the centre
+    const double p0x = a1x * cx + a2x * cy + a0x, p0y = a1y * cx + a2y * cy + a0y, p0z = a1z * cx + a2z * cy + a0z;
+    double qa = a1x * a1x + a1y * a1y - c2 * a1z * a1z;
+    double qb = a1x * a2x + a1y * a2y - c2 * a1z * a2z;
+    double qc = a2x * a2x + a2y * a2y - c2 * a2z * a2z;
+    double qd = a1x * p0x + a1y * p0y - c2 * a1z * p0z;
+    double qe = a2x * p0x + a2y * p0y - c2 * a2z * p0z;
+    double qg = p0x * p0x + p0y * p0y - c2 * p0z * p0z;
+    const double sc = fmax(fmax(fabs(qa), fabs(qc)), fabs(qb));
+    if (sc > 0.0 && isfinite(sc) && isfinite(qd) && isfinite(qe) && isfinite(qg)) {
+      const double inv = 1.0 / sc;
+      out[1] = make_float4((float)(qa * inv), (float)(qb * inv), (float)(qc * inv), (float)(qd * inv));
+      const float ge = (float)(qe * inv);
+      const float gg = __double2float_rd(qg * inv);
+      if (isfinite(out[1].w) && isfinite(ge) && isfinite(gg)) out[2] = make_float4(ge, gg, xy.x, xy.y);
+      else out[2] = make_float4(0.f, -BIG, xy.x, xy.y);
+    }
+  }
+
+  // ---- box of the c-sigma ellipse (only when the whole c-sigma disk is in front of the camera plane)
+  const double wn = c2 * (wx * wx + wy * wy);
+  if (!(wz > 0.0) || !(wz * wz > wn * 1.0201)) { out[0] = all; return; }
+  const double d = wn - wz * wz;  // < 0
+  const double inv = 1.0 / d;
+  const double cx = (c2 * (ux * wx + uy * wy) - uz * wz) * inv;
+  const double cy = (c2 * (vx * wx + vy * wy) - vz * wz) * inv;
+  const double hx2 = cx * cx - (c2 * (ux * ux + uy * uy) - uz * uz) * inv;
+  const double hy2 = cy * cy - (c2 * (vx * vx + vy * vy) - vz * vz) * inv;
+  if (!(hx2 >= 0.0) || !(hy2 >= 0.0) || !isfinite(hx2) || !isfinite(hy2)) { out[0] = all; return; }
+  const double hx = sqrt(hx2) * 1.01 + 0.5;
+  const double hy = sqrt(hy2) * 1.01 + 0.5;
+  const double r2 = sqrt(0.5 * c2) + 0.5;
+  const double x0 = fmin(cx - hx, (double)xy.x - r2), x1 = fmax(cx + hx, (double)xy.x + r2);
+  const double y0 = fmin(cy - hy, (double)xy.y - r2), y1 = fmax(cy + hy, (double)xy.y + r2);
+  if (!isfinite(x0) || !isfinite(x1) || !isfinite(y0) || !isfinite(y1)) { out[0] = all; return; }
+  out[0] = make_float4(__double2float_rd(x0), __double2float_rd(y0), __double2float_ru(x1), __double2float_ru(y1));
 }
 
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessFwdArgs a) {
@@ -251,7 +286,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessFwdArgs a
   rec[2] = make_float4(T[2].x, T[2].y, T[2].z, opa);
   rec[3] = make_float4(normal.x, normal.y, normal.z, p_view.z);
   rec[4] = make_float4(r, g, b, __uint_as_float(clamped));
-  a.bbox[idx] = cull_box(T, point_image, opa);
+  cull_record(T, point_image, opa, a.bbox + (size_t)idx * CULL_QUADS);
 
   a.radii[idx] = (int)radius;
   a.tiles_touched[idx] = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
@@ -359,7 +394,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_part_kernel(PreprocessFwdA
   rec[2] = make_float4(T[2].x, T[2].y, T[2].z, opa);
   rec[3] = make_float4(normal.x, normal.y, normal.z, p_view.z);
   rec[4] = make_float4(r, g, b, __uint_as_float(clamped));
-  a.bbox[idx] = cull_box(T, center, opa);
+  cull_record(T, center, opa, a.bbox + (size_t)idx * CULL_QUADS);
   a.radii[idx] = (int)radius;
   a.tiles_touched[idx] = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
 }

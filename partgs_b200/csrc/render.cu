@@ -47,6 +47,43 @@ __device__ __forceinline__ bool box_hits(const float4 b, float x0, float y0, flo
   return !(b.x > x1 || b.z < x0 || b.y > y1 || b.w < y0);
 }
 
+// Second-level cull (after the box): can any pixel centre of the footprint [x0,x1]x[y0,y1] pass
+// the reference's alpha >= 1/255 test?  Only if the footprint meets {f <= 0} (f = the surfel's
+// conic, see common.cuh) or the low-pass disc around (cx, cy).  The minimum of the quadratic f
+// over the rectangle is attained at the interior critical point (convex case) or on an edge.
+__device__ __forceinline__ bool conic_hits(const float4 c1, const float4 c2, float x0, float y0, float x1, float y1) {
+  const float a = c1.x, b = c1.y, c = c1.z, d = c1.w, e = c2.x, g = c2.y;
+  const float X0 = x0 - c2.z, X1 = x1 - c2.z, Y0 = y0 - c2.w, Y1 = y1 - c2.w;
+  // low-pass disc: distance from the centre to the rectangle
+  const float ddx = fmaxf(fmaxf(X0, -X1), 0.f), ddy = fmaxf(fmaxf(Y0, -Y1), 0.f);
+  if (ddx * ddx + ddy * ddy <= PGS_LOWPASS_RADIUS * PGS_LOWPASS_RADIUS) return true;
+  auto f = [&](float X, float Y) { return (a * X + 2.f * (b * Y + d)) * X + (c * Y + 2.f * e) * Y + g; };
+  float fmin_ = fminf(fminf(f(X0, Y0), f(X1, Y0)), fminf(f(X0, Y1), f(X1, Y1)));
+  // edges Y = const: a X^2 + 2 (bY + d) X + ...,  vertex at X = -(bY + d)/a when a > 0
+  if (a > 0.f) {
+    const float ia = __frcp_rn(a);
+    const float xa = fminf(fmaxf(-(b * Y0 + d) * ia, X0), X1), xb = fminf(fmaxf(-(b * Y1 + d) * ia, X0), X1);
+    fmin_ = fminf(fmin_, fminf(f(xa, Y0), f(xb, Y1)));
+  }
+  if (c > 0.f) {
+    const float ic = __frcp_rn(c);
+    const float ya = fminf(fmaxf(-(b * X0 + e) * ic, Y0), Y1), yb = fminf(fmaxf(-(b * X1 + e) * ic, Y0), Y1);
+    fmin_ = fminf(fmin_, fminf(f(X0, ya), f(X1, yb)));
+  }
+  // interior critical point (global minimum when the quadratic part is positive definite)
+  const float det = a * c - b * b;
+  if (a > 0.f && det > 0.f) {
+    const float idet = __frcp_rn(det);
+    const float xc = (b * e - c * d) * idet, yc = (b * d - a * e) * idet;
+    if (xc >= X0 && xc <= X1 && yc >= Y0 && yc <= Y1) fmin_ = fminf(fmin_, f(xc, yc));
+  }
+  // slack for the fp32 evaluation: 1e-5 x (sum of |terms| at the farthest corner); coefficients are
+  // normalised to max(|a|,|b|,|c|) = 1.  NaN compares false -> keep the surfel.
+  const float mx = fmaxf(fmaxf(fabsf(X0), fabsf(X1)), fmaxf(fabsf(Y0), fabsf(Y1)));
+  const float slack = 0.05f + 1e-5f * (4.f * mx * mx + 2.f * (fabsf(d) + fabsf(e)) * mx + fabsf(g));
+  return !(fmin_ > slack);
+}
+
 // =============================================================================
 // tile order: longest list first (approximate LPT by counting sort on len/16)
 // =============================================================================
@@ -98,7 +135,7 @@ void launch_tile_order(const uint2* ranges, int ntiles, uint32_t* order, cudaStr
 // forward
 // =============================================================================
 template <bool PART>
-__global__ void __launch_bounds__(TILE_PIX) render_fwd_kernel(RenderFwdArgs a) {
+__global__ void __launch_bounds__(TILE_PIX, PART ? 3 : 4) render_fwd_kernel(RenderFwdArgs a) {
   __shared__ WarpStage s_stage[NWARP];
   extern __shared__ float s_sem_dyn[];  // PART: [NWARP][CHUNK][MAX_SEMANTIC]
 
@@ -142,7 +179,7 @@ __global__ void __launch_bounds__(TILE_PIX) render_fwd_kernel(RenderFwdArgs a) {
   float4 box_cur = nobox;
   if ((int)lane < total) id_cur = list[lane];
   if ((int)lane + CHUNK < total) id_nxt = list[lane + CHUNK];
-  if ((int)lane < total) box_cur = __ldg(&a.bbox[id_cur]);
+  if ((int)lane < total) box_cur = __ldg(&a.bbox[(size_t)id_cur * CULL_QUADS]);
 
   for (int base = 0; base < total; base += CHUNK) {
     if (__all_sync(RFULL, done)) break;
@@ -150,9 +187,13 @@ __global__ void __launch_bounds__(TILE_PIX) render_fwd_kernel(RenderFwdArgs a) {
     uint32_t id_n2 = 0;
     if (base + 2 * CHUNK + (int)lane < total) id_n2 = list[base + 2 * CHUNK + lane];
     float4 box_nxt = nobox;
-    if (base + CHUNK + (int)lane < total) box_nxt = __ldg(&a.bbox[id_nxt]);
+    if (base + CHUNK + (int)lane < total) box_nxt = __ldg(&a.bbox[(size_t)id_nxt * CULL_QUADS]);
 
-    const bool hit = box_hits(box_cur, wx0, wy0, wx1, wy1);  // lanes past the end carry `nobox`
+    bool hit = box_hits(box_cur, wx0, wy0, wx1, wy1);  // lanes past the end carry `nobox`
+    if (hit) {
+      const float4* cr = a.bbox + (size_t)id_cur * CULL_QUADS;
+      hit = conic_hits(__ldg(cr + 1), __ldg(cr + 2), wx0, wy0, wx1, wy1);
+    }
     const unsigned m = __ballot_sync(RFULL, hit);
     const int n = __popc(m);
     if (n > 0) {
@@ -404,15 +445,19 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(Rend
   float4 box_cur = nobox;
   if ((int)lane < total) id_cur = list[total - 1 - lane];
   if ((int)lane + CHUNK < total) id_nxt = list[total - 1 - lane - CHUNK];
-  if ((int)lane < total) box_cur = __ldg(&a.bbox[id_cur]);
+  if ((int)lane < total) box_cur = __ldg(&a.bbox[(size_t)id_cur * CULL_QUADS]);
 
   for (int base = 0; base < total; base += CHUNK) {
     uint32_t id_n2 = 0;
     if (base + 2 * CHUNK + (int)lane < total) id_n2 = list[total - 1 - (base + 2 * CHUNK + lane)];
     float4 box_nxt = nobox;
-    if (base + CHUNK + (int)lane < total) box_nxt = __ldg(&a.bbox[id_nxt]);
+    if (base + CHUNK + (int)lane < total) box_nxt = __ldg(&a.bbox[(size_t)id_nxt * CULL_QUADS]);
 
-    const bool hit = box_hits(box_cur, wx0, wy0, wx1, wy1);
+    bool hit = box_hits(box_cur, wx0, wy0, wx1, wy1);
+    if (hit) {
+      const float4* cr = a.bbox + (size_t)id_cur * CULL_QUADS;
+      hit = conic_hits(__ldg(cr + 1), __ldg(cr + 2), wx0, wy0, wx1, wy1);
+    }
     const unsigned m = __ballot_sync(RFULL, hit);
     const int n = __popc(m);
     if (n > 0) {

@@ -49,7 +49,8 @@ def parse_state(geom: torch.Tensor, img: torch.Tensor, binning: torch.Tensor, P:
         depths=rec[:, 15],
         rgb=rec[:, 16:19],
         clamped_mask=rec[:, 19].contiguous().view(torch.int32),
-        bbox=_view(geom, lay.geom_bbox, 16 * P, torch.float32, (P, 4)),
+        bbox=_view(geom, lay.geom_bbox, 48 * P, torch.float32, (P, 12))[:, :4],
+        cull=_view(geom, lay.geom_bbox, 48 * P, torch.float32, (P, 12)),
         internal_radii=_view(geom, lay.geom_radii, 4 * P, torch.int32, (P,)),
         tiles_touched=_view(geom, lay.geom_tiles_touched, 4 * P, torch.int32, (P,)),
         point_offsets=_view(geom, lay.geom_point_offsets, 4 * P, torch.int32, (P,)),
