@@ -51,54 +51,86 @@ def dist_setup(n_gpus: int):
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle-reason samples DURING the timed region, read through NVML (pynvml) from
+    a background thread.  (An `nvidia-smi -lms` subprocess polling power/clock fields was measured
+    to stall this process's kernel launches for milliseconds per poll; two NVML getters do not.)
+    Falls back to one nvidia-smi query per 250 ms if pynvml is unavailable."""
 
-    def __init__(self, gpu_index: int):
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+
+    def __init__(self, gpu_index: int, period_s: float = 0.025):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.period = period_s
+        self.samples = []
+        self.mask = 0
+        self.smax = None
+        self._stop = threading.Event()
+        self.thread = None
+        self.nvml = None
+
+    def _run_nvml(self):
+        n = self.nvml
+        h = n.nvmlDeviceGetHandleByIndex(self.gpu)
+        try:
+            self.smax = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+        except Exception:
+            self.smax = None
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    self.mask |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def _run_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.smax = float(f[1])
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     f[2:6]):
+                    if val.lower().startswith("active"):
+                        self.mask |= self.REASONS[name]
+            except Exception:
+                pass
+            self._stop.wait(0.25)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
-                 str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            # CUDA_VISIBLE_DEVICES remaps indices for CUDA but not for NVML
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    self.gpu = int(vis.split(",")[self.gpu])
+                except Exception:
+                    pass
+            target = self._run_nvml
         except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            target = self._run_smi
+        self.thread = threading.Thread(target=target, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sampler"], "samples": 0}
+        self._stop.set()
+        self.thread.join(timeout=6)
+        reasons = sorted(k for k, bit in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.smax,
+                "reasons": reasons, "samples": len(self.samples),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peak():
@@ -245,7 +277,10 @@ def run(args):
         torch.cuda.synchronize()
 
     # ---- warm-up ---------------------------------------------------------------------
-    for i in range(max(args.warmup, 3)):
+    # W warm-up steps; additionally every camera of this rank is rendered once (untimed) so that
+    # the caching allocator has seen each view's instance count before the timed region
+    n_warm = max(args.warmup, 3)
+    for i in range(max(n_warm, min(len(my_cams), 64))):
         one_step(i)
     for h in pending:
         h.wait()

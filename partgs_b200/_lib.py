@@ -116,14 +116,24 @@ class ByteBuffer:
     """Growable device byte buffer handed to the library through the alloc callback
     (the role resizeFunctional plays in the reference glue, rasterize_points.cu:31-37)."""
 
-    def __init__(self, device):
+    # grow-only high-water marks per (device, tag): requesting the same size every frame lets
+    # torch's caching allocator hand back the same block instead of growing / fragmenting when the
+    # number of surfel-tile instances changes from view to view
+    _hwm = {}
+
+    def __init__(self, device, tag=None):
         self.device = device
         self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
         self.error = None
 
         def _cb(nbytes, _user):
             try:
-                self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+                nbytes = int(nbytes)
+                if tag is not None:
+                    key = (str(self.device), tag)
+                    nbytes = max(nbytes, ByteBuffer._hwm.get(key, 0))
+                    ByteBuffer._hwm[key] = nbytes
+                self.tensor = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
                 return self.tensor.data_ptr()
             except Exception as ex:  # surfaced by the caller; returning NULL makes the C side fail cleanly
                 self.error = ex

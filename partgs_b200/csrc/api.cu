@@ -118,10 +118,12 @@ struct BinningState {
   static BinningState from(char*& p, size_t R_exact, int end_bit) {
     const size_t R = align_up(R_exact > 0 ? R_exact : 1, (size_t)1 << 19);
     BinningState b;
-    carve(p, b.keys_a, R);
-    carve(p, b.keys_b, R);
+    // vals_a first: the final point list always ends up there, at an offset that does not depend
+    // on R, so the caller may hand in a larger (grow-only) buffer than requested
     carve(p, b.vals_a, R);
     carve(p, b.vals_b, R);
+    carve(p, b.keys_a, R);
+    carve(p, b.keys_b, R);
     carve(p, b.sort_temp, radix_sort_temp_bytes((int)R, end_bit));
     return b;
   }
@@ -196,7 +198,7 @@ int pgs_dsr_get_layout(int P, int width, int height, int R, pgs_dsr_layout* out)
     out->binning_bytes = (size_t)p + 256;
     const bool in_b = ((end_bit + 7) / 8) & 1;
     out->binning_keys_sorted = in_b ? (size_t)b.keys_b : (size_t)b.keys_a;
-    out->binning_point_list = in_b ? (size_t)b.vals_b : (size_t)b.vals_a;
+    out->binning_point_list = (size_t)b.vals_a;
   }
   out->rec_floats = REC_FLOATS;
   out->tile_pixels = TILE_PIX;
@@ -293,7 +295,9 @@ static int forward_impl(bool part, int S, const float* semantics, float* out_sem
                                       bin.sort_temp, s); }
     if (int e = check_cuda("radix_sort")) return e;
     const uint64_t* sorted_keys = where ? bin.keys_b : bin.keys_a;
-    point_list = where ? bin.vals_b : bin.vals_a;
+    if (where)  // odd number of digit passes (<= 256 tiles): bring the sorted values home
+      cudaMemcpyAsync(bin.vals_a, bin.vals_b, (size_t)num_rendered * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
+    point_list = bin.vals_a;
     { StageTimer t(PGS_STAGE_TILE_RANGES, s); launch_identify_tile_ranges(num_rendered, sorted_keys, img.ranges, s); }
     if (int e = check_cuda("identify_tile_ranges")) return e;
     if (debug) if (int e = check_sync(s, "binning")) return e;
@@ -387,7 +391,7 @@ static int backward_impl(bool part, int S, const float* semantics, const float* 
   const uint32_t* point_list = nullptr;
   if (R > 0) {
     BinningState bin = BinningState::from(binning_buffer, R, end_bit);
-    point_list = (((end_bit + 7) / 8) & 1) ? bin.vals_b : bin.vals_a;
+    point_list = bin.vals_a;
   }
 
   float* grad = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(scratch), 256));

@@ -56,7 +56,7 @@ def _native_forward(bg, means3D, colors, opacity, scales, rotations, scale_modif
     out_color = torch.empty((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
     out_others = torch.empty((NUM_AUX, H, W), dtype=torch.float32, device=dev)
     radii = torch.empty((P,), dtype=torch.int32, device=dev)
-    geom, binning, img = _lib.ByteBuffer(dev), _lib.ByteBuffer(dev), _lib.ByteBuffer(dev)
+    geom, binning, img = _lib.ByteBuffer(dev), _lib.ByteBuffer(dev, tag="binning"), _lib.ByteBuffer(dev)
     rendered = 0
     if P != 0:
         M = sh.size(1) if sh.numel() != 0 else 0

@@ -58,7 +58,7 @@ def _native_forward(bg, means3D, colors, opacity, semantics, scales, rotations, 
     out_semantic = torch.empty((S, H, W), **f32)
     out_others = torch.empty((NUM_AUX, H, W), **f32)
     radii = torch.empty((P,), dtype=torch.int32, device=dev)
-    geom, binning, img = _lib.ByteBuffer(dev), _lib.ByteBuffer(dev), _lib.ByteBuffer(dev)
+    geom, binning, img = _lib.ByteBuffer(dev), _lib.ByteBuffer(dev, tag="binning"), _lib.ByteBuffer(dev)
     rendered = 0
     if P != 0:
         M = sh.size(1) if sh.numel() != 0 else 0
