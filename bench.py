@@ -262,7 +262,9 @@ def run(args):
             h.wait()
         pending.clear()
         if world > 1:
-            for t in grads:
+            from partgs_b200.dist import grad_bucket
+            bucket = grad_bucket(grads)  # ours: the five gradients are views of one flat buffer
+            for t in ([bucket] if bucket is not None else grads):
                 pending.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
 
     def one_step(i):
@@ -280,7 +282,8 @@ def run(args):
     # W warm-up steps; additionally every camera of this rank is rendered once (untimed) so that
     # the caching allocator has seen each view's instance count before the timed region
     n_warm = max(args.warmup, 3)
-    for i in range(max(n_warm, min(len(my_cams), 64))):
+    views_per_rank = (len(all_cams) + world - 1) // world  # same count on every rank (collectives must match)
+    for i in range(max(n_warm, min(views_per_rank, 64))):
         one_step(i)
     for h in pending:
         h.wait()

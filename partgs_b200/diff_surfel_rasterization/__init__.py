@@ -79,6 +79,20 @@ def _native_forward(bg, means3D, colors, opacity, scales, rotations, scale_modif
     return rendered, out_color, out_others, radii, geom.tensor, binning.tensor, img.tensor
 
 
+def _carve_bucket(dev, shapes, align_elems=64):
+    """Views of the given shapes into one flat float32 buffer (each view 256-byte aligned).
+    The views' ``_base`` is the bucket itself."""
+    offs, total = [], 0
+    for shp in shapes:
+        n = 1
+        for d in shp:
+            n *= int(d)
+        offs.append((total, n))
+        total += (n + align_elems - 1) // align_elems * align_elems
+    flat = torch.empty((max(total, 1),), dtype=torch.float32, device=dev)
+    return [flat[o:o + n].view(*shp) for (o, n), shp in zip(offs, shapes)]
+
+
 def _native_backward(bg, means3D, radii, colors, scales, rotations, scale_modifier, transMat_precomp, viewmatrix,
                      projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_others, sh, degree, campos, geomBuffer, R,
                      binningBuffer, imageBuffer, debug):
@@ -89,15 +103,15 @@ def _native_backward(bg, means3D, radii, colors, scales, rotations, scale_modifi
     H, W = dL_dout_color.size(1), dL_dout_color.size(2)
     M = sh.size(1) if sh.numel() != 0 else 0
     f32 = dict(dtype=torch.float32, device=dev)
-    # every row is written by the kernels -> torch.empty, no 304 B/surfel zero fill
-    dL_dmeans3D = torch.empty((P, 3), **f32)
+    # every row is written by the kernels -> torch.empty, no 304 B/surfel zero fill.
+    # The five parameter gradients (232 B/surfel) are carved out of ONE flat buffer ("gradient
+    # bucket"): the backward-preprocess kernel writes them in place, and a data-parallel caller can
+    # all-reduce the whole bucket with a single collective (see partgs_b200.dist.grad_bucket).
+    dL_dmeans3D, dL_dsh, dL_dopacity, dL_dscales, dL_drotations = _carve_bucket(
+        dev, [(P, 3), (P, M, 3), (P, 1), (P, 2), (P, 4)])
     dL_dmeans2D = torch.empty((P, 3), **f32)
     dL_dcolors = torch.empty((P, NUM_CHANNELS), **f32)
-    dL_dopacity = torch.empty((P, 1), **f32)
     dL_dtransMat = torch.empty((P, 9), **f32)
-    dL_dsh = torch.empty((P, M, 3), **f32)
-    dL_dscales = torch.empty((P, 2), **f32)
-    dL_drotations = torch.empty((P, 4), **f32)
     if P != 0:
         means3D = means3D.contiguous()
         dL_dout_color = _lib.require_cuda_float(dL_dout_color, "dL_dout_color")

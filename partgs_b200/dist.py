@@ -24,6 +24,21 @@ def shard_views(n_views: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_views, world))
 
 
+def grad_bucket(grads: Iterable[torch.Tensor]):
+    """If all gradients are views into one flat buffer (the rasteriser's backward carves its five
+    parameter gradients out of a single allocation), return that buffer so that one collective
+    reduces everything; otherwise None."""
+    base = None
+    for g in grads:
+        if g is None:
+            continue
+        b = g._base
+        if b is None or (base is not None and b is not base):
+            return None
+        base = b
+    return base
+
+
 class GradAllReducer:
     """Asynchronous per-parameter-group gradient all-reduce (SUM)."""
 
@@ -39,6 +54,10 @@ class GradAllReducer:
     def launch(self, tensors: Iterable[torch.Tensor]):
         if self.world == 1:
             return
+        tensors = list(tensors)
+        bucket = grad_bucket(tensors)
+        if bucket is not None:
+            tensors = [bucket]  # one collective for the whole 232 B/surfel bucket
         for t in tensors:
             if t is None:
                 continue
