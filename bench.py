@@ -298,6 +298,7 @@ def run(args):
     if rank == 0:
         clocks.start()
     l0 = arm.launches()
+    mem0 = torch.cuda.memory_stats(dev)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -310,6 +311,7 @@ def run(args):
     barrier()
     t_ms = e0.elapsed_time(e1)
     l1 = arm.launches()
+    mem1 = torch.cuda.memory_stats(dev)
     stage = None
     if arm.name == "ours":
         stage = arm._lib.timing_read(reset=True)
@@ -406,6 +408,7 @@ def run(args):
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                 "d2h_bytes_per_step": 4},
         "gpu_launches": int(l1 - l0),
+        "device_mallocs_in_timed_region": int(mem1.get("num_device_alloc", 0) - mem0.get("num_device_alloc", 0)),
         "clocks": clock_info,
         "frame_roofline": {"algorithmic_bytes": int(a_f + a_b), "achieved_gbs": round((a_f + a_b) / (t_ms / args.steps * 1e-3) / 1e9, 1),
                            "peak_gbs": peak, "frac": round((a_f + a_b) / (t_ms / args.steps * 1e-3) / 1e9 / peak, 4)},

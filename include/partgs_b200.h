@@ -171,6 +171,8 @@ typedef struct {
   size_t geom_bytes, geom_rec, geom_bbox, geom_radii, geom_tiles_touched, geom_point_offsets;
   size_t image_bytes, image_final_T, image_n_contrib, image_ranges;
   size_t binning_bytes, binning_keys_sorted, binning_point_list;
+  size_t binning_frag_mask; /* u32 [8 warps][binning_mask_stride]: pixels of each warp footprint that blended instance i */
+  size_t binning_mask_stride;
   int rec_floats;  /* floats per surfel record */
   int tile_pixels; /* per-pixel state is tile-major [tile][256] */
 } pgs_dsr_layout;

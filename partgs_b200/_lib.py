@@ -23,7 +23,7 @@ class DsrLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in (
         "geom_bytes", "geom_rec", "geom_bbox", "geom_radii", "geom_tiles_touched", "geom_point_offsets",
         "image_bytes", "image_final_T", "image_n_contrib", "image_ranges",
-        "binning_bytes", "binning_keys_sorted", "binning_point_list")] + [
+        "binning_bytes", "binning_keys_sorted", "binning_point_list", "binning_frag_mask", "binning_mask_stride")] + [
         ("rec_floats", C.c_int), ("tile_pixels", C.c_int)]
 
 
@@ -114,12 +114,15 @@ def current_stream(device) -> int:
 
 class ByteBuffer:
     """Growable device byte buffer handed to the library through the alloc callback
-    (the role resizeFunctional plays in the reference glue, rasterize_points.cu:31-37)."""
+    (the role resizeFunctional plays in the reference glue, rasterize_points.cu:31-37).
 
-    # grow-only high-water marks per (device, tag): requesting the same size every frame lets
-    # torch's caching allocator hand back the same block instead of growing / fragmenting when the
-    # number of surfel-tile instances changes from view to view
-    _hwm = {}
+    Tagged buffers (the per-instance binning arena, whose size changes with every view) come from a
+    small grow-only pool per (device, stream, tag) instead of a fresh ``torch.empty`` per frame: a
+    frame-to-frame varying request of a few hundred MB makes the caching allocator split / re-grow
+    segments (cudaMalloc inside the step).  An arena is handed out again only when nothing but the
+    pool references it any more (autograd has released the previous frame's saved state)."""
+
+    _pool = {}
 
     def __init__(self, device, tag=None):
         self.device = device
@@ -129,17 +132,34 @@ class ByteBuffer:
         def _cb(nbytes, _user):
             try:
                 nbytes = int(nbytes)
-                if tag is not None:
-                    key = (str(self.device), tag)
-                    nbytes = max(nbytes, ByteBuffer._hwm.get(key, 0))
-                    ByteBuffer._hwm[key] = nbytes
-                self.tensor = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                if tag is None:
+                    self.tensor = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                else:
+                    self.tensor = self._from_pool(nbytes, tag)
                 return self.tensor.data_ptr()
             except Exception as ex:  # surfaced by the caller; returning NULL makes the C side fail cleanly
                 self.error = ex
                 return None
 
         self.callback = ALLOC_FN(_cb)
+
+    def _from_pool(self, nbytes, tag):
+        import sys
+        key = (str(self.device), torch.cuda.current_stream(self.device).cuda_stream, tag)
+        pool = ByteBuffer._pool.setdefault(key, [])
+        hwm = max([nbytes] + [t.numel() for t in pool])
+        for i in range(len(pool)):
+            t = pool[i]
+            # free <=> only the pool list, the local `t` and getrefcount's argument reference the Python
+            # object, and no C++ owner (autograd's saved tensors) holds the TensorImpl
+            if t._use_count() == 1 and sys.getrefcount(t) <= 3:
+                if t.numel() < nbytes:
+                    t = torch.empty(hwm, dtype=torch.uint8, device=self.device)  # grow: replace the small arena
+                    pool[i] = t
+                return t
+        t = torch.empty(hwm, dtype=torch.uint8, device=self.device)
+        pool.append(t)
+        return t
 
 
 def require_cuda_float(t: torch.Tensor, name: str) -> torch.Tensor:

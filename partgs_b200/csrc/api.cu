@@ -111,6 +111,8 @@ struct BinningState {
   uint64_t* keys_b;
   uint32_t* vals_a;
   uint32_t* vals_b;
+  uint32_t* frag_mask;  // [8 warps][mask_stride]: forward's per-warp blend masks (render.cu)
+  size_t mask_stride;
   char* sort_temp;
   // The arena is laid out for R rounded up to 512 Ki instances: the request the caller's
   // allocator sees then takes only a handful of distinct sizes across views, so a caching
@@ -121,6 +123,8 @@ struct BinningState {
     // vals_a first: the final point list always ends up there, at an offset that does not depend
     // on R, so the caller may hand in a larger (grow-only) buffer than requested
     carve(p, b.vals_a, R);
+    b.mask_stride = R;
+    carve(p, b.frag_mask, (size_t)(TILE_PIX / 32) * R);
     carve(p, b.vals_b, R);
     carve(p, b.keys_a, R);
     carve(p, b.keys_b, R);
@@ -199,6 +203,8 @@ int pgs_dsr_get_layout(int P, int width, int height, int R, pgs_dsr_layout* out)
     const bool in_b = ((end_bit + 7) / 8) & 1;
     out->binning_keys_sorted = in_b ? (size_t)b.keys_b : (size_t)b.keys_a;
     out->binning_point_list = (size_t)b.vals_a;
+    out->binning_frag_mask = (size_t)b.frag_mask;
+    out->binning_mask_stride = b.mask_stride;
   }
   out->rec_floats = REC_FLOATS;
   out->tile_pixels = TILE_PIX;
@@ -311,6 +317,7 @@ static int forward_impl(bool part, int S, const float* semantics, float* out_sem
   ra.rec = geom.rec; ra.bbox = geom.bbox; ra.bg_color = background;
   ra.final_T = img.final_T; ra.n_contrib = img.n_contrib; ra.out_color = out_color; ra.out_others = out_others;
   ra.S = S; ra.semantics = semantics; ra.out_semantic = out_semantic;
+  ra.frag_mask = bin.frag_mask; ra.mask_stride = bin.mask_stride;
   {
     StageTimer t(PGS_STAGE_RENDER_FWD, s);
     if (part) launch_render_fwd_part(ra, s); else launch_render_fwd(ra, s);
@@ -389,9 +396,13 @@ static int backward_impl(bool part, int S, const float* semantics, const float* 
   ImageState img = ImageState::from(image_buffer, ntiles);
   if (radii == nullptr) radii = geom.radii;
   const uint32_t* point_list = nullptr;
+  const uint32_t* frag_mask = nullptr;
+  size_t mask_stride = 0;
   if (R > 0) {
     BinningState bin = BinningState::from(binning_buffer, R, end_bit);
     point_list = bin.vals_a;
+    frag_mask = bin.frag_mask;
+    mask_stride = bin.mask_stride;
   }
 
   float* grad = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(scratch), 256));
@@ -405,6 +416,7 @@ static int backward_impl(bool part, int S, const float* semantics, const float* 
   rb.rec = geom.rec; rb.bbox = geom.bbox; rb.bg_color = background; rb.final_T = img.final_T;
   rb.n_contrib = img.n_contrib; rb.dL_dpixels = dL_dpix; rb.dL_dothers = dL_dothers; rb.grad = grad;
   rb.S = S; rb.semantics = semantics; rb.dL_dsemantic = dL_dsemantic_pix; rb.grad_semantics = dL_dsemantics;
+  rb.frag_mask = frag_mask; rb.mask_stride = mask_stride;
   if (part && S > 0) cudaMemsetAsync(dL_dsemantics, 0, (size_t)P * S * sizeof(float), s);
   {
     StageTimer t(PGS_STAGE_RENDER_BWD, s);

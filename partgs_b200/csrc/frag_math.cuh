@@ -22,6 +22,18 @@
 
 namespace pgs {
 
+// MUFU approximations (~1 ulp) for the backward pass, where no decision depends on the values.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 struct FragGeom {
   float3 k, l, p;
   float2 s, d;

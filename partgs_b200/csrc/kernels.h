@@ -76,6 +76,10 @@ struct RenderFwdArgs {
   uint32_t* n_contrib;  // [2][ntile*256]: last, median
   float* out_color;   // [3][H][W]
   float* out_others;  // [7][H][W] (base) / [8][H][W] (`_part`)
+  // per (warp, list position): the pixels of the warp's 8x4 footprint that blended the surfel;
+  // written here, consumed by the backward pass.  [8][mask_stride], indexed [warp][range.x + pos]
+  uint32_t* frag_mask;
+  size_t mask_stride;
   // `_part` fork only
   int S;                   // semantic channels (<= MAX_SEMANTIC)
   const float* semantics;  // [P][S]
@@ -99,6 +103,8 @@ struct RenderBwdArgs {
   const float* dL_dpixels;  // [3][H][W]
   const float* dL_dothers;  // [7][H][W]
   float* grad;              // [P][GRAD_FLOATS], zeroed
+  const uint32_t* frag_mask;  // forward's blend masks, [8][mask_stride]
+  size_t mask_stride;
   // `_part` fork only
   int S;
   const float* semantics;       // [P][S]

@@ -11,21 +11,29 @@
 //   * a tile is still one 256-thread CTA, but its 8 warps are independent streams: each warp
 //     owns an 8x4 pixel footprint and walks the tile's depth-sorted list on its own, 32
 //     candidates per step — one candidate per lane: fetch id (coalesced) and the surfel's
-//     16-byte cull box, test the box against the warp's footprint, ballot-compact the
-//     survivors and stage only their 80-byte records into the warp's private shared-memory
-//     ring with 128-bit cp.async (LDGSTS); ids / boxes of the next step are prefetched while
-//     the current survivors are blended.  No __syncthreads anywhere in the loop, so a warp
-//     never waits for a sibling with more work, and a surfel costs ALU time only in the
-//     warps whose footprint its cull box touches;
+//     16-byte cull box, test the box (then the exact conic) against the warp's footprint,
+//     ballot-compact the survivors and stage only their 80-byte records into the warp's
+//     private shared-memory ring with 128-bit cp.async (LDGSTS).  The ring is double
+//     buffered: the survivors of step k+1 are in flight while those of step k are blended;
+//     ids are prefetched two steps ahead, cull boxes one.  No __syncthreads anywhere in the
+//     loop, so a warp never waits for a sibling with more work, and a surfel costs ALU time
+//     only in the warps whose footprint it can touch;
 //   * tiles are issued longest-list-first (tile_order, built by tile_order_kernel) so the
 //     heavy tiles do not form the tail of the launch;
-//   * warp-level early termination (all 32 pixels saturated) in forward; in backward each
-//     warp starts at its own deepest contributing fragment (max n_contrib over its pixels);
+//   * warp-level early termination (all 32 pixels saturated) in forward;
+//   * the forward pass records, per warp and list position, the 32-bit mask of pixels that
+//     actually blended the surfel (`frag_mask`, 4 B per warp x instance, written coalesced).
+//     The backward pass walks the same list back to front but never culls or re-decides
+//     anything: a candidate is staged iff its mask is non-zero, and a lane takes part iff its
+//     bit is set.  That removes the replay of the reference's decision chain (which would have
+//     to be bit-identical to forward, i.e. IEEE divisions and precise expf) from the backward
+//     pass: its per-fragment values are recomputed with MUFU.RCP / MUFU.EX2 (gradients are
+//     gated at 1e-4 relative, measured ~1e-6);
 //   * backward: the 16+3(+S) per-fragment gradient components are reduced over the 32 pixels
 //     with a transposed butterfly (16 shuffles for 16 values instead of 80); 16 lanes then
 //     hold one finished component each and issue one coalesced red.global.add.f32 into the
 //     surfel's 80-byte gradient record.
-// The per-fragment arithmetic is pinned in frag_math.cuh; accumulations below use the
+// The forward per-fragment arithmetic is pinned in frag_math.cuh; accumulations below use the
 // reference's rounding sequence (explicit fma/mul), so images are bit-identical.
 #include "common.cuh"
 #include "frag_math.cuh"
@@ -41,6 +49,7 @@ struct __align__(16) WarpStage {
   float4 rec[CHUNK][REC_QUADS];  // 32 x 80 B
   uint32_t pos[CHUNK];           // list position of the staged surfel
   uint32_t id[CHUNK];            // surfel index (backward only)
+  uint32_t mask[CHUNK];          // pixels that blended it in forward (backward only)
 };
 
 __device__ __forceinline__ bool box_hits(const float4 b, float x0, float y0, float x1, float y1) {
@@ -135,13 +144,14 @@ void launch_tile_order(const uint2* ranges, int ntiles, uint32_t* order, cudaStr
 // forward
 // =============================================================================
 template <bool PART>
-__global__ void __launch_bounds__(TILE_PIX, PART ? 3 : 4) render_fwd_kernel(RenderFwdArgs a) {
-  __shared__ WarpStage s_stage[NWARP];
-  extern __shared__ float s_sem_dyn[];  // PART: [NWARP][CHUNK][MAX_SEMANTIC]
+__global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 4) render_fwd_kernel(RenderFwdArgs a) {
+  __shared__ WarpStage s_stage[2][NWARP];
+  extern __shared__ float s_sem_dyn[];  // PART: [2][NWARP][CHUNK][MAX_SEMANTIC]
 
   const int S = PART ? a.S : 0;
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31, wid = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
   const int tile_id = a.tile_order ? (int)a.tile_order[blockIdx.x] : (int)blockIdx.x;
   const int tile_x = tile_id % a.grid_x, tile_y = tile_id / a.grid_x;
   const int fx0 = tile_x * TILE_X + (wid & 1) * WARP_FX;
@@ -154,12 +164,10 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 3 : 4) render_fwd_kernel(Rend
   const float wx0 = (float)fx0 + poff, wy0 = (float)fy0 + poff;
   const float wx1 = wx0 + (float)(WARP_FX - 1), wy1 = wy0 + (float)(WARP_FY - 1);
 
-  WarpStage& st = s_stage[wid];
-  float* sem_stage = PART ? (s_sem_dyn + (size_t)wid * CHUNK * MAX_SEMANTIC) : nullptr;
-
   const uint2 range = a.ranges[tile_id];
   const int total = (int)(range.y - range.x);
   const uint32_t* __restrict__ list = a.point_list + range.x;
+  uint32_t* __restrict__ fmask = a.frag_mask + (size_t)wid * a.mask_stride + range.x;
 
   float T = 1.0f;
   uint32_t last_contributor = 0;
@@ -173,53 +181,72 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 3 : 4) render_fwd_kernel(Rend
     for (int i = 0; i < MAX_SEMANTIC; i++) Sem[i] = 0.f;
   }
 
-  // software pipeline: ids two steps ahead, cull boxes one step ahead
   const float4 nobox = make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);
-  uint32_t id_cur = 0, id_nxt = 0;
-  float4 box_cur = nobox;
-  if ((int)lane < total) id_cur = list[lane];
-  if ((int)lane + CHUNK < total) id_nxt = list[lane + CHUNK];
-  if ((int)lane < total) box_cur = __ldg(&a.bbox[(size_t)id_cur * CULL_QUADS]);
-
-  for (int base = 0; base < total; base += CHUNK) {
-    if (__all_sync(RFULL, done)) break;
-    // prefetch for the following steps
-    uint32_t id_n2 = 0;
-    if (base + 2 * CHUNK + (int)lane < total) id_n2 = list[base + 2 * CHUNK + lane];
-    float4 box_nxt = nobox;
-    if (base + CHUNK + (int)lane < total) box_nxt = __ldg(&a.bbox[(size_t)id_nxt * CULL_QUADS]);
-
-    bool hit = box_hits(box_cur, wx0, wy0, wx1, wy1);  // lanes past the end carry `nobox`
+  auto load_id = [&](int base) -> uint32_t { return (base + (int)lane < total) ? list[base + lane] : 0u; };
+  auto load_box = [&](int base, uint32_t id) -> float4 {
+    return (base + (int)lane < total) ? __ldg(&a.bbox[(size_t)id * CULL_QUADS]) : nobox;  // lanes past the end never hit
+  };
+  // cull the 32 candidates of one step and start the copy of the survivors' records into ring buffer `buf`
+  auto stage = [&](int base, int buf, uint32_t id, float4 box, bool& hit, int& slot) -> int {
+    hit = box_hits(box, wx0, wy0, wx1, wy1);
     if (hit) {
-      const float4* cr = a.bbox + (size_t)id_cur * CULL_QUADS;
+      const float4* cr = a.bbox + (size_t)id * CULL_QUADS;
       hit = conic_hits(__ldg(cr + 1), __ldg(cr + 2), wx0, wy0, wx1, wy1);
     }
     const unsigned m = __ballot_sync(RFULL, hit);
-    const int n = __popc(m);
-    if (n > 0) {
-      if (hit) {
-        const int slot = __popc(m & ((1u << lane) - 1));
-        const float4* src = a.rec + (size_t)id_cur * REC_QUADS;
+    slot = __popc(m & lt_mask);
+    if (hit) {
+      WarpStage& st = s_stage[buf][wid];
+      const float4* src = a.rec + (size_t)id * REC_QUADS;
 #pragma unroll
-        for (int q = 0; q < REC_QUADS; q++) cp_async16(&st.rec[slot][q], src + q);
-        st.pos[slot] = (uint32_t)(base + lane + 1);
-        if (PART) {
-          const float* sem = a.semantics + (size_t)id_cur * S;
-          for (int ch = 0; ch < S; ch++) sem_stage[slot * MAX_SEMANTIC + ch] = __ldg(sem + ch);
-        }
+      for (int q = 0; q < REC_QUADS; q++) cp_async16(&st.rec[slot][q], src + q);
+      st.pos[slot] = (uint32_t)(base + lane + 1);
+      if (PART) {
+        float* sem_stage = s_sem_dyn + ((size_t)(buf * NWARP + wid) * CHUNK + slot) * MAX_SEMANTIC;
+        const float* sem = a.semantics + (size_t)id * S;
+        for (int ch = 0; ch < S; ch++) sem_stage[ch] = __ldg(sem + ch);
       }
-      cp_async_commit();
-      cp_async_wait<0>();
-      __syncwarp();
+    }
+    cp_async_commit();
+    return __popc(m);
+  };
 
+  // software pipeline: step k is blended while the records of step k+1 are in flight, the cull box of
+  // step k+2 and the ids of step k+3 are being fetched
+  uint32_t id_n = load_id(0);
+  float4 box_n = load_box(0, id_n);
+  uint32_t id_n2 = load_id(CHUNK);
+  bool hit_c = false;
+  int slot_c = 0;
+  int n_c = stage(0, 0, id_n, box_n, hit_c, slot_c);
+  id_n = id_n2;
+  box_n = load_box(CHUNK, id_n);
+  id_n2 = load_id(2 * CHUNK);
+
+  for (int base = 0, buf = 0; base < total; base += CHUNK, buf ^= 1) {
+    if (__all_sync(RFULL, done)) break;
+    bool hit_n = false;
+    int slot_n = 0, n_n = 0;
+    if (base + CHUNK < total) n_n = stage(base + CHUNK, buf ^ 1, id_n, box_n, hit_n, slot_n);
+    else cp_async_commit();
+    id_n = id_n2;
+    box_n = load_box(base + 2 * CHUNK, id_n);
+    id_n2 = load_id(base + 3 * CHUNK);
+    cp_async_wait<1>();
+    __syncwarp();
+
+    uint32_t my_mask = 0;  // lane j: pixels that blended the survivor in slot j
+    if (n_c > 0) {
+      const WarpStage& st = s_stage[buf][wid];
+      const float* sem_stage = PART ? (s_sem_dyn + (size_t)(buf * NWARP + wid) * CHUNK * MAX_SEMANTIC) : nullptr;
       // Two fragments are evaluated (geometry, alpha: independent of the pixel's running state)
       // before they are blended in order: doubles the ILP of the per-pixel dependency chain,
       // which is what bounds the deepest tiles (thousands of fragments on the same pixels).
-      auto blend = [&](const int j, const float alpha, const float depth) {
+      auto blend = [&](const int j, const float alpha, const float depth) -> bool {
         const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
         if (test_T < 0.0001f) {
           done = true;
-          return;
+          return false;
         }
         const float4 q3 = st.rec[j][3];
         const float4 q4 = st.rec[j][4];
@@ -272,21 +299,30 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 3 : 4) render_fwd_kernel(Rend
         }
         T = test_T;
         last_contributor = contributor;
+        return true;
       };
-      for (int j = 0; j < n; j += 2) {
+      for (int j = 0; j < n_c; j += 2) {
         float alpha0, depth0, alpha1 = 0.f, depth1 = 0.f;
         const bool ok0 = frag_eval<PART>(pixf, st.rec[j][0], st.rec[j][1], st.rec[j][2], alpha0, depth0);
         bool ok1 = false;
-        if (j + 1 < n) ok1 = frag_eval<PART>(pixf, st.rec[j + 1][0], st.rec[j + 1][1], st.rec[j + 1][2], alpha1, depth1);
-        if (ok0 && !done) blend(j, alpha0, depth0);
-        if (ok1 && !done) blend(j + 1, alpha1, depth1);
+        if (j + 1 < n_c) ok1 = frag_eval<PART>(pixf, st.rec[j + 1][0], st.rec[j + 1][1], st.rec[j + 1][2], alpha1, depth1);
+        bool b0 = false, b1 = false;
+        if (ok0 && !done) b0 = blend(j, alpha0, depth0);
+        if (ok1 && !done) b1 = blend(j + 1, alpha1, depth1);
+        const unsigned m0 = __ballot_sync(RFULL, b0), m1 = __ballot_sync(RFULL, b1);
+        if ((int)lane == j) my_mask = m0;
+        if ((int)lane == j + 1) my_mask = m1;
       }
-      __syncwarp();  // the ring is rewritten in the next step
     }
-    id_cur = id_nxt;
-    id_nxt = id_n2;
-    box_cur = box_nxt;
+    // what backward needs to know about this step: per candidate, the pixels that blended it
+    const uint32_t mv = __shfl_sync(RFULL, my_mask, slot_c & 31);
+    if (base + (int)lane < total) fmask[base + lane] = hit_c ? mv : 0u;
+    __syncwarp();  // ring buffer `buf` is refilled by the next iteration's stage()
+    n_c = n_n;
+    hit_c = hit_n;
+    slot_c = slot_n;
   }
+  cp_async_wait<0>();
 
   // per-pixel state for backward, tile-major so that a warp writes 128 contiguous bytes
   const size_t npt = (size_t)a.grid_x * a.grid_y * TILE_PIX;
@@ -365,11 +401,12 @@ __device__ __forceinline__ float warp_reduce4(float (&c)[4], unsigned lane) {
 
 template <bool PART>
 __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(RenderBwdArgs a) {
-  __shared__ WarpStage s_stage[NWARP];
+  __shared__ WarpStage s_stage[2][NWARP];
 
   const int S = PART ? a.S : 0;
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31, wid = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
   const int tile_id = a.tile_order ? (int)a.tile_order[blockIdx.x] : (int)blockIdx.x;
   const int tile_x = tile_id % a.grid_x, tile_y = tile_id / a.grid_x;
   const int fx0 = tile_x * TILE_X + (wid & 1) * WARP_FX;
@@ -378,12 +415,10 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(Rend
   const float poff = PART ? 0.5f : 0.0f;
   const float2 pixf = {(float)pix.x + poff, (float)pix.y + poff};
   const bool inside = pix.x < (unsigned)a.W && pix.y < (unsigned)a.H;
-  const float wx0 = (float)fx0 + poff, wy0 = (float)fy0 + poff;
-  const float wx1 = wx0 + (float)(WARP_FX - 1), wy1 = wy0 + (float)(WARP_FY - 1);
 
-  WarpStage& st = s_stage[wid];
   const uint2 range = a.ranges[tile_id];
   const uint32_t* __restrict__ list = a.point_list + range.x;
+  const uint32_t* __restrict__ fmask = a.frag_mask + (size_t)wid * a.mask_stride + range.x;
 
   const size_t npt = (size_t)a.grid_x * a.grid_y * TILE_PIX;
   const size_t sidx = (size_t)tile_id * TILE_PIX + tid;
@@ -422,6 +457,7 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(Rend
   }
   float bg_dot_dpixel = 0;
   for (int i = 0; i < 3; i++) bg_dot_dpixel += a.bg_color[i] * dL_dpixel[i];
+  const float Tf_bg = T_final * bg_dot_dpixel;
 
   float accum_rec[3] = {0.f, 0.f, 0.f};
   float last_color[3] = {0.f, 0.f, 0.f};
@@ -439,187 +475,187 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(Rend
   for (int o = 16; o > 0; o >>= 1) top = max(top, __shfl_xor_sync(RFULL, top, o));
   const int total = (int)top;
 
-  const float4 nobox = make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);
   // candidate c of step `base` sits at list position total-1-(base+lane)  (back to front)
-  uint32_t id_cur = 0, id_nxt = 0;
-  float4 box_cur = nobox;
-  if ((int)lane < total) id_cur = list[total - 1 - lane];
-  if ((int)lane + CHUNK < total) id_nxt = list[total - 1 - lane - CHUNK];
-  if ((int)lane < total) box_cur = __ldg(&a.bbox[(size_t)id_cur * CULL_QUADS]);
-
-  for (int base = 0; base < total; base += CHUNK) {
-    uint32_t id_n2 = 0;
-    if (base + 2 * CHUNK + (int)lane < total) id_n2 = list[total - 1 - (base + 2 * CHUNK + lane)];
-    float4 box_nxt = nobox;
-    if (base + CHUNK + (int)lane < total) box_nxt = __ldg(&a.bbox[(size_t)id_nxt * CULL_QUADS]);
-
-    bool hit = box_hits(box_cur, wx0, wy0, wx1, wy1);
-    if (hit) {
-      const float4* cr = a.bbox + (size_t)id_cur * CULL_QUADS;
-      hit = conic_hits(__ldg(cr + 1), __ldg(cr + 2), wx0, wy0, wx1, wy1);
+  auto load_cand = [&](int base, uint32_t& id, uint32_t& mk) {
+    id = 0;
+    mk = 0;
+    if (base + (int)lane < total) {
+      const int p = total - 1 - (base + (int)lane);
+      id = list[p];
+      mk = fmask[p];
     }
+  };
+  auto stage = [&](int base, int buf, uint32_t id, uint32_t mk) -> int {
+    const bool hit = mk != 0u;
     const unsigned m = __ballot_sync(RFULL, hit);
-    const int n = __popc(m);
-    if (n > 0) {
-      if (hit) {
-        const int slot = __popc(m & ((1u << lane) - 1));
-        const float4* src = a.rec + (size_t)id_cur * REC_QUADS;
+    if (hit) {
+      const int slot = __popc(m & lt_mask);
+      WarpStage& st = s_stage[buf][wid];
+      const float4* src = a.rec + (size_t)id * REC_QUADS;
 #pragma unroll
-        for (int q = 0; q < REC_QUADS; q++) cp_async16(&st.rec[slot][q], src + q);
-        st.pos[slot] = (uint32_t)(total - 1 - (base + (int)lane));
-        st.id[slot] = id_cur;
-      }
-      cp_async_commit();
-      cp_async_wait<0>();
-      __syncwarp();
-
-      for (int j = 0; j < n; j++) {
-        const uint32_t contributor = st.pos[j];
-        const float4 q0 = st.rec[j][0];
-        const float4 q1 = st.rec[j][1];
-        const float4 q2 = st.rec[j][2];
-        const float3 Tu = {q0.x, q0.y, q0.z};
-        const float3 Tv = {q1.x, q1.y, q1.z};
-        const float3 Tw = {q2.x, q2.y, q2.z};
-        const float opa = q2.w;
-
-        // replay the forward decision sequence bit-identically
-        FragGeom f;
-        bool valid = contributor < last_contributor;
-        valid = frag_geometry<PART>(pixf, Tu, Tv, Tw, make_float2(q0.w, q1.w), f) && valid;
-        const float c_d = f.depth;
-        if (PART) valid = valid && !((double)c_d < 0.2);
-        else valid = valid && !(c_d < PGS_NEAR_N);
-        float power, G;
-        const float alpha = frag_alpha(f.rho3d, f.rho2d, opa, power, G);
-        valid = valid && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-
-        if (!__any_sync(RFULL, valid)) continue;
-
-        float g[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) g[i] = 0.f;
-        float gc[4] = {0.f, 0.f, 0.f, 0.f};
-        float w_sem = 0.f;
-
-        if (valid) {
-          // Gradient arithmetic (not part of the replayed decisions): approximate reciprocals
-          // (MUFU.RCP, ~1 ulp) instead of IEEE divisions, both branches of the rho3d/rho2d
-          // choice evaluated and selected.  Gradients are gated at 1e-4 relative.
-          const float4 q3 = st.rec[j][3];
-          const float4 q4 = st.rec[j][4];
-          const float normal[3] = {q3.x, q3.y, q3.z};
-          const float col[3] = {q4.x, q4.y, q4.z};
-          const float3 k = f.k, l = f.l;
-          const float2 s = f.s, d = f.d;
-
-          const float inv_1ma = __frcp_rn(1.f - alpha);
-          T = T * inv_1ma;
-          const float w = alpha * T;
-          w_sem = w;
-          const float one_m_la = 1.f - last_alpha;
-          float dL_dalpha = 0.0f;
-#pragma unroll
-          for (int ch = 0; ch < 3; ch++) {
-            const float c = col[ch];
-            accum_rec[ch] = last_alpha * last_color[ch] + one_m_la * accum_rec[ch];
-            last_color[ch] = c;
-            dL_dalpha += (c - accum_rec[ch]) * dL_dpixel[ch];
-            gc[ch] = w * dL_dpixel[ch];
-          }
-
-          const float inv_cd = __frcp_rn(c_d);
-          float m_d, dmd_dd;
-          if (PART) {
-            m_d = (float)(100.0 / (100.0 - 0.2)) * (1.f - 0.2f * inv_cd);
-            dmd_dd = (float)(100.0 * 0.2 / (100.0 - 0.2)) * inv_cd * inv_cd;
-          } else {
-            m_d = (PGS_FAR_N / (PGS_FAR_N - PGS_NEAR_N)) * (1.f - PGS_NEAR_N * inv_cd);
-            dmd_dd = ((PGS_FAR_N * PGS_NEAR_N) / (PGS_FAR_N - PGS_NEAR_N)) * inv_cd * inv_cd;
-          }
-          float dL_dz = 0.0f;
-          float dL_dweight = 0;
-          if (contributor == median_contributor - 1) {
-            dL_dz += dL_dmedian_depth;
-            if (PART) dL_dweight += dL_dmax_dweight;
-          }
-          dL_dweight += (final_D2 + m_d * m_d * final_A - 2 * m_d * final_D) * dL_dreg;
-          dL_dalpha += dL_dweight - last_dL_dT;
-          last_dL_dT = dL_dweight * alpha + (1 - alpha) * last_dL_dT;
-          const float dL_dmd = 2.0f * w * (m_d * final_A - final_D) * dL_dreg;
-          dL_dz += dL_dmd * dmd_dd;
-
-          accum_depth_rec = last_alpha * last_depth + one_m_la * accum_depth_rec;
-          last_depth = c_d;
-          dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
-          accum_alpha_rec = last_alpha + one_m_la * accum_alpha_rec;
-          dL_dalpha += (1 - accum_alpha_rec) * dL_daccum;
-
-#pragma unroll
-          for (int ch = 0; ch < 3; ch++) {
-            accum_normal_rec[ch] = last_alpha * last_normal[ch] + one_m_la * accum_normal_rec[ch];
-            last_normal[ch] = normal[ch];
-            dL_dalpha += (normal[ch] - accum_normal_rec[ch]) * dL_dnormal2D[ch];
-            g[12 + ch] = w * dL_dnormal2D[ch];
-          }
-
-          dL_dalpha *= T;
-          last_alpha = alpha;
-          dL_dalpha -= T_final * inv_1ma * bg_dot_dpixel;
-
-          const float dL_dG = opa * dL_dalpha;
-          dL_dz += w * dL_ddepth;
-          g[11] = G * dL_dalpha;
-
-          const bool use3d = f.rho3d <= f.rho2d;
-          // ray-splat branch: gradient w.r.t. the 3x3 transform through s = p.xy / p.z
-          const float mGG = -G * dL_dG;
-          const float inv_pz = __frcp_rn(f.p.z);
-          const float dsx_pz = (mGG * s.x + dL_dz * Tw.x) * inv_pz;
-          const float dsy_pz = (mGG * s.y + dL_dz * Tw.y) * inv_pz;
-          const float3 dL_dp = {dsx_pz, dsy_pz, -(dsx_pz * s.x + dsy_pz * s.y)};
-          const float3 dL_dk = {l.y * dL_dp.z - l.z * dL_dp.y, l.z * dL_dp.x - l.x * dL_dp.z,
-                                l.x * dL_dp.y - l.y * dL_dp.x};
-          const float3 dL_dl = {dL_dp.y * k.z - dL_dp.z * k.y, dL_dp.z * k.x - dL_dp.x * k.z,
-                                dL_dp.x * k.y - dL_dp.y * k.x};
-          // low-pass branch: gradient w.r.t. the screen-space centre
-          const float fis = PART ? (float)(1 / (0.7071067811865476 * 0.7071067811865476)) : PGS_FILTER_INV_SQUARE;
-          const float mGGf = mGG * fis;
-          g[0] = use3d ? -dL_dk.x : 0.f;
-          g[1] = use3d ? -dL_dk.y : 0.f;
-          g[2] = use3d ? -dL_dk.z : 0.f;
-          g[3] = use3d ? -dL_dl.x : 0.f;
-          g[4] = use3d ? -dL_dl.y : 0.f;
-          g[5] = use3d ? -dL_dl.z : 0.f;
-          g[6] = use3d ? pixf.x * dL_dk.x + pixf.y * dL_dl.x + dL_dz * s.x : 0.f;
-          g[7] = use3d ? pixf.x * dL_dk.y + pixf.y * dL_dl.y + dL_dz * s.y : 0.f;
-          g[8] = use3d ? pixf.x * dL_dk.z + pixf.y * dL_dl.z + dL_dz : dL_dz;
-          g[9] = use3d ? 0.f : mGGf * d.x;
-          g[10] = use3d ? 0.f : mGGf * d.y;
-        }
-
-        const float r16 = warp_reduce16(g, lane);
-        const float r4 = warp_reduce4(gc, lane);
-        const uint32_t gid = st.id[j];
-        float* dst = a.grad + (size_t)gid * GRAD_FLOATS;
-        if ((lane & 1) == 0 && (lane >> 1) != 15) atomicAdd(dst + (lane >> 1), r16);
-        if ((lane & 7) == 0 && (lane >> 3) != 3) atomicAdd(dst + 16 + (lane >> 3), r4);
-        if (PART && S > 0) {
-          // dL/dsem[ch] = sum_pixels alpha*T * dL/dpixel_sem[ch]  (no alpha gradient in the reference fork)
-          float gs[16];
-#pragma unroll
-          for (int i = 0; i < 16; i++) gs[i] = w_sem * dL_dsem[i];
-          const float rs = warp_reduce16(gs, lane);
-          const int ch = lane >> 1;
-          if ((lane & 1) == 0 && ch < S) atomicAdd(a.grad_semantics + (size_t)gid * S + ch, rs);
-        }
-      }
-      __syncwarp();
+      for (int q = 0; q < REC_QUADS; q++) cp_async16(&st.rec[slot][q], src + q);
+      st.pos[slot] = (uint32_t)(total - 1 - (base + (int)lane));
+      st.id[slot] = id;
+      st.mask[slot] = mk;
     }
-    id_cur = id_nxt;
-    id_nxt = id_n2;
-    box_cur = box_nxt;
+    cp_async_commit();
+    return __popc(m);
+  };
+
+  uint32_t id_n, mk_n, id_n2, mk_n2;
+  load_cand(0, id_n, mk_n);
+  int n_c = stage(0, 0, id_n, mk_n);
+  load_cand(CHUNK, id_n, mk_n);
+  load_cand(2 * CHUNK, id_n2, mk_n2);
+
+  const float fis = PART ? (float)(1 / (0.7071067811865476 * 0.7071067811865476)) : PGS_FILTER_INV_SQUARE;
+
+  for (int base = 0, buf = 0; base < total; base += CHUNK, buf ^= 1) {
+    int n_n = 0;
+    if (base + CHUNK < total) n_n = stage(base + CHUNK, buf ^ 1, id_n, mk_n);
+    else cp_async_commit();
+    id_n = id_n2;
+    mk_n = mk_n2;
+    load_cand(base + 3 * CHUNK, id_n2, mk_n2);
+    cp_async_wait<1>();
+    __syncwarp();
+
+    const WarpStage& st = s_stage[buf][wid];
+    for (int j = 0; j < n_c; j++) {
+      const uint32_t contributor = st.pos[j];
+      const bool valid = (st.mask[j] >> lane) & 1u;  // this pixel blended the surfel in forward
+      const float4 q0 = st.rec[j][0];
+      const float4 q1 = st.rec[j][1];
+      const float4 q2 = st.rec[j][2];
+      const float3 Tu = {q0.x, q0.y, q0.z};
+      const float3 Tv = {q1.x, q1.y, q1.z};
+      const float3 Tw = {q2.x, q2.y, q2.z};
+      const float opa = q2.w;
+
+      // Fragment values (forward.cu:344-387) recomputed with approximate reciprocal / exp2: no decision
+      // depends on them any more (forward recorded which pixels blended), gradients are gated at 1e-4.
+      const float3 k = {pixf.x * Tw.x - Tu.x, pixf.x * Tw.y - Tu.y, pixf.x * Tw.z - Tu.z};
+      const float3 l = {pixf.y * Tw.x - Tv.x, pixf.y * Tw.y - Tv.y, pixf.y * Tw.z - Tv.z};
+      const float3 p = {k.y * l.z - k.z * l.y, k.z * l.x - k.x * l.z, k.x * l.y - k.y * l.x};
+      // lanes that did not blend this surfel run the arithmetic below with w = dL_dalpha = dL_dz = 0;
+      // inv_pz = 0 keeps every intermediate finite for them
+      const float inv_pz = valid ? rcp_approx(p.z) : 0.f;
+      const float2 s = {p.x * inv_pz, p.y * inv_pz};
+      const float rho3d = s.x * s.x + s.y * s.y;
+      const float2 d = {q0.w - pixf.x, q1.w - pixf.y};
+      const float rho2d = fis * (d.x * d.x + d.y * d.y);
+      const bool use3d = rho3d <= rho2d;
+      const float c_d = use3d ? (s.x * Tw.x + s.y * Tw.y) + Tw.z : Tw.z;
+      const float G = ex2_approx(-0.5f * 1.4426950408889634f * fminf(rho3d, rho2d));
+      const float alpha = fminf(0.99f, opa * G);
+
+      float w = 0.f, dL_dalpha = 0.f, dL_dz = 0.f;
+      const float4 q3 = st.rec[j][3];
+      const float4 q4 = st.rec[j][4];
+      if (valid) {
+        const float normal[3] = {q3.x, q3.y, q3.z};
+        const float col[3] = {q4.x, q4.y, q4.z};
+        const float inv_1ma = rcp_approx(1.f - alpha);
+        T = T * inv_1ma;
+        w = alpha * T;
+        const float one_m_la = 1.f - last_alpha;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+          accum_rec[ch] = last_alpha * last_color[ch] + one_m_la * accum_rec[ch];
+          last_color[ch] = col[ch];
+          dL_dalpha += (col[ch] - accum_rec[ch]) * dL_dpixel[ch];
+        }
+        const float inv_cd = rcp_approx(c_d);
+        float m_d, dmd_dd;
+        if (PART) {
+          m_d = (float)(100.0 / (100.0 - 0.2)) * (1.f - 0.2f * inv_cd);
+          dmd_dd = (float)(100.0 * 0.2 / (100.0 - 0.2)) * inv_cd * inv_cd;
+        } else {
+          m_d = (PGS_FAR_N / (PGS_FAR_N - PGS_NEAR_N)) * (1.f - PGS_NEAR_N * inv_cd);
+          dmd_dd = ((PGS_FAR_N * PGS_NEAR_N) / (PGS_FAR_N - PGS_NEAR_N)) * inv_cd * inv_cd;
+        }
+        float dL_dweight = 0;
+        if (contributor == median_contributor - 1) {
+          dL_dz += dL_dmedian_depth;
+          if (PART) dL_dweight += dL_dmax_dweight;
+        }
+        dL_dweight += (final_D2 + m_d * m_d * final_A - 2 * m_d * final_D) * dL_dreg;
+        dL_dalpha += dL_dweight - last_dL_dT;
+        last_dL_dT = dL_dweight * alpha + (1 - alpha) * last_dL_dT;
+        const float dL_dmd = 2.0f * w * (m_d * final_A - final_D) * dL_dreg;
+        dL_dz += dL_dmd * dmd_dd;
+
+        accum_depth_rec = last_alpha * last_depth + one_m_la * accum_depth_rec;
+        last_depth = c_d;
+        dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
+        accum_alpha_rec = last_alpha + one_m_la * accum_alpha_rec;
+        dL_dalpha += (1 - accum_alpha_rec) * dL_daccum;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+          accum_normal_rec[ch] = last_alpha * last_normal[ch] + one_m_la * accum_normal_rec[ch];
+          last_normal[ch] = normal[ch];
+          dL_dalpha += (normal[ch] - accum_normal_rec[ch]) * dL_dnormal2D[ch];
+        }
+        dL_dalpha *= T;
+        last_alpha = alpha;
+        dL_dalpha -= Tf_bg * inv_1ma;
+        dL_dz += w * dL_ddepth;
+      }
+
+      float g[16];
+      float gc[4];
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) {
+        gc[ch] = w * dL_dpixel[ch];
+        g[12 + ch] = w * dL_dnormal2D[ch];
+      }
+      gc[3] = 0.f;
+      g[15] = 0.f;
+      g[11] = G * dL_dalpha;
+      const float dL_dG = opa * dL_dalpha;
+      // ray-splat branch: gradient w.r.t. the 3x3 transform through s = p.xy / p.z
+      const float mGG = -G * dL_dG;
+      const float dsx_pz = (mGG * s.x + dL_dz * Tw.x) * inv_pz;
+      const float dsy_pz = (mGG * s.y + dL_dz * Tw.y) * inv_pz;
+      const float3 dL_dp = {dsx_pz, dsy_pz, -(dsx_pz * s.x + dsy_pz * s.y)};
+      const float3 dL_dk = {l.y * dL_dp.z - l.z * dL_dp.y, l.z * dL_dp.x - l.x * dL_dp.z,
+                            l.x * dL_dp.y - l.y * dL_dp.x};
+      const float3 dL_dl = {dL_dp.y * k.z - dL_dp.z * k.y, dL_dp.z * k.x - dL_dp.x * k.z,
+                            dL_dp.x * k.y - dL_dp.y * k.x};
+      // low-pass branch: gradient w.r.t. the screen-space centre
+      const float mGGf = mGG * fis;
+      g[0] = use3d ? -dL_dk.x : 0.f;
+      g[1] = use3d ? -dL_dk.y : 0.f;
+      g[2] = use3d ? -dL_dk.z : 0.f;
+      g[3] = use3d ? -dL_dl.x : 0.f;
+      g[4] = use3d ? -dL_dl.y : 0.f;
+      g[5] = use3d ? -dL_dl.z : 0.f;
+      g[6] = use3d ? pixf.x * dL_dk.x + pixf.y * dL_dl.x + dL_dz * s.x : 0.f;
+      g[7] = use3d ? pixf.x * dL_dk.y + pixf.y * dL_dl.y + dL_dz * s.y : 0.f;
+      g[8] = use3d ? pixf.x * dL_dk.z + pixf.y * dL_dl.z + dL_dz : dL_dz;
+      g[9] = use3d ? 0.f : mGGf * d.x;
+      g[10] = use3d ? 0.f : mGGf * d.y;
+
+      const float r16 = warp_reduce16(g, lane);
+      const float r4 = warp_reduce4(gc, lane);
+      const uint32_t gid = st.id[j];
+      float* dst = a.grad + (size_t)gid * GRAD_FLOATS;
+      if ((lane & 1) == 0 && (lane >> 1) != 15) atomicAdd(dst + (lane >> 1), r16);
+      if ((lane & 7) == 0 && (lane >> 3) != 3) atomicAdd(dst + 16 + (lane >> 3), r4);
+      if (PART && S > 0) {
+        // dL/dsem[ch] = sum_pixels alpha*T * dL/dpixel_sem[ch]  (no alpha gradient in the reference fork)
+        float gs[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) gs[i] = w * dL_dsem[i];
+        const float rs = warp_reduce16(gs, lane);
+        const int ch = lane >> 1;
+        if ((lane & 1) == 0 && ch < S) atomicAdd(a.grad_semantics + (size_t)gid * S + ch, rs);
+      }
+    }
+    __syncwarp();  // ring buffer `buf` is refilled by the next iteration's stage()
+    n_c = n_n;
   }
+  cp_async_wait<0>();
 }
 
 // =============================================================================
@@ -627,7 +663,14 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(Rend
 // =============================================================================
 template <bool PART> static void launch_fwd(const RenderFwdArgs& a, cudaStream_t s) {
   const int ntiles = a.grid_x * a.grid_y;
-  const size_t dyn = PART ? (size_t)NWARP * CHUNK * MAX_SEMANTIC * sizeof(float) : 0;
+  const size_t dyn = PART ? (size_t)2 * NWARP * CHUNK * MAX_SEMANTIC * sizeof(float) : 0;
+  if (PART) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(render_fwd_kernel<PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      attr_set = true;
+    }
+  }
   render_fwd_kernel<PART><<<ntiles, TILE_PIX, dyn, s>>>(a);
   count_launch();
 }

@@ -61,6 +61,9 @@ def parse_state(geom: torch.Tensor, img: torch.Tensor, binning: torch.Tensor, P:
     if R > 0:
         out["point_list_keys"] = _view(binning, lay.binning_keys_sorted, 8 * R, torch.int64, (R,))
         out["point_list"] = _view(binning, lay.binning_point_list, 4 * R, torch.int32, (R,))
+        # [8 warps][R]: bit l of frag_mask[w][i] = pixel (lane l of warp w's 8x4 footprint) blended instance i
+        ms = lay.binning_mask_stride
+        out["frag_mask"] = _view(binning, lay.binning_frag_mask, 4 * 8 * ms, torch.int32, (8, ms))[:, :R]
     return out
 
 

@@ -235,3 +235,33 @@ def test_vs_cpu_oracle_small():
     for k in ("means3D", "opacity", "scales", "rotations", "sh"):
         ok, info = pu.robust_close(o["grads"][k].cpu(), gr[k], atol_frac=1e-3, max_frac=5e-3)
         assert ok, (k, info)
+
+
+def test_blend_masks_consistent_with_pixel_state():
+    """The forward pass hands the backward pass one 32-bit mask per (warp footprint, list position):
+    the pixels that blended that surfel.  Per pixel, the highest position with its bit set must be the
+    (bit-exact) last contributor, and no bit may be set at or beyond it for a pixel that blended nothing."""
+    from partgs_b200 import debug
+    cfg, scene, cams, bg, g = _setup("C2", 60_000, views=1)
+    W, H, Pn = cfg["W"], cfg["H"], cfg["P"]
+    o = pu.run_ours_raw(scene, cams[0], bg)
+    R = o["num_rendered"]
+    st = debug.parse_state(o["geom"], o["img"], o["binning"], Pn, W, H, R)
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    ranges = st["ranges"].long()
+    L = ranges[:, 1] - ranges[:, 0]
+    nc = torch.zeros(gy * 16, gx * 16, dtype=torch.int64, device=DEV)
+    nc[:H, :W] = st["n_contrib"][0].long()
+    last = nc.reshape(gy, 4, 4, gx, 2, 8).permute(0, 3, 1, 4, 2, 5).reshape(gy * gx, 8, 32)  # [tile][warp][lane]
+    top = last.amax(-1)                                                                       # [tile][warp]
+    tile_of = torch.repeat_interleave(torch.arange(gy * gx, device=DEV), L)
+    pos = torch.arange(R, device=DEV) - ranges[tile_of, 0]
+    m = st["frag_mask"].long() & 0xFFFFFFFF                                                    # [8][R]
+    walked = pos[None, :] < top[tile_of].t()           # entries the backward pass will read
+    for lane in range(32):
+        bit = ((m >> lane) & 1).bool() & walked          # [8][R]
+        # highest set position + 1 per (tile, warp)
+        p1 = torch.where(bit, (pos + 1)[None, :].expand(8, -1), torch.zeros_like(bit, dtype=torch.int64))
+        hi = torch.zeros(gy * gx, 8, dtype=torch.int64, device=DEV)
+        hi.scatter_reduce_(0, tile_of[:, None].expand(-1, 8), p1.t().contiguous(), reduce="amax")
+        assert torch.equal(hi, last[:, :, lane]), f"lane {lane}"
