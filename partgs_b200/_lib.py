@@ -11,7 +11,9 @@ from pathlib import Path
 import torch
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libpartgs_b200.so"
+import os as _os
+# PARTGS_B200_LIB: load an alternative build of the same library (kernel-tuning experiments only)
+LIB_PATH = Path(_os.environ["PARTGS_B200_LIB"]) if _os.environ.get("PARTGS_B200_LIB") else _PKG / "libpartgs_b200.so"
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
 

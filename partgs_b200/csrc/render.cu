@@ -38,12 +38,20 @@
 #include "common.cuh"
 #include "frag_math.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace pgs {
 
 constexpr unsigned RFULL = 0xffffffffu;
 constexpr int NWARP = TILE_PIX / 32;
 constexpr int CHUNK = 32;  // candidates per warp step (one per lane)
+#ifndef PGS_FWD_ILP
+#define PGS_FWD_ILP 2
+#endif
+#ifndef PGS_FWD_MINB
+#define PGS_FWD_MINB 4
+#endif
+constexpr int FWD_ILP = PGS_FWD_ILP;  // fragments evaluated ahead of the in-order blend
 
 struct __align__(16) WarpStage {
   float4 rec[CHUNK][REC_QUADS];  // 32 x 80 B
@@ -144,7 +152,7 @@ void launch_tile_order(const uint2* ranges, int ntiles, uint32_t* order, cudaStr
 // forward
 // =============================================================================
 template <bool PART>
-__global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 4) render_fwd_kernel(RenderFwdArgs a) {
+__global__ void __launch_bounds__(TILE_PIX, PART ? 2 : PGS_FWD_MINB) render_fwd_kernel(RenderFwdArgs a) {
   __shared__ WarpStage s_stage[2][NWARP];
   extern __shared__ float s_sem_dyn[];  // PART: [2][NWARP][CHUNK][MAX_SEMANTIC]
 
@@ -152,7 +160,7 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 4) render_fwd_kernel(Rend
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31, wid = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int tile_id = a.tile_order ? (int)a.tile_order[blockIdx.x] : (int)blockIdx.x;
+  const int tile_id = a.tile_order ? (int)a.tile_order[blockIdx.x + a.tile_begin] : (int)blockIdx.x + a.tile_begin;
   const int tile_x = tile_id % a.grid_x, tile_y = tile_id / a.grid_x;
   const int fx0 = tile_x * TILE_X + (wid & 1) * WARP_FX;
   const int fy0 = tile_y * TILE_Y + (wid >> 1) * WARP_FY;
@@ -161,8 +169,11 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 4) render_fwd_kernel(Rend
   const float2 pixf = {(float)pix.x + poff, (float)pix.y + poff};
   const bool inside = pix.x < (unsigned)a.W && pix.y < (unsigned)a.H;
   bool done = !inside;
-  const float wx0 = (float)fx0 + poff, wy0 = (float)fy0 + poff;
-  const float wx1 = wx0 + (float)(WARP_FX - 1), wy1 = wy0 + (float)(WARP_FY - 1);
+  // Cull region: bounding box of the footprint's pixels that are still blending.  It starts as the
+  // whole 8x4 footprint and shrinks as pixels saturate, so the long tail of a deep tile (a few
+  // unsaturated pixels walking thousands of candidates) only evaluates surfels that can reach them.
+  float wx0 = (float)fx0 + poff, wy0 = (float)fy0 + poff;
+  float wx1 = wx0 + (float)(WARP_FX - 1), wy1 = wy0 + (float)(WARP_FY - 1);
 
   const uint2 range = a.ranges[tile_id];
   const int total = (int)(range.y - range.x);
@@ -224,7 +235,15 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 4) render_fwd_kernel(Rend
   id_n2 = load_id(2 * CHUNK);
 
   for (int base = 0, buf = 0; base < total; base += CHUNK, buf ^= 1) {
-    if (__all_sync(RFULL, done)) break;
+    const unsigned act = __ballot_sync(RFULL, !done);
+    if (act == 0u) break;
+    {
+      const unsigned cols = (act | (act >> 8) | (act >> 16) | (act >> 24)) & 0xffu;
+      wx0 = (float)(fx0 + (__ffs(cols) - 1)) + poff;
+      wx1 = (float)(fx0 + (31 - __clz(cols))) + poff;
+      wy0 = (float)(fy0 + ((__ffs(act) - 1) >> 3)) + poff;
+      wy1 = (float)(fy0 + ((31 - __clz(act)) >> 3)) + poff;
+    }
     bool hit_n = false;
     int slot_n = 0, n_n = 0;
     if (base + CHUNK < total) n_n = stage(base + CHUNK, buf ^ 1, id_n, box_n, hit_n, slot_n);
@@ -239,9 +258,6 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 4) render_fwd_kernel(Rend
     if (n_c > 0) {
       const WarpStage& st = s_stage[buf][wid];
       const float* sem_stage = PART ? (s_sem_dyn + (size_t)(buf * NWARP + wid) * CHUNK * MAX_SEMANTIC) : nullptr;
-      // Two fragments are evaluated (geometry, alpha: independent of the pixel's running state)
-      // before they are blended in order: doubles the ILP of the per-pixel dependency chain,
-      // which is what bounds the deepest tiles (thousands of fragments on the same pixels).
       auto blend = [&](const int j, const float alpha, const float depth) -> bool {
         const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
         if (test_T < 0.0001f) {
@@ -301,17 +317,26 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 4) render_fwd_kernel(Rend
         last_contributor = contributor;
         return true;
       };
-      for (int j = 0; j < n_c; j += 2) {
-        float alpha0, depth0, alpha1 = 0.f, depth1 = 0.f;
-        const bool ok0 = frag_eval<PART>(pixf, st.rec[j][0], st.rec[j][1], st.rec[j][2], alpha0, depth0);
-        bool ok1 = false;
-        if (j + 1 < n_c) ok1 = frag_eval<PART>(pixf, st.rec[j + 1][0], st.rec[j + 1][1], st.rec[j + 1][2], alpha1, depth1);
-        bool b0 = false, b1 = false;
-        if (ok0 && !done) b0 = blend(j, alpha0, depth0);
-        if (ok1 && !done) b1 = blend(j + 1, alpha1, depth1);
-        const unsigned m0 = __ballot_sync(RFULL, b0), m1 = __ballot_sync(RFULL, b1);
-        if ((int)lane == j) my_mask = m0;
-        if ((int)lane == j + 1) my_mask = m1;
+      // FWD_ILP fragments are evaluated (geometry, alpha: independent of the pixel's running state)
+      // before they are blended in order.  The deepest tiles (thousands of fragments on the same
+      // pixels, one warp alone on its scheduler at the end of the launch) are bound by the latency
+      // of this chain, not by issue slots.
+      for (int j = 0; j < n_c; j += FWD_ILP) {
+        float alpha[FWD_ILP], depth[FWD_ILP];
+        unsigned ok = 0;
+#pragma unroll
+        for (int u = 0; u < FWD_ILP; u++) {
+          const int ju = min(j + u, CHUNK - 1);
+          if (frag_eval<PART>(pixf, st.rec[ju][0], st.rec[ju][1], st.rec[ju][2], alpha[u], depth[u]) && (j + u < n_c))
+            ok |= 1u << u;
+        }
+#pragma unroll
+        for (int u = 0; u < FWD_ILP; u++) {
+          bool b = false;
+          if (((ok >> u) & 1u) && !done) b = blend(j + u, alpha[u], depth[u]);
+          const unsigned m = __ballot_sync(RFULL, b);
+          if ((int)lane == j + u) my_mask = m;
+        }
       }
     }
     // what backward needs to know about this step: per candidate, the pixels that blended it
@@ -407,7 +432,7 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(Rend
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31, wid = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int tile_id = a.tile_order ? (int)a.tile_order[blockIdx.x] : (int)blockIdx.x;
+  const int tile_id = a.tile_order ? (int)a.tile_order[blockIdx.x + a.tile_begin] : (int)blockIdx.x + a.tile_begin;
   const int tile_x = tile_id % a.grid_x, tile_y = tile_id / a.grid_x;
   const int fx0 = tile_x * TILE_X + (wid & 1) * WARP_FX;
   const int fy0 = tile_y * TILE_Y + (wid >> 1) * WARP_FY;
@@ -661,23 +686,65 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(Rend
 // =============================================================================
 // launchers
 // =============================================================================
-template <bool PART> static void launch_fwd(const RenderFwdArgs& a, cudaStream_t s) {
+// Heavy tiles (the head of tile_order: depth complexity in the thousands) are the critical path of the
+// launch: their warps advance at 1/8 of an SM sub-partition's issue rate while the SM is full, and then
+// finish alone.  They are therefore launched first, on a forked stream, with extra dynamic shared memory
+// so that an SM hosting one of them takes at most one more CTA; the remaining tiles follow on the caller's
+// stream and fill the other SMs.  Fork/join are events, so the sequence stays graph-capturable.
+struct ForkJoin {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool init() {
+    if (side) return true;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
+    cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
+    return true;
+  }
+};
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <bool PART> static void launch_fwd(const RenderFwdArgs& a0, cudaStream_t s) {
+  RenderFwdArgs a = a0;
   const int ntiles = a.grid_x * a.grid_y;
   const size_t dyn = PART ? (size_t)2 * NWARP * CHUNK * MAX_SEMANTIC * sizeof(float) : 0;
-  if (PART) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(render_fwd_kernel<PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-      attr_set = true;
-    }
+  static const int heavy_k = env_int("PGS_HEAVY_TILES", 0);
+  static const int heavy_smem = env_int("PGS_HEAVY_SMEM_KB", 64) * 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(render_fwd_kernel<PART>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)dyn + heavy_smem);
+    attr_set = true;
   }
-  render_fwd_kernel<PART><<<ntiles, TILE_PIX, dyn, s>>>(a);
+  static thread_local ForkJoin fj[16];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int K = (a.tile_order && heavy_k > 0 && ntiles >= 4 * heavy_k && dev < 16 && fj[dev].init()) ? heavy_k : 0;
+  if (K > 0) {
+    ForkJoin& f = fj[dev];
+    cudaEventRecord(f.fork, s);
+    cudaStreamWaitEvent(f.side, f.fork, 0);
+    a.tile_begin = 0;
+    render_fwd_kernel<PART><<<K, TILE_PIX, dyn + heavy_smem, f.side>>>(a);
+    cudaEventRecord(f.join, f.side);
+    count_launch();
+  }
+  a.tile_begin = K;
+  render_fwd_kernel<PART><<<ntiles - K, TILE_PIX, dyn, s>>>(a);
   count_launch();
+  if (K > 0) cudaStreamWaitEvent(s, fj[dev].join, 0);
 }
 void launch_render_fwd(const RenderFwdArgs& a, cudaStream_t s) { launch_fwd<false>(a, s); }
 void launch_render_fwd_part(const RenderFwdArgs& a, cudaStream_t s) { launch_fwd<true>(a, s); }
 
-template <bool PART> static void launch_bwd(const RenderBwdArgs& a, cudaStream_t s) {
+template <bool PART> static void launch_bwd(const RenderBwdArgs& a0, cudaStream_t s) {
+  RenderBwdArgs a = a0;
+  a.tile_begin = 0;
   const int ntiles = a.grid_x * a.grid_y;
   render_bwd_kernel<PART><<<ntiles, TILE_PIX, 0, s>>>(a);
   count_launch();
