@@ -401,32 +401,18 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], unsigned lane) {
   v[0] += __shfl_xor_sync(RFULL, v[0], 1);
   return v[0];
 }
-// Sum c[0..3] over the warp; every lane returns component (lane >> 3).
-__device__ __forceinline__ float warp_reduce4(float (&c)[4], unsigned lane) {
-  {
-    const bool hi = lane & 16;
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-      const float keep = hi ? c[i + 2] : c[i];
-      const float send = hi ? c[i] : c[i + 2];
-      c[i] = keep + __shfl_xor_sync(RFULL, send, 16);
-    }
-  }
-  {
-    const bool hi = lane & 8;
-    const float keep = hi ? c[1] : c[0];
-    const float send = hi ? c[0] : c[1];
-    c[0] = keep + __shfl_xor_sync(RFULL, send, 8);
-  }
-  c[0] += __shfl_xor_sync(RFULL, c[0], 4);
-  c[0] += __shfl_xor_sync(RFULL, c[0], 2);
-  c[0] += __shfl_xor_sync(RFULL, c[0], 1);
-  return c[0];
-}
+// Shared-memory plan of the backward kernel (dynamic): the double-buffered record ring of every warp, then
+// one [RED_COLS][32] float transposition buffer per warp.
+constexpr int RED_COLS = 16;
+constexpr size_t BWD_STAGE_BYTES = 2 * NWARP * sizeof(WarpStage);
+constexpr size_t BWD_SMEM_BYTES = BWD_STAGE_BYTES + (size_t)NWARP * RED_COLS * 32 * sizeof(float);
 
 template <bool PART>
 __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(RenderBwdArgs a) {
-  __shared__ WarpStage s_stage[2][NWARP];
+  extern __shared__ __align__(16) unsigned char bwd_smem[];
+  WarpStage(*s_stage)[NWARP] = reinterpret_cast<WarpStage(*)[NWARP]>(bwd_smem);  // [2][NWARP]
+  // per-warp transposition buffer of the gradient reduction: [RED_COLS][32 lanes]
+  float* red = reinterpret_cast<float*>(bwd_smem + BWD_STAGE_BYTES) + (threadIdx.x >> 5) * (RED_COLS * 32);
 
   const int S = PART ? a.S : 0;
   const int tid = threadIdx.x;
@@ -484,15 +470,12 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(Rend
   for (int i = 0; i < 3; i++) bg_dot_dpixel += a.bg_color[i] * dL_dpixel[i];
   const float Tf_bg = T_final * bg_dot_dpixel;
 
-  float accum_rec[3] = {0.f, 0.f, 0.f};
-  float last_color[3] = {0.f, 0.f, 0.f};
-  float last_alpha = 0;
-  float last_depth = 0;
-  float last_normal[3] = {0.f, 0.f, 0.f};
-  float accum_depth_rec = 0;
-  float accum_alpha_rec = 0;
-  float accum_normal_rec[3] = {0.f, 0.f, 0.f};
-  float last_dL_dT = 0;
+  // The reference keeps one "blend of everything behind me" recurrence per output channel
+  // (accum_rec[3], accum_depth_rec, accum_alpha_rec, accum_normal_rec[3], last_dL_dT; backward.cu:316-372).
+  // They all have the form A <- last_alpha * last_x + (1 - last_alpha) * A and enter dL_dalpha only through
+  // sum_ch g_ch * (x_ch - A_ch) with per-pixel constant upstream gradients g_ch, so one scalar recurrence on
+  // v = sum_ch g_ch * x_ch carries the same information.
+  float last_alpha = 0.f, last_v = 0.f, accum_v = 0.f;
 
   // deepest contributing fragment over the warp's 32 pixels: positions [0, top) matter
   uint32_t top = last_contributor;
@@ -578,18 +561,9 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(Rend
       const float4 q3 = st.rec[j][3];
       const float4 q4 = st.rec[j][4];
       if (valid) {
-        const float normal[3] = {q3.x, q3.y, q3.z};
-        const float col[3] = {q4.x, q4.y, q4.z};
         const float inv_1ma = rcp_approx(1.f - alpha);
         T = T * inv_1ma;
         w = alpha * T;
-        const float one_m_la = 1.f - last_alpha;
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-          accum_rec[ch] = last_alpha * last_color[ch] + one_m_la * accum_rec[ch];
-          last_color[ch] = col[ch];
-          dL_dalpha += (col[ch] - accum_rec[ch]) * dL_dpixel[ch];
-        }
         const float inv_cd = rcp_approx(c_d);
         float m_d, dmd_dd;
         if (PART) {
@@ -599,43 +573,30 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(Rend
           m_d = (PGS_FAR_N / (PGS_FAR_N - PGS_NEAR_N)) * (1.f - PGS_NEAR_N * inv_cd);
           dmd_dd = ((PGS_FAR_N * PGS_NEAR_N) / (PGS_FAR_N - PGS_NEAR_N)) * inv_cd * inv_cd;
         }
-        float dL_dweight = 0;
+        // v = sum over channels of (upstream gradient x this fragment's attribute); the distortion weight
+        // (and, in `_part`, the median-weight gradient) is the attribute of a channel with unit gradient
+        float v = (final_D2 + m_d * m_d * final_A - 2 * m_d * final_D) * dL_dreg;
         if (contributor == median_contributor - 1) {
           dL_dz += dL_dmedian_depth;
-          if (PART) dL_dweight += dL_dmax_dweight;
+          if (PART) v += dL_dmax_dweight;
         }
-        dL_dweight += (final_D2 + m_d * m_d * final_A - 2 * m_d * final_D) * dL_dreg;
-        dL_dalpha += dL_dweight - last_dL_dT;
-        last_dL_dT = dL_dweight * alpha + (1 - alpha) * last_dL_dT;
-        const float dL_dmd = 2.0f * w * (m_d * final_A - final_D) * dL_dreg;
-        dL_dz += dL_dmd * dmd_dd;
-
-        accum_depth_rec = last_alpha * last_depth + one_m_la * accum_depth_rec;
-        last_depth = c_d;
-        dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
-        accum_alpha_rec = last_alpha + one_m_la * accum_alpha_rec;
-        dL_dalpha += (1 - accum_alpha_rec) * dL_daccum;
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-          accum_normal_rec[ch] = last_alpha * last_normal[ch] + one_m_la * accum_normal_rec[ch];
-          last_normal[ch] = normal[ch];
-          dL_dalpha += (normal[ch] - accum_normal_rec[ch]) * dL_dnormal2D[ch];
-        }
-        dL_dalpha *= T;
+        v += q4.x * dL_dpixel[0] + q4.y * dL_dpixel[1] + q4.z * dL_dpixel[2];
+        v += c_d * dL_ddepth + dL_daccum;
+        v += q3.x * dL_dnormal2D[0] + q3.y * dL_dnormal2D[1] + q3.z * dL_dnormal2D[2];
+        accum_v = last_alpha * last_v + (1.f - last_alpha) * accum_v;
+        last_v = v;
         last_alpha = alpha;
-        dL_dalpha -= Tf_bg * inv_1ma;
-        dL_dz += w * dL_ddepth;
+        dL_dalpha = (v - accum_v) * T - Tf_bg * inv_1ma;
+        dL_dz += (2.0f * w * (m_d * final_A - final_D) * dL_dreg) * dmd_dd + w * dL_ddepth;
       }
 
       float g[16];
-      float gc[4];
+      float gc[3];
 #pragma unroll
       for (int ch = 0; ch < 3; ch++) {
         gc[ch] = w * dL_dpixel[ch];
         g[12 + ch] = w * dL_dnormal2D[ch];
       }
-      gc[3] = 0.f;
-      g[15] = 0.f;
       g[11] = G * dL_dalpha;
       const float dL_dG = opa * dL_dalpha;
       // ray-splat branch: gradient w.r.t. the 3x3 transform through s = p.xy / p.z
@@ -661,12 +622,42 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(Rend
       g[9] = use3d ? 0.f : mGGf * d.x;
       g[10] = use3d ? 0.f : mGGf * d.y;
 
-      const float r16 = warp_reduce16(g, lane);
-      const float r4 = warp_reduce4(gc, lane);
+      // Sum the 18 gradient components over the warp's 32 pixels.  16 of them (g[0..14], gc[0]) go through
+      // shared memory: every lane stores its values column-wise (conflict-free), then lanes (2c, 2c+1) each
+      // add one half of column c with four rotated 128-bit loads and exchange halves with one shuffle —
+      // ~40 instructions instead of the ~90 of a select-and-shuffle butterfly.  The two remaining colour
+      // components take a 2-value butterfly in registers.
+      g[15] = gc[0];
+#pragma unroll
+      for (int c = 0; c < RED_COLS; c++) red[c * 32 + lane] = g[c];
+      __syncwarp();
+      float r16;
+      {
+        const int col = lane >> 1;
+        const float4* colp = reinterpret_cast<const float4*>(red + col * 32 + (lane & 1) * 16);
+        const float4 t0 = colp[(0 + col) & 3], t1 = colp[(1 + col) & 3], t2 = colp[(2 + col) & 3],
+                     t3 = colp[(3 + col) & 3];
+        r16 = ((t0.x + t0.y) + (t0.z + t0.w)) + ((t1.x + t1.y) + (t1.z + t1.w)) +
+              (((t2.x + t2.y) + (t2.z + t2.w)) + ((t3.x + t3.y) + (t3.z + t3.w)));
+        r16 += __shfl_xor_sync(RFULL, r16, 1);
+      }
+      float r2;
+      {
+        const bool hi = lane & 16;
+        const float keep = hi ? gc[2] : gc[1];
+        const float send = hi ? gc[1] : gc[2];
+        r2 = keep + __shfl_xor_sync(RFULL, send, 16);
+        r2 += __shfl_xor_sync(RFULL, r2, 8);
+        r2 += __shfl_xor_sync(RFULL, r2, 4);
+        r2 += __shfl_xor_sync(RFULL, r2, 2);
+        r2 += __shfl_xor_sync(RFULL, r2, 1);
+      }
+      __syncwarp();  // `red` is rewritten by the next fragment
       const uint32_t gid = st.id[j];
       float* dst = a.grad + (size_t)gid * GRAD_FLOATS;
-      if ((lane & 1) == 0 && (lane >> 1) != 15) atomicAdd(dst + (lane >> 1), r16);
-      if ((lane & 7) == 0 && (lane >> 3) != 3) atomicAdd(dst + 16 + (lane >> 3), r4);
+      // lanes 0,2,..,28 own dL/dT[9], dL/dmean2D[2], dL/dopacity, dL/dnormal[3]; lane 30 owns colour 0
+      if ((lane & 1) == 0) atomicAdd(dst + (lane >> 1) + (lane == 30 ? 1 : 0), r16);
+      if ((lane & 15) == 0) atomicAdd(dst + 17 + (lane >> 4), r2);
       if (PART && S > 0) {
         // dL/dsem[ch] = sum_pixels alpha*T * dL/dpixel_sem[ch]  (no alpha gradient in the reference fork)
         float gs[16];
@@ -746,7 +737,12 @@ template <bool PART> static void launch_bwd(const RenderBwdArgs& a0, cudaStream_
   RenderBwdArgs a = a0;
   a.tile_begin = 0;
   const int ntiles = a.grid_x * a.grid_y;
-  render_bwd_kernel<PART><<<ntiles, TILE_PIX, 0, s>>>(a);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(render_bwd_kernel<PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES);
+    attr_set = true;
+  }
+  render_bwd_kernel<PART><<<ntiles, TILE_PIX, BWD_SMEM_BYTES, s>>>(a);
   count_launch();
 }
 void launch_render_bwd(const RenderBwdArgs& a, cudaStream_t s) { launch_bwd<false>(a, s); }
