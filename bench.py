@@ -261,7 +261,7 @@ def run(args):
         for h in pending:
             h.wait()
         pending.clear()
-        if world > 1:
+        if world > 1 and not args.no_allreduce:
             from partgs_b200.dist import grad_bucket
             bucket = grad_bucket(grads)  # ours: the five gradients are views of one flat buffer
             for t in ([bucket] if bucket is not None else grads):
@@ -279,11 +279,11 @@ def run(args):
         torch.cuda.synchronize()
 
     # ---- warm-up ---------------------------------------------------------------------
-    # W warm-up steps; additionally every camera of this rank is rendered once (untimed) so that
-    # the caching allocator has seen each view's instance count before the timed region
+    # every camera of this rank is rendered once (untimed) so that the instance arena has seen each
+    # view's size, then W more warm-up steps let the caching allocator settle before the timed region
     n_warm = max(args.warmup, 3)
     views_per_rank = (len(all_cams) + world - 1) // world  # same count on every rank (collectives must match)
-    for i in range(max(n_warm, min(views_per_rank, 64))):
+    for i in range(min(views_per_rank, 64) + n_warm):
         one_step(i)
     for h in pending:
         h.wait()
@@ -402,7 +402,8 @@ def run(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{name}: {P} surfels, {W}x{H}, fwd+bwd, all 10 output channels get gradient",
                    "views": cfg["views"], "views_per_rank": len(my_cams), "sharding": "by camera",
-                   "collective": "nccl all-reduce of 232 B/surfel parameter gradients per step" if world > 1 else "none",
+                   "collective": ("nccl all-reduce of 232 B/surfel parameter gradients per step (one bucket)"
+                                  if world > 1 and not args.no_allreduce else "none"),
                    "l2": "inputs (232 MB parameters + per-view state) exceed the 126 MB L2; views cycle every step",
                    "V_visible": V, "R_instances": int(R)},
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
@@ -460,6 +461,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-allreduce", action="store_true",
+                    help="diagnostic: skip the gradient all-reduce at N>1 (shows what the collective costs)")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")

@@ -114,41 +114,55 @@ def current_stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-class ByteBuffer:
-    """Growable device byte buffer handed to the library through the alloc callback
-    (the role resizeFunctional plays in the reference glue, rasterize_points.cu:31-37).
+class AllocScope:
+    """Device byte buffers handed to the library through its alloc callbacks (the role resizeFunctional
+    plays in the reference glue, rasterize_points.cu:31-37).  One scope per native call::
 
-    Tagged buffers (the per-instance binning arena, whose size changes with every view) come from a
-    small grow-only pool per (device, stream, tag) instead of a fresh ``torch.empty`` per frame: a
-    frame-to-frame varying request of a few hundred MB makes the caching allocator split / re-grow
-    segments (cudaMalloc inside the step).  An arena is handed out again only when nothing but the
-    pool references it any more (autograd has released the previous frame's saved state)."""
+        with AllocScope(dev) as sc:
+            lib.pgs_dsr_forward(ALLOC_CB, sc.GEOM, ALLOC_CB, sc.BINNING, ALLOC_CB, sc.IMAGE, ...)
+        geom, binning, img = sc.tensor(sc.GEOM), ...
 
+    A single module-level C callback serves every call (the `user` pointer carries the slot), so no
+    per-call closure / reference cycle keeps a buffer alive after the call returns.
+
+    The per-instance binning arena, whose size changes with every view, comes from a small grow-only
+    pool per (device, stream) instead of a fresh ``torch.empty`` per frame: a frame-to-frame varying
+    request of a few hundred MB makes the caching allocator split / re-grow segments (cudaMalloc inside
+    the step).  An arena is handed out again only when nothing but the pool references it any more
+    (autograd has released the previous frame's saved state)."""
+
+    GEOM, BINNING, IMAGE = 1, 2, 3
     _pool = {}
 
-    def __init__(self, device, tag=None):
+    def __init__(self, device):
         self.device = device
-        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        self.tensors = {}
         self.error = None
 
-        def _cb(nbytes, _user):
-            try:
-                nbytes = int(nbytes)
-                if tag is None:
-                    self.tensor = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-                else:
-                    self.tensor = self._from_pool(nbytes, tag)
-                return self.tensor.data_ptr()
-            except Exception as ex:  # surfaced by the caller; returning NULL makes the C side fail cleanly
-                self.error = ex
-                return None
+    def __enter__(self):
+        _tls.scope = self
+        return self
 
-        self.callback = ALLOC_FN(_cb)
+    def __exit__(self, *exc):
+        _tls.scope = None
+        return False
 
-    def _from_pool(self, nbytes, tag):
+    def tensor(self, slot):
+        t = self.tensors.get(slot)
+        return t if t is not None else torch.empty(0, dtype=torch.uint8, device=self.device)
+
+    def _alloc(self, nbytes, slot):
+        if slot == AllocScope.BINNING:
+            t = self._from_pool(nbytes)
+        else:
+            t = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.tensors[slot] = t
+        return t.data_ptr()
+
+    def _from_pool(self, nbytes):
         import sys
-        key = (str(self.device), torch.cuda.current_stream(self.device).cuda_stream, tag)
-        pool = ByteBuffer._pool.setdefault(key, [])
+        key = (str(self.device), torch.cuda.current_stream(self.device).cuda_stream)
+        pool = AllocScope._pool.setdefault(key, [])
         hwm = max([nbytes] + [t.numel() for t in pool])
         for i in range(len(pool)):
             t = pool[i]
@@ -156,12 +170,33 @@ class ByteBuffer:
             # object, and no C++ owner (autograd's saved tensors) holds the TensorImpl
             if t._use_count() == 1 and sys.getrefcount(t) <= 3:
                 if t.numel() < nbytes:
-                    t = torch.empty(hwm, dtype=torch.uint8, device=self.device)  # grow: replace the small arena
+                    # grow with 25 % headroom: few growth events, so the caching allocator settles quickly
+                    t = pool[i] = None
+                    t = torch.empty(hwm + hwm // 4, dtype=torch.uint8, device=self.device)
                     pool[i] = t
                 return t
         t = torch.empty(hwm, dtype=torch.uint8, device=self.device)
         pool.append(t)
         return t
+
+
+import threading as _threading
+
+_tls = _threading.local()
+
+
+def _alloc_cb(nbytes, user):
+    scope = getattr(_tls, "scope", None)
+    if scope is None:
+        return None
+    try:
+        return scope._alloc(int(nbytes), int(user or 0))
+    except Exception as ex:  # surfaced by the caller; returning NULL makes the C side fail cleanly
+        scope.error = ex
+        return None
+
+
+ALLOC_CB = ALLOC_FN(_alloc_cb)
 
 
 def require_cuda_float(t: torch.Tensor, name: str) -> torch.Tensor:

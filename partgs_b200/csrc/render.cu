@@ -153,14 +153,21 @@ void launch_tile_order(const uint2* ranges, int ntiles, uint32_t* order, cudaStr
 // =============================================================================
 template <bool PART>
 __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : PGS_FWD_MINB) render_fwd_kernel(RenderFwdArgs a) {
-  __shared__ WarpStage s_stage[2][NWARP];
-  extern __shared__ float s_sem_dyn[];  // PART: [2][NWARP][CHUNK][MAX_SEMANTIC]
+  // dynamic shared memory: WarpStage [2][nw], then (PART) the semantic staging [2][nw][CHUNK][MAX_SEMANTIC];
+  // nw = warps per CTA (8 = whole tile; 4/2/1 when the image has too few tiles to fill the GPU)
+  extern __shared__ __align__(16) unsigned char fwd_smem[];
+  const int nw = blockDim.x >> 5;
+  WarpStage* s_stage = reinterpret_cast<WarpStage*>(fwd_smem);
+  float* s_sem_dyn = reinterpret_cast<float*>(fwd_smem + (size_t)2 * nw * sizeof(WarpStage));
 
   const int S = PART ? a.S : 0;
-  const int tid = threadIdx.x;
-  const unsigned lane = tid & 31, wid = tid >> 5;
+  const unsigned lane = threadIdx.x & 31, lw = threadIdx.x >> 5;  // lw: warp within the CTA
+  const int groups = NWARP / nw;                                  // CTAs per tile
+  const unsigned wid = (blockIdx.x % groups) * nw + lw;           // footprint (0..7) within the tile
+  const int tid = wid * 32 + lane;                                // pixel slot within the tile
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int tile_id = a.tile_order ? (int)a.tile_order[blockIdx.x + a.tile_begin] : (int)blockIdx.x + a.tile_begin;
+  const int tile_slot = blockIdx.x / groups + a.tile_begin;
+  const int tile_id = a.tile_order ? (int)a.tile_order[tile_slot] : tile_slot;
   const int tile_x = tile_id % a.grid_x, tile_y = tile_id / a.grid_x;
   const int fx0 = tile_x * TILE_X + (wid & 1) * WARP_FX;
   const int fy0 = tile_y * TILE_Y + (wid >> 1) * WARP_FY;
@@ -207,13 +214,13 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : PGS_FWD_MINB) render_fwd_
     const unsigned m = __ballot_sync(RFULL, hit);
     slot = __popc(m & lt_mask);
     if (hit) {
-      WarpStage& st = s_stage[buf][wid];
+      WarpStage& st = s_stage[buf * nw + lw];
       const float4* src = a.rec + (size_t)id * REC_QUADS;
 #pragma unroll
       for (int q = 0; q < REC_QUADS; q++) cp_async16(&st.rec[slot][q], src + q);
       st.pos[slot] = (uint32_t)(base + lane + 1);
       if (PART) {
-        float* sem_stage = s_sem_dyn + ((size_t)(buf * NWARP + wid) * CHUNK + slot) * MAX_SEMANTIC;
+        float* sem_stage = s_sem_dyn + ((size_t)(buf * nw + lw) * CHUNK + slot) * MAX_SEMANTIC;
         const float* sem = a.semantics + (size_t)id * S;
         for (int ch = 0; ch < S; ch++) sem_stage[ch] = __ldg(sem + ch);
       }
@@ -256,8 +263,8 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : PGS_FWD_MINB) render_fwd_
 
     uint32_t my_mask = 0;  // lane j: pixels that blended the survivor in slot j
     if (n_c > 0) {
-      const WarpStage& st = s_stage[buf][wid];
-      const float* sem_stage = PART ? (s_sem_dyn + (size_t)(buf * NWARP + wid) * CHUNK * MAX_SEMANTIC) : nullptr;
+      const WarpStage& st = s_stage[buf * nw + lw];
+      const float* sem_stage = PART ? (s_sem_dyn + (size_t)(buf * nw + lw) * CHUNK * MAX_SEMANTIC) : nullptr;
       auto blend = [&](const int j, const float alpha, const float depth) -> bool {
         const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
         if (test_T < 0.0001f) {
@@ -404,21 +411,26 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], unsigned lane) {
 // Shared-memory plan of the backward kernel (dynamic): the double-buffered record ring of every warp, then
 // one [RED_COLS][32] float transposition buffer per warp.
 constexpr int RED_COLS = 16;
-constexpr size_t BWD_STAGE_BYTES = 2 * NWARP * sizeof(WarpStage);
-constexpr size_t BWD_SMEM_BYTES = BWD_STAGE_BYTES + (size_t)NWARP * RED_COLS * 32 * sizeof(float);
+constexpr size_t bwd_smem_bytes(int nw) {
+  return (size_t)2 * nw * sizeof(WarpStage) + (size_t)nw * RED_COLS * 32 * sizeof(float);
+}
 
 template <bool PART>
 __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(RenderBwdArgs a) {
   extern __shared__ __align__(16) unsigned char bwd_smem[];
-  WarpStage(*s_stage)[NWARP] = reinterpret_cast<WarpStage(*)[NWARP]>(bwd_smem);  // [2][NWARP]
+  const int nw = blockDim.x >> 5;  // warps per CTA (8 = whole tile)
+  WarpStage* s_stage = reinterpret_cast<WarpStage*>(bwd_smem);  // [2][nw]
   // per-warp transposition buffer of the gradient reduction: [RED_COLS][32 lanes]
-  float* red = reinterpret_cast<float*>(bwd_smem + BWD_STAGE_BYTES) + (threadIdx.x >> 5) * (RED_COLS * 32);
+  float* red = reinterpret_cast<float*>(bwd_smem + (size_t)2 * nw * sizeof(WarpStage)) + (threadIdx.x >> 5) * (RED_COLS * 32);
 
   const int S = PART ? a.S : 0;
-  const int tid = threadIdx.x;
-  const unsigned lane = tid & 31, wid = tid >> 5;
+  const unsigned lane = threadIdx.x & 31, lw = threadIdx.x >> 5;
+  const int groups = NWARP / nw;
+  const unsigned wid = (blockIdx.x % groups) * nw + lw;
+  const int tid = wid * 32 + lane;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int tile_id = a.tile_order ? (int)a.tile_order[blockIdx.x + a.tile_begin] : (int)blockIdx.x + a.tile_begin;
+  const int tile_slot = blockIdx.x / groups + a.tile_begin;
+  const int tile_id = a.tile_order ? (int)a.tile_order[tile_slot] : tile_slot;
   const int tile_x = tile_id % a.grid_x, tile_y = tile_id / a.grid_x;
   const int fx0 = tile_x * TILE_X + (wid & 1) * WARP_FX;
   const int fy0 = tile_y * TILE_Y + (wid >> 1) * WARP_FY;
@@ -498,7 +510,7 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(Rend
     const unsigned m = __ballot_sync(RFULL, hit);
     if (hit) {
       const int slot = __popc(m & lt_mask);
-      WarpStage& st = s_stage[buf][wid];
+      WarpStage& st = s_stage[buf * nw + lw];
       const float4* src = a.rec + (size_t)id * REC_QUADS;
 #pragma unroll
       for (int q = 0; q < REC_QUADS; q++) cp_async16(&st.rec[slot][q], src + q);
@@ -528,7 +540,7 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(Rend
     cp_async_wait<1>();
     __syncwarp();
 
-    const WarpStage& st = s_stage[buf][wid];
+    const WarpStage& st = s_stage[buf * nw + lw];
     for (int j = 0; j < n_c; j++) {
       const uint32_t contributor = st.pos[j];
       const bool valid = (st.mask[j] >> lane) & 1u;  // this pixel blended the surfel in forward
@@ -700,16 +712,32 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+// Warps per CTA.  A whole tile (8 warps) per CTA is the default; images with few tiles (e.g. the
+// 400x300 DTU training resolution: 475 tiles for 592 CTA slots) are launched in finer units so that
+// the block scheduler can balance the warps of heavy tiles over all SMs.
+static int warps_per_cta(int ntiles) {
+  static const int forced = env_int("PGS_WARPS_PER_CTA", 0);
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
+  if (ntiles >= 3000) return 8;
+  if (ntiles >= 1500) return 4;
+  if (ntiles >= 750) return 2;
+  return 1;
+}
+
 template <bool PART> static void launch_fwd(const RenderFwdArgs& a0, cudaStream_t s) {
   RenderFwdArgs a = a0;
   const int ntiles = a.grid_x * a.grid_y;
-  const size_t dyn = PART ? (size_t)2 * NWARP * CHUNK * MAX_SEMANTIC * sizeof(float) : 0;
+  const int nw = warps_per_cta(ntiles);
+  const int groups = NWARP / nw;
+  const size_t smem = (size_t)2 * nw * sizeof(WarpStage) +
+                      (PART ? (size_t)2 * nw * CHUNK * MAX_SEMANTIC * sizeof(float) : 0);
   static const int heavy_k = env_int("PGS_HEAVY_TILES", 0);
   static const int heavy_smem = env_int("PGS_HEAVY_SMEM_KB", 64) * 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(render_fwd_kernel<PART>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)dyn + heavy_smem);
+    const size_t mx = (size_t)2 * NWARP * sizeof(WarpStage) +
+                      (PART ? (size_t)2 * NWARP * CHUNK * MAX_SEMANTIC * sizeof(float) : 0) + heavy_smem;
+    cudaFuncSetAttribute(render_fwd_kernel<PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
     attr_set = true;
   }
   static thread_local ForkJoin fj[16];
@@ -721,12 +749,12 @@ template <bool PART> static void launch_fwd(const RenderFwdArgs& a0, cudaStream_
     cudaEventRecord(f.fork, s);
     cudaStreamWaitEvent(f.side, f.fork, 0);
     a.tile_begin = 0;
-    render_fwd_kernel<PART><<<K, TILE_PIX, dyn + heavy_smem, f.side>>>(a);
+    render_fwd_kernel<PART><<<K * groups, 32 * nw, smem + heavy_smem, f.side>>>(a);
     cudaEventRecord(f.join, f.side);
     count_launch();
   }
   a.tile_begin = K;
-  render_fwd_kernel<PART><<<ntiles - K, TILE_PIX, dyn, s>>>(a);
+  render_fwd_kernel<PART><<<(ntiles - K) * groups, 32 * nw, smem, s>>>(a);
   count_launch();
   if (K > 0) cudaStreamWaitEvent(s, fj[dev].join, 0);
 }
@@ -737,12 +765,14 @@ template <bool PART> static void launch_bwd(const RenderBwdArgs& a0, cudaStream_
   RenderBwdArgs a = a0;
   a.tile_begin = 0;
   const int ntiles = a.grid_x * a.grid_y;
+  const int nw = warps_per_cta(ntiles);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(render_bwd_kernel<PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES);
+    cudaFuncSetAttribute(render_bwd_kernel<PART>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)bwd_smem_bytes(NWARP));
     attr_set = true;
   }
-  render_bwd_kernel<PART><<<ntiles, TILE_PIX, BWD_SMEM_BYTES, s>>>(a);
+  render_bwd_kernel<PART><<<ntiles * (NWARP / nw), 32 * nw, bwd_smem_bytes(nw), s>>>(a);
   count_launch();
 }
 void launch_render_bwd(const RenderBwdArgs& a, cudaStream_t s) { launch_bwd<false>(a, s); }

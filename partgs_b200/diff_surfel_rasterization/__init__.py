@@ -56,27 +56,26 @@ def _native_forward(bg, means3D, colors, opacity, scales, rotations, scale_modif
     out_color = torch.empty((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
     out_others = torch.empty((NUM_AUX, H, W), dtype=torch.float32, device=dev)
     radii = torch.empty((P,), dtype=torch.int32, device=dev)
-    geom, binning, img = _lib.ByteBuffer(dev), _lib.ByteBuffer(dev, tag="binning"), _lib.ByteBuffer(dev)
+    sc = _lib.AllocScope(dev)
     rendered = 0
     if P != 0:
         M = sh.size(1) if sh.numel() != 0 else 0
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), sc:
             rc = lib.pgs_dsr_forward(
-                geom.callback, None, binning.callback, None, img.callback, None, P, int(degree), int(M),
+                _lib.ALLOC_CB, sc.GEOM, _lib.ALLOC_CB, sc.BINNING, _lib.ALLOC_CB, sc.IMAGE, P, int(degree), int(M),
                 _lib.ptr(bg), W, H, _lib.ptr(means3D), _lib.ptr(sh), _lib.ptr(colors), _lib.ptr(opacity),
                 _lib.ptr(scales), float(scale_modifier), _lib.ptr(rotations), _lib.ptr(transMat_precomp),
                 _lib.ptr(viewmatrix), _lib.ptr(projmatrix), _lib.ptr(campos), float(tan_fovx), float(tan_fovy),
                 int(bool(prefiltered)), _lib.ptr(out_color), _lib.ptr(out_others), _lib.ptr(radii),
                 int(bool(debug)), _lib.current_stream(dev))
-        for b in (geom, binning, img):
-            if b.error is not None:
-                raise b.error
+        if sc.error is not None:
+            raise sc.error
         rendered = _lib.check(rc, "pgs_dsr_forward")
     else:
         # reference: zero images and no state when there is nothing to draw (rasterize_points.cu:85-99)
         out_color.zero_()
         out_others.zero_()
-    return rendered, out_color, out_others, radii, geom.tensor, binning.tensor, img.tensor
+    return rendered, out_color, out_others, radii, sc.tensor(sc.GEOM), sc.tensor(sc.BINNING), sc.tensor(sc.IMAGE)
 
 
 def _carve_bucket(dev, shapes, align_elems=64):

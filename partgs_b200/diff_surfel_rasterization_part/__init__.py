@@ -58,27 +58,26 @@ def _native_forward(bg, means3D, colors, opacity, semantics, scales, rotations, 
     out_semantic = torch.empty((S, H, W), **f32)
     out_others = torch.empty((NUM_AUX, H, W), **f32)
     radii = torch.empty((P,), dtype=torch.int32, device=dev)
-    geom, binning, img = _lib.ByteBuffer(dev), _lib.ByteBuffer(dev, tag="binning"), _lib.ByteBuffer(dev)
+    sc = _lib.AllocScope(dev)
     rendered = 0
     if P != 0:
         M = sh.size(1) if sh.numel() != 0 else 0
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), sc:
             rc = lib.pgs_dsrp_forward(
-                geom.callback, None, binning.callback, None, img.callback, None, P, int(degree), int(M), _lib.ptr(bg),
+                _lib.ALLOC_CB, sc.GEOM, _lib.ALLOC_CB, sc.BINNING, _lib.ALLOC_CB, sc.IMAGE, P, int(degree), int(M), _lib.ptr(bg),
                 W, H, S, _lib.ptr(means3D), _lib.ptr(sh), _lib.ptr(colors), _lib.ptr(semantics), _lib.ptr(opacity),
                 _lib.ptr(scales), float(scale_modifier), _lib.ptr(rotations), _lib.ptr(transMat_precomp),
                 _lib.ptr(viewmatrix), _lib.ptr(projmatrix), _lib.ptr(campos), float(tan_fovx), float(tan_fovy),
                 int(bool(prefiltered)), _lib.ptr(out_color), _lib.ptr(out_semantic), _lib.ptr(out_others),
                 _lib.ptr(radii), int(bool(debug)), _lib.current_stream(dev))
-        for b in (geom, binning, img):
-            if b.error is not None:
-                raise b.error
+        if sc.error is not None:
+            raise sc.error
         rendered = _lib.check(rc, "pgs_dsrp_forward")
     else:
         out_color.zero_()
         out_semantic.zero_()
         out_others.zero_()
-    return rendered, out_color, out_semantic, out_others, radii, geom.tensor, binning.tensor, img.tensor
+    return rendered, out_color, out_semantic, out_others, radii, sc.tensor(sc.GEOM), sc.tensor(sc.BINNING), sc.tensor(sc.IMAGE)
 
 
 def _native_backward(bg, means3D, radii, colors, semantics, scales, rotations, scale_modifier, transMat_precomp,

@@ -1,0 +1,96 @@
+"""fwd+bwd device time of every BASELINE.json config (C1..C5), ours vs the unmodified reference CUDA build
+(oracle/_ref), plus distCUDA2 and the superquadric->surfel kernels.  One JSON line per measurement.
+
+usage: python tools/config_table.py [--cfgs C1,C2,C3,C4,C5] [--views 6] [--reps 3]
+"""
+import argparse, json, statistics, sys
+from pathlib import Path
+import torch
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+from partgs_b200 import synth, _lib  # noqa: E402
+import parity_utils as pu  # noqa: E402
+from oracle import ref_cuda  # noqa: E402
+
+
+def timed(fn, reps):
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return ts
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cfgs", default="C1,C2,C3,C4,C5"); ap.add_argument("--views", type=int, default=6)
+    ap.add_argument("--reps", type=int, default=3)
+    a = ap.parse_args()
+    dev = "cuda"
+    for name in a.cfgs.split(","):
+        cfg = dict(synth.CONFIGS[name]); nv = min(cfg["views"], a.views)
+        cfg, scene, cams = synth.make_config(name, device=dev, views=nv)
+        S, W, H = cfg["S"], cfg["W"], cfg["H"]
+        bg = torch.zeros(3, device=dev)
+        g = synth.upstream_grads(W, H, synth.SEED_BASE, n_aux=8 if S else 7, S=S, device=dev)
+        part = S > 0
+        if part:
+            sys.path.insert(0, str(ROOT / "tests"))
+            import test_gpu_part_raster as tp
+            ours = lambda cam: tp.run_ours(scene, cam, bg, g)
+            def ref(cam):
+                f = ref_cuda.forward_part(scene, cam, bg)
+                ref_cuda.backward_part(f, scene, cam, bg, g["color"], g["semantic"], g["allmap"])
+            have_ref = ref_cuda.available("ref_dsrp_C")
+        else:
+            ours = lambda cam: pu.run_ours(scene, cam, bg, grads=g)
+            def ref(cam):
+                f = ref_cuda.forward(scene, cam, bg)
+                ref_cuda.backward(f, scene, cam, bg, g["color"], g["allmap"])
+            have_ref = ref_cuda.available("ref_dsr_C")
+        res = {}
+        for label, fn in (("ours", ours), ("reference", ref)):
+            if label == "reference" and not have_ref:
+                continue
+            for cam in cams:       # warm-up: every view once
+                fn(cam)
+            torch.cuda.synchronize()
+            if label == "ours":
+                _lib.timing_enable(True); _lib.timing_read(reset=True)
+            ts = []
+            for cam in cams:
+                ts += timed(lambda: fn(cam), a.reps)
+            res[label] = statistics.median(ts)
+            if label == "ours":
+                st = _lib.timing_read(reset=True); _lib.timing_enable(False)
+                n = len(cams) * a.reps
+                res["stage_ms"] = {k: round(v[0] / n, 4) for k, v in st.items() if v[1]}
+        o = pu.run_ours_raw(scene, cams[0], bg) if not part else None
+        out = dict(cfg=name, P=cfg["P"], W=W, H=H, S=S, views=nv, fork="part" if part else "base",
+                   ours_ms=round(res["ours"], 4), ours_fps=round(1e3 / res["ours"], 1),
+                   reference_ms=round(res.get("reference", float("nan")), 4),
+                   speedup=round(res.get("reference", float("nan")) / res["ours"], 2), stage_ms=res["stage_ms"])
+        if o is not None:
+            out["R_view0"] = int(o["num_rendered"]); out["V_view0"] = int((o["radii"] > 0).sum())
+        print(json.dumps(out), flush=True)
+        del scene, cams, g
+        torch.cuda.empty_cache()
+
+    # distCUDA2 and superquadric->surfel (C1 / C5 shapes)
+    from partgs_b200.simple_knn._C import distCUDA2
+    for n in (100_000, 1_000_000, 3_000_000):
+        pts = torch.randn(n, 3, device=dev)
+        distCUDA2(pts); torch.cuda.synchronize()
+        t = statistics.median(timed(lambda: distCUDA2(pts), 5))
+        row = dict(kernel="distCUDA2", P=n, ours_ms=round(t, 4))
+        if ref_cuda.available("ref_knn_C"):
+            K = ref_cuda.load("ref_knn_C")
+            K.distCUDA2(pts); torch.cuda.synchronize()
+            row["reference_ms"] = round(statistics.median(timed(lambda: K.distCUDA2(pts), 3)), 4)
+            row["speedup"] = round(row["reference_ms"] / row["ours_ms"], 1)
+        print(json.dumps(row), flush=True)
+
+
+if __name__ == "__main__":
+    main()
