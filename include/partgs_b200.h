@@ -70,7 +70,8 @@ size_t pgs_dsr_backward_scratch_bytes(int P);
 
 /* Replaces CudaRasterizer::Rasterizer::backward (DSR/cuda_rasterizer/rasterizer.h:63-94,
  * rasterizer_impl.cu:346-448).  R = num_rendered returned by the forward call that
- * filled the three buffers.  All nine gradient arrays are fully written (no
+ * filled the three buffers; binning_bytes = the size the binning callback was asked for by
+ * that call (the arena is laid out for a capacity >= R that backward recovers from it).  All nine gradient arrays are fully written (no
  * pre-zeroing required): dL_dmean2D [P,3], dL_dopacity [P], dL_dcolor [P,3],
  * dL_dmean3D [P,3], dL_dtransMat [P,9], dL_dsh [P,M,3], dL_dscale [P,2], dL_drot [P,4].
  * `scratch` replaces the reference's internal dL_dnormal [P,3] tensor. */
@@ -78,8 +79,8 @@ int pgs_dsr_backward(int P, int D, int M, int R, const float* background, int wi
                      const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
                      float scale_modifier, const float* rotations, const float* transMat_precomp,
                      const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
-                     float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
-                     const float* dL_dpix, const float* dL_dothers, float* dL_dmean2D, float* scratch,
+                     float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, size_t binning_bytes,
+                     char* image_buffer, const float* dL_dpix, const float* dL_dothers, float* dL_dmean2D, float* scratch,
                      float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh,
                      float* dL_dscale, float* dL_drot, int debug, void* stream);
 
@@ -103,7 +104,8 @@ int pgs_dsrp_backward(int P, int D, int M, int R, const float* background, int w
                       const float* scales, float scale_modifier, const float* rotations,
                       const float* transMat_precomp, const float* viewmatrix, const float* projmatrix,
                       const float* campos, float tan_fovx, float tan_fovy, const int* radii, char* geom_buffer,
-                      char* binning_buffer, char* image_buffer, const float* dL_dpix, const float* dL_dsemantic_pix,
+                      char* binning_buffer, size_t binning_bytes, char* image_buffer, const float* dL_dpix,
+                      const float* dL_dsemantic_pix,
                       const float* dL_dothers, float* dL_dmean2D, float* scratch, float* dL_dopacity, float* dL_dcolor,
                       float* dL_dsemantics, float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh, float* dL_dscale,
                       float* dL_drot, int debug, void* stream);
@@ -176,7 +178,7 @@ typedef struct {
   int rec_floats;  /* floats per surfel record */
   int tile_pixels; /* per-pixel state is tile-major [tile][256] */
 } pgs_dsr_layout;
-int pgs_dsr_get_layout(int P, int width, int height, int R, pgs_dsr_layout* out);
+int pgs_dsr_get_layout(int P, int width, int height, size_t binning_bytes, pgs_dsr_layout* out);
 
 #ifdef __cplusplus
 }

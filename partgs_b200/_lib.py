@@ -43,16 +43,16 @@ SIGNATURES = {
     "pgs_dsr_backward_scratch_bytes": (C.c_size_t, [C.c_int]),
     "pgs_dsr_backward": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, _f32p, _f32p,
                                    _f32p, _f32p, C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float,
-                                   C.c_float, _vp, _vp, _vp, _vp, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
-                                   _f32p, _f32p, _f32p, _f32p, C.c_int, _vp]),
+                                   C.c_float, _vp, _vp, _vp, C.c_size_t, _vp, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
+                                   _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _vp]),
     "pgs_dsrp_forward": (C.c_int, [ALLOC_FN, _vp, ALLOC_FN, _vp, ALLOC_FN, _vp, C.c_int, C.c_int, C.c_int,
                                    _f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
                                    C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_int,
                                    _f32p, _f32p, _f32p, _vp, C.c_int, _vp]),
     "pgs_dsrp_backward": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, _f32p,
                                     _f32p, _f32p, _f32p, _f32p, C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p,
-                                    C.c_float, C.c_float, _vp, _vp, _vp, _vp, _f32p, _f32p, _f32p, _f32p, _f32p,
-                                    _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _vp]),
+                                    C.c_float, C.c_float, _vp, _vp, _vp, C.c_size_t, _vp, _f32p, _f32p, _f32p, _f32p,
+                                    _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _vp]),
     "pgs_mark_visible": (C.c_int, [C.c_int, _f32p, _f32p, _f32p, _vp, _vp]),
     "pgs_sq2surfel_forward": (C.c_int, [C.c_int] * 4 + [_f32p] * 7 + [_vp, _f32p, _f32p, C.c_float, C.c_float] +
                               [_f32p] * 5 + [_vp]),
@@ -68,7 +68,7 @@ SIGNATURES = {
     "pgs_dsr_duplicate_with_keys": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "pgs_identify_tile_ranges": (C.c_int, [C.c_int, _vp, _vp, C.c_int, _vp]),
     "pgs_higher_msb": (C.c_uint32, [C.c_uint32]),
-    "pgs_dsr_get_layout": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DsrLayout)]),
+    "pgs_dsr_get_layout": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(DsrLayout)]),
 }
 
 _lib = None
@@ -123,16 +123,11 @@ class AllocScope:
         geom, binning, img = sc.tensor(sc.GEOM), ...
 
     A single module-level C callback serves every call (the `user` pointer carries the slot), so no
-    per-call closure / reference cycle keeps a buffer alive after the call returns.
-
-    The per-instance binning arena, whose size changes with every view, comes from a small grow-only
-    pool per (device, stream) instead of a fresh ``torch.empty`` per frame: a frame-to-frame varying
-    request of a few hundred MB makes the caching allocator split / re-grow segments (cudaMalloc inside
-    the step).  An arena is handed out again only when nothing but the pool references it any more
-    (autograd has released the previous frame's saved state)."""
+    per-call closure / reference cycle keeps a buffer alive after the call returns.  The library sizes
+    the per-instance binning arena for a grow-only capacity, so the request is the same every frame and
+    torch's caching allocator hands back the same block."""
 
     GEOM, BINNING, IMAGE = 1, 2, 3
-    _pool = {}
 
     def __init__(self, device):
         self.device = device
@@ -152,32 +147,9 @@ class AllocScope:
         return t if t is not None else torch.empty(0, dtype=torch.uint8, device=self.device)
 
     def _alloc(self, nbytes, slot):
-        if slot == AllocScope.BINNING:
-            t = self._from_pool(nbytes)
-        else:
-            t = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        t = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         self.tensors[slot] = t
         return t.data_ptr()
-
-    def _from_pool(self, nbytes):
-        import sys
-        key = (str(self.device), torch.cuda.current_stream(self.device).cuda_stream)
-        pool = AllocScope._pool.setdefault(key, [])
-        hwm = max([nbytes] + [t.numel() for t in pool])
-        for i in range(len(pool)):
-            t = pool[i]
-            # free <=> only the pool list, the local `t` and getrefcount's argument reference the Python
-            # object, and no C++ owner (autograd's saved tensors) holds the TensorImpl
-            if t._use_count() == 1 and sys.getrefcount(t) <= 3:
-                if t.numel() < nbytes:
-                    # grow with 25 % headroom: few growth events, so the caching allocator settles quickly
-                    t = pool[i] = None
-                    t = torch.empty(hwm + hwm // 4, dtype=torch.uint8, device=self.device)
-                    pool[i] = t
-                return t
-        t = torch.empty(hwm, dtype=torch.uint8, device=self.device)
-        pool.append(t)
-        return t
 
 
 import threading as _threading

@@ -2,6 +2,7 @@
 // base rasteriser: buffer carving, kernel sequencing on the caller's stream.
 // Mirrors the call order of reference CudaRasterizer::Rasterizer::forward/backward
 // (cuda_rasterizer/rasterizer_impl.cu:198-342, 346-448).
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -59,6 +60,24 @@ struct StageTimer {
   }
 };
 
+// pinned host word + event through which forward reads the instance count of the frame in flight
+struct CountFetch {
+  int* host = nullptr;
+  cudaEvent_t ev = nullptr;
+  bool init() {
+    if (host) return true;
+    if (cudaHostAlloc((void**)&host, 64, cudaHostAllocDefault) != cudaSuccess) { host = nullptr; return false; }
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return false;
+    return true;
+  }
+};
+static CountFetch& count_fetch() {
+  static thread_local CountFetch cf[16];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return cf[dev & 15];
+}
+
 // reference getHigherMsb (rasterizer_impl.cu:35-50)
 static uint32_t higher_msb(uint32_t n) {
   uint32_t msb = sizeof(n) * 4;
@@ -114,15 +133,16 @@ struct BinningState {
   uint32_t* frag_mask;  // [8 warps][mask_stride]: forward's per-warp blend masks (render.cu)
   size_t mask_stride;
   char* sort_temp;
-  // The arena is laid out for R rounded up to 512 Ki instances: the request the caller's
-  // allocator sees then takes only a handful of distinct sizes across views, so a caching
-  // allocator (torch) reuses blocks instead of growing / fragmenting every frame.
-  static BinningState from(char*& p, size_t R_exact, int end_bit) {
-    const size_t R = align_up(R_exact > 0 ? R_exact : 1, (size_t)1 << 19);
+  // The arena is laid out for a CAPACITY (a multiple of 512 Ki instances), not for the frame's exact
+  // instance count: forward launches binning + render before the host has read the count (see
+  // forward_impl), and a capacity that only ever grows makes the request the caller's allocator sees
+  // constant from frame to frame.  Backward recovers the capacity from the buffer size.
+  static constexpr size_t GRAIN = (size_t)1 << 19;
+  static size_t capacity_for(size_t instances) { return align_up(instances > 0 ? instances : 1, GRAIN); }
+  static BinningState from(char*& p, size_t capacity, int end_bit) {
+    const size_t R = capacity;
     BinningState b;
-    // vals_a first: the final point list always ends up there, at an offset that does not depend
-    // on R, so the caller may hand in a larger (grow-only) buffer than requested
-    carve(p, b.vals_a, R);
+    carve(p, b.vals_a, R);  // the final point list always ends up here
     b.mask_stride = R;
     carve(p, b.frag_mask, (size_t)(TILE_PIX / 32) * R);
     carve(p, b.vals_b, R);
@@ -130,6 +150,20 @@ struct BinningState {
     carve(p, b.keys_b, R);
     carve(p, b.sort_temp, radix_sort_temp_bytes((int)R, end_bit));
     return b;
+  }
+  static size_t bytes(size_t capacity, int end_bit) {
+    char* p = nullptr;
+    from(p, capacity, end_bit);
+    return (size_t)p + 256;
+  }
+  // inverse of bytes(): 0 if `nbytes` is not the size of any capacity
+  static size_t capacity_from_bytes(size_t nbytes, int end_bit) {
+    for (size_t c = GRAIN; c <= ((size_t)1 << 31); c += GRAIN) {
+      const size_t b = bytes(c, end_bit);
+      if (b == nbytes) return c;
+      if (b > nbytes) break;
+    }
+    return 0;
   }
 };
 template <typename F> static size_t required(F f) {
@@ -172,8 +206,8 @@ int pgs_timing_read(double* ms, unsigned long long* counts, int reset) {
   return 0;
 }
 
-int pgs_dsr_get_layout(int P, int width, int height, int R, pgs_dsr_layout* out) {
-  if (!out || P < 0 || width <= 0 || height <= 0 || R < 0) return set_error(PGS_ERR_INVALID_ARG, "bad layout query");
+int pgs_dsr_get_layout(int P, int width, int height, size_t binning_bytes, pgs_dsr_layout* out) {
+  if (!out || P < 0 || width <= 0 || height <= 0) return set_error(PGS_ERR_INVALID_ARG, "bad layout query");
   const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
   const size_t ntiles = (size_t)gx * gy;
   const int end_bit = 32 + (int)higher_msb(gx * gy);
@@ -197,8 +231,10 @@ int pgs_dsr_get_layout(int P, int width, int height, int R, pgs_dsr_layout* out)
     out->image_ranges = (size_t)s.ranges;
   }
   {
+    size_t cap = binning_bytes ? BinningState::capacity_from_bytes(binning_bytes, end_bit) : BinningState::GRAIN;
+    if (cap == 0) return set_error(PGS_ERR_INVALID_ARG, "binning buffer size %zu matches no capacity", binning_bytes);
     char* p = nullptr;
-    BinningState b = BinningState::from(p, R, end_bit);
+    BinningState b = BinningState::from(p, cap, end_bit);
     out->binning_bytes = (size_t)p + 256;
     const bool in_b = ((end_bit + 7) / 8) & 1;
     out->binning_keys_sorted = in_b ? (size_t)b.keys_b : (size_t)b.keys_a;
@@ -276,53 +312,88 @@ static int forward_impl(bool part, int S, const float* semantics, float* out_sem
   { StageTimer t(PGS_STAGE_SCAN, s); launch_inclusive_scan_u32(geom.tiles_touched, geom.point_offsets, P, geom.scan_temp, s); }
   if (int e = check_cuda("scan")) return e;
 
-  // number of surfel x tile instances; sizes the binning buffer (reference: rasterizer_impl.cu:282)
-  int num_rendered = 0;
-  cudaError_t ce = cudaMemcpyAsync(&num_rendered, geom.point_offsets + P - 1, sizeof(int), cudaMemcpyDeviceToHost, s);
+  // Number of surfel x tile instances R (reference: blocking cudaMemcpy, rasterizer_impl.cu:282).  The
+  // count travels to pinned host memory asynchronously; meanwhile binning + render are launched
+  // SPECULATIVELY for a capacity remembered from earlier frames, reading the count on the device.  Only
+  // then does the host wait for the count: the GPU already has the rest of the frame queued, so the
+  // round trip costs no device idle time, and the exact count is still returned to the caller.  If the
+  // count exceeds the capacity the speculative kernels did nothing and everything is launched again
+  // with a larger arena (first frames of a scene only).
+  int dev = 0;
+  cudaGetDevice(&dev);
+  CountFetch& cf = count_fetch();
+  if (!cf.init()) return set_error(PGS_ERR_CUDA, "pinned count buffer: %s", cudaGetErrorString(cudaGetLastError()));
+  const uint32_t* n_dev = geom.point_offsets + P - 1;
+  cudaError_t ce = cudaMemcpyAsync(cf.host, n_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
   if (ce != cudaSuccess) return set_error(PGS_ERR_CUDA, "memcpy num_rendered: %s", cudaGetErrorString(ce));
-  if (int e = check_sync(s, "scan/num_rendered")) return e;
-  if (num_rendered < 0) return set_error(PGS_ERR_UNSUPPORTED, "more than 2^31 surfel-tile instances");
+  cudaEventRecord(cf.ev, s);
 
   const int end_bit = 32 + (int)higher_msb(gx * gy);
-  size_t bin_bytes = required([&](char*& p) { BinningState::from(p, num_rendered, end_bit); });
-  char* bptr = binning_buffer(bin_bytes, binning_user);
-  if (!bptr) return set_error(PGS_ERR_ALLOC, "binning buffer allocation failed (%zu B)", bin_bytes);
-  BinningState bin = BinningState::from(bptr, num_rendered, end_bit);
+  auto launch_rest = [&](size_t capacity, const uint32_t* count_dev, int count_host) -> int {
+    const size_t bin_bytes = BinningState::bytes(capacity, end_bit);
+    char* bptr = binning_buffer(bin_bytes, binning_user);
+    if (!bptr) return set_error(PGS_ERR_ALLOC, "binning buffer allocation failed (%zu B)", bin_bytes);
+    BinningState bin = BinningState::from(bptr, capacity, end_bit);
+    const int n = count_dev ? (int)capacity : count_host;  // launch size
 
-  cudaMemsetAsync(img.ranges, 0, ntiles * sizeof(uint2), s);
-  const uint32_t* point_list = bin.vals_a;
-  if (num_rendered > 0) {
-    { StageTimer t(PGS_STAGE_DUP_KEYS, s);
-      launch_duplicate_with_keys(P, geom.rec, geom.point_offsets, bin.keys_a, bin.vals_a, radii, gx, gy, s); }
-    if (int e = check_cuda("duplicate_with_keys")) return e;
-    int where;
-    { StageTimer t(PGS_STAGE_SORT, s);
-      where = launch_radix_sort_pairs(bin.keys_a, bin.vals_a, bin.keys_b, bin.vals_b, num_rendered, end_bit,
-                                      bin.sort_temp, s); }
-    if (int e = check_cuda("radix_sort")) return e;
-    const uint64_t* sorted_keys = where ? bin.keys_b : bin.keys_a;
-    if (where)  // odd number of digit passes (<= 256 tiles): bring the sorted values home
-      cudaMemcpyAsync(bin.vals_a, bin.vals_b, (size_t)num_rendered * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
-    point_list = bin.vals_a;
-    { StageTimer t(PGS_STAGE_TILE_RANGES, s); launch_identify_tile_ranges(num_rendered, sorted_keys, img.ranges, s); }
-    if (int e = check_cuda("identify_tile_ranges")) return e;
-    if (debug) if (int e = check_sync(s, "binning")) return e;
+    cudaMemsetAsync(img.ranges, 0, ntiles * sizeof(uint2), s);
+    if (n > 0) {
+      { StageTimer t(PGS_STAGE_DUP_KEYS, s);
+        launch_duplicate_with_keys(P, geom.rec, geom.point_offsets, bin.keys_a, bin.vals_a, radii, gx, gy, s,
+                                   (uint32_t)capacity); }
+      if (int e = check_cuda("duplicate_with_keys")) return e;
+      int where;
+      { StageTimer t(PGS_STAGE_SORT, s);
+        where = launch_radix_sort_pairs(bin.keys_a, bin.vals_a, bin.keys_b, bin.vals_b, n, end_bit, bin.sort_temp, s,
+                                        count_dev); }
+      if (int e = check_cuda("radix_sort")) return e;
+      const uint64_t* sorted_keys = where ? bin.keys_b : bin.keys_a;
+      if (where)  // odd number of digit passes (<= 256 tiles): bring the sorted values home
+        cudaMemcpyAsync(bin.vals_a, bin.vals_b, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
+      { StageTimer t(PGS_STAGE_TILE_RANGES, s); launch_identify_tile_ranges(n, sorted_keys, img.ranges, s, count_dev); }
+      if (int e = check_cuda("identify_tile_ranges")) return e;
+      if (debug) if (int e = check_sync(s, "binning")) return e;
+    }
+    launch_tile_order(img.ranges, (int)ntiles, img.tile_order, s);
+    if (int e = check_cuda("tile_order")) return e;
+
+    RenderFwdArgs ra;
+    ra.ranges = img.ranges; ra.tile_order = img.tile_order; ra.point_list = bin.vals_a; ra.W = width; ra.H = height;
+    ra.grid_x = gx; ra.grid_y = gy;
+    ra.rec = geom.rec; ra.bbox = geom.bbox; ra.bg_color = background;
+    ra.final_T = img.final_T; ra.n_contrib = img.n_contrib; ra.out_color = out_color; ra.out_others = out_others;
+    ra.S = S; ra.semantics = semantics; ra.out_semantic = out_semantic;
+    ra.frag_mask = bin.frag_mask; ra.mask_stride = bin.mask_stride;
+    {
+      StageTimer t(PGS_STAGE_RENDER_FWD, s);
+      if (part) launch_render_fwd_part(ra, s); else launch_render_fwd(ra, s);
+    }
+    if (int e = check_cuda("render_fwd")) return e;
+    return 0;
+  };
+
+  static std::atomic<size_t> capacity_hint[16];
+  const bool speculate = !debug && dev < 16 && capacity_hint[dev].load() > 0;
+  size_t capacity = 0;
+  if (speculate) {
+    capacity = BinningState::capacity_for(capacity_hint[dev].load());
+    if (int e = launch_rest(capacity, n_dev, 0)) return e;
   }
-
-  launch_tile_order(img.ranges, (int)ntiles, img.tile_order, s);
-  if (int e = check_cuda("tile_order")) return e;
-
-  RenderFwdArgs ra;
-  ra.ranges = img.ranges; ra.tile_order = img.tile_order; ra.point_list = point_list; ra.W = width; ra.H = height; ra.grid_x = gx; ra.grid_y = gy;
-  ra.rec = geom.rec; ra.bbox = geom.bbox; ra.bg_color = background;
-  ra.final_T = img.final_T; ra.n_contrib = img.n_contrib; ra.out_color = out_color; ra.out_others = out_others;
-  ra.S = S; ra.semantics = semantics; ra.out_semantic = out_semantic;
-  ra.frag_mask = bin.frag_mask; ra.mask_stride = bin.mask_stride;
-  {
-    StageTimer t(PGS_STAGE_RENDER_FWD, s);
-    if (part) launch_render_fwd_part(ra, s); else launch_render_fwd(ra, s);
+  ce = cudaEventSynchronize(cf.ev);
+  if (ce != cudaSuccess) return set_error(PGS_ERR_CUDA, "scan/num_rendered: %s", cudaGetErrorString(ce));
+  const int num_rendered = *cf.host;
+  if (num_rendered < 0) return set_error(PGS_ERR_UNSUPPORTED, "more than 2^31 surfel-tile instances");
+  if (!speculate || (size_t)num_rendered > capacity) {
+    // first frame / debug mode / the speculative capacity was too small
+    size_t want = (size_t)num_rendered + (size_t)num_rendered / 4;
+    if (dev < 16 && !debug) {
+      size_t cur = capacity_hint[dev].load();
+      while (want > cur && !capacity_hint[dev].compare_exchange_weak(cur, want)) {}
+      want = std::max(want, cur);
+    }
+    capacity = BinningState::capacity_for(debug ? (size_t)num_rendered : want);
+    if (int e = launch_rest(capacity, nullptr, num_rendered)) return e;
   }
-  if (int e = check_cuda("render_fwd")) return e;
   if (debug) if (int e = check_sync(s, "render_fwd")) return e;
   return num_rendered;
 }
@@ -365,7 +436,8 @@ static int backward_impl(bool part, int S, const float* semantics, const float* 
                          const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
                          float scale_modifier, const float* rotations, const float* transMat_precomp,
                          const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
-                         float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                         float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer,
+                         size_t binning_bytes, char* image_buffer,
                          const float* dL_dpix, const float* dL_dothers, float* dL_dmean2D, float* scratch,
                          float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh,
                          float* dL_dscale, float* dL_drot, int debug, void* stream) {
@@ -399,7 +471,11 @@ static int backward_impl(bool part, int S, const float* semantics, const float* 
   const uint32_t* frag_mask = nullptr;
   size_t mask_stride = 0;
   if (R > 0) {
-    BinningState bin = BinningState::from(binning_buffer, R, end_bit);
+    const size_t capacity = BinningState::capacity_from_bytes(binning_bytes, end_bit);
+    if (capacity == 0 || capacity < (size_t)R)
+      return set_error(PGS_ERR_INVALID_ARG, "binning buffer of %zu bytes was not produced by the forward pass of "
+                                            "this frame (%d instances)", binning_bytes, R);
+    BinningState bin = BinningState::from(binning_buffer, capacity, end_bit);
     point_list = bin.vals_a;
     frag_mask = bin.frag_mask;
     mask_stride = bin.mask_stride;
@@ -448,14 +524,14 @@ int pgs_dsr_backward(int P, int D, int M, int R, const float* background, int wi
                      const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
                      float scale_modifier, const float* rotations, const float* transMat_precomp,
                      const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
-                     float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
-                     const float* dL_dpix, const float* dL_dothers, float* dL_dmean2D, float* scratch,
+                     float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, size_t binning_bytes,
+                     char* image_buffer, const float* dL_dpix, const float* dL_dothers, float* dL_dmean2D, float* scratch,
                      float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh,
                      float* dL_dscale, float* dL_drot, int debug, void* stream) {
   return backward_impl(false, 0, nullptr, nullptr, nullptr, P, D, M, R, background, width, height, means3D, shs,
                        colors_precomp, scales, scale_modifier, rotations, transMat_precomp, viewmatrix, projmatrix,
-                       campos, tan_fovx, tan_fovy, radii, geom_buffer, binning_buffer, image_buffer, dL_dpix,
-                       dL_dothers, dL_dmean2D, scratch, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dtransMat, dL_dsh,
+                       campos, tan_fovx, tan_fovy, radii, geom_buffer, binning_buffer, binning_bytes, image_buffer,
+                       dL_dpix, dL_dothers, dL_dmean2D, scratch, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dtransMat, dL_dsh,
                        dL_dscale, dL_drot, debug, stream);
 }
 
@@ -464,14 +540,15 @@ int pgs_dsrp_backward(int P, int D, int M, int R, const float* background, int w
                       const float* scales, float scale_modifier, const float* rotations,
                       const float* transMat_precomp, const float* viewmatrix, const float* projmatrix,
                       const float* campos, float tan_fovx, float tan_fovy, const int* radii, char* geom_buffer,
-                      char* binning_buffer, char* image_buffer, const float* dL_dpix, const float* dL_dsemantic_pix,
+                      char* binning_buffer, size_t binning_bytes, char* image_buffer, const float* dL_dpix,
+                      const float* dL_dsemantic_pix,
                       const float* dL_dothers, float* dL_dmean2D, float* scratch, float* dL_dopacity, float* dL_dcolor,
                       float* dL_dsemantics, float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh, float* dL_dscale,
                       float* dL_drot, int debug, void* stream) {
   return backward_impl(true, semantic_types, semantics, dL_dsemantic_pix, dL_dsemantics, P, D, M, R, background,
                        width, height, means3D, shs, colors_precomp, scales, scale_modifier, rotations,
                        transMat_precomp, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, radii, geom_buffer,
-                       binning_buffer, image_buffer, dL_dpix, dL_dothers, dL_dmean2D, scratch, dL_dopacity, dL_dcolor,
+                       binning_buffer, binning_bytes, image_buffer, dL_dpix, dL_dothers, dL_dmean2D, scratch, dL_dopacity, dL_dcolor,
                        dL_dmean3D, dL_dtransMat, dL_dsh, dL_dscale, dL_drot, debug, stream);
 }
 

@@ -11,6 +11,16 @@
 
 namespace pgs {
 
+// Element count of a launch: the host value `n_cap`, or — when the host launched speculatively for a
+// capacity, before the count was known to it — the device value *n_dev.  Returns -1 when the device
+// count exceeds the capacity the buffers were sized for (the launch then does nothing; the host
+// re-launches with larger buffers once it has read the count).
+__device__ __forceinline__ int resolve_count(int n_cap, const uint32_t* __restrict__ n_dev) {
+  if (n_dev == nullptr) return n_cap;
+  const uint32_t v = __ldg(n_dev);
+  return v > (uint32_t)n_cap ? -1 : (int)v;
+}
+
 // =============================================================================
 // Single-pass inclusive scan (decoupled look-back), u32.
 // =============================================================================
@@ -126,9 +136,10 @@ __global__ void __launch_bounds__(256) duplicate_with_keys_kernel(int P, const f
                                                                   uint64_t* __restrict__ keys,
                                                                   uint32_t* __restrict__ values,
                                                                   const int* __restrict__ radii, unsigned gx,
-                                                                  unsigned gy) {
+                                                                  unsigned gy, uint32_t capacity) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P) return;
+  if (__ldg(&offsets[P - 1]) > capacity) return;  // speculative launch whose buffers are too small
   const int radius = radii[idx];
   if (radius > 0) {
     uint32_t off = (idx == 0) ? 0 : offsets[idx - 1];
@@ -151,9 +162,10 @@ __global__ void __launch_bounds__(256) duplicate_with_keys_kernel(int P, const f
 }
 
 void launch_duplicate_with_keys(int P, const float4* rec, const uint32_t* offsets, uint64_t* keys, uint32_t* values,
-                                const int* radii, int grid_x, int grid_y, cudaStream_t s) {
+                                const int* radii, int grid_x, int grid_y, cudaStream_t s, uint32_t capacity) {
   if (P <= 0) return;
-  duplicate_with_keys_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, rec, offsets, keys, values, radii, grid_x, grid_y);
+  duplicate_with_keys_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, rec, offsets, keys, values, radii, grid_x, grid_y,
+                                                              capacity);
   count_launch();
 }
 
@@ -186,9 +198,12 @@ size_t radix_sort_temp_bytes(int n, int end_bit) { return rs_temp_bytes<uint64_t
 size_t radix_sort32_temp_bytes(int n, int end_bit) { return rs_temp_bytes<uint32_t>(n, end_bit); }
 
 template <typename KeyT>
-__global__ void __launch_bounds__(RS_THREADS) rs_histogram_kernel(const KeyT* __restrict__ keys, int n, int passes,
-                                                                   int end_bit, uint32_t* __restrict__ hist) {
+__global__ void __launch_bounds__(RS_THREADS) rs_histogram_kernel(const KeyT* __restrict__ keys, int n_cap, int passes,
+                                                                   int end_bit, uint32_t* __restrict__ hist,
+                                                                   const uint32_t* __restrict__ n_dev) {
   __shared__ uint32_t s_hist[RS_MAX_PASSES * RS_RADIX];
+  const int n = resolve_count(n_cap, n_dev);
+  if (n < 0) return;
   for (int i = threadIdx.x; i < passes * RS_RADIX; i += RS_THREADS) s_hist[i] = 0;
   __syncthreads();
   const int stride = gridDim.x * RS_THREADS;
@@ -234,10 +249,10 @@ __global__ void __launch_bounds__(RS_RADIX) rs_scan_hist_kernel(uint32_t* hist) 
 template <typename KeyT>
 __global__ void __launch_bounds__(RS_THREADS)
     rs_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                       KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift, int bits,
+                       KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n_cap, int shift, int bits,
                        const uint32_t* __restrict__ bin_base,  // [256] exclusive global digit offsets
                        uint32_t* lookback,                     // [tiles][256]
-                       uint32_t* tile_counter) {
+                       uint32_t* tile_counter, const uint32_t* __restrict__ n_dev) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
   KeyT* s_keys = reinterpret_cast<KeyT*>(rs_smem);                                   // [RS_TILE]
   uint32_t* s_vals = reinterpret_cast<uint32_t*>(rs_smem + sizeof(KeyT) * RS_TILE);  // [RS_TILE]
@@ -249,11 +264,14 @@ __global__ void __launch_bounds__(RS_THREADS)
 
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31, wid = tid >> 5;
+  const int n = resolve_count(n_cap, n_dev);
+  if (n < 0) return;
   if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
   for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) s_warp_hist[i] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   const int base = tile * RS_TILE;
+  if (base >= n) return;  // grid was sized for the capacity; no tile ever looks back at this one
   const uint32_t mask = (1u << bits) - 1;
 
   // warp-striped load: element order e = wid*ITEMS*32 + i*32 + lane
@@ -368,7 +386,7 @@ __global__ void __launch_bounds__(RS_THREADS)
 
 template <typename KeyT>
 static int rs_sort(KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, int n, int end_bit, void* temp,
-                   cudaStream_t s) {
+                   cudaStream_t s, const uint32_t* n_dev) {
   if (n <= 0) return 0;
   const int passes = rs_passes(end_bit);
   const int tiles = (n + RS_TILE - 1) / RS_TILE;
@@ -378,7 +396,7 @@ static int rs_sort(KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_
   uint32_t* lookback = (uint32_t*)((char*)counters + 256);
 
   int hist_blocks = min(tiles, 148 * 8);
-  rs_histogram_kernel<KeyT><<<hist_blocks, RS_THREADS, 0, s>>>(keys_a, n, passes, end_bit, hist);
+  rs_histogram_kernel<KeyT><<<hist_blocks, RS_THREADS, 0, s>>>(keys_a, n, passes, end_bit, hist, n_dev);
   count_launch();
   rs_scan_hist_kernel<<<passes, RS_RADIX, 0, s>>>(hist);
   count_launch();
@@ -398,7 +416,8 @@ static int rs_sort(KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_
     int bits = min(RS_BITS, end_bit - shift);
     rs_onesweep_kernel<KeyT><<<tiles, RS_THREADS, smem, s>>>(kin, vin, kout, vout, n, shift, bits,
                                                               hist + p * RS_RADIX,
-                                                              lookback + (size_t)p * tiles * RS_RADIX, counters + p);
+                                                              lookback + (size_t)p * tiles * RS_RADIX, counters + p,
+                                                              n_dev);
     count_launch();
     KeyT* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
@@ -407,20 +426,21 @@ static int rs_sort(KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_
 }
 
 int launch_radix_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int n, int end_bit,
-                            void* temp, cudaStream_t s) {
-  return rs_sort<uint64_t>(keys_a, vals_a, keys_b, vals_b, n, end_bit, temp, s);
+                            void* temp, cudaStream_t s, const uint32_t* n_dev) {
+  return rs_sort<uint64_t>(keys_a, vals_a, keys_b, vals_b, n, end_bit, temp, s, n_dev);
 }
 int launch_radix_sort_pairs32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, int n,
                               int end_bit, void* temp, cudaStream_t s) {
-  return rs_sort<uint32_t>(keys_a, vals_a, keys_b, vals_b, n, end_bit, temp, s);
+  return rs_sort<uint32_t>(keys_a, vals_a, keys_b, vals_b, n, end_bit, temp, s, nullptr);
 }
 
 // =============================================================================
 // identifyTileRanges
 // =============================================================================
-__global__ void __launch_bounds__(256) identify_tile_ranges_kernel(int L, const uint64_t* __restrict__ keys,
-                                                                   uint2* ranges) {
+__global__ void __launch_bounds__(256) identify_tile_ranges_kernel(int L_cap, const uint64_t* __restrict__ keys,
+                                                                   uint2* ranges, const uint32_t* __restrict__ n_dev) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int L = resolve_count(L_cap, n_dev);
   if (idx >= L) return;
   uint32_t currtile = (uint32_t)(keys[idx] >> 32);
   if (idx == 0)
@@ -435,9 +455,9 @@ __global__ void __launch_bounds__(256) identify_tile_ranges_kernel(int L, const 
   if (idx == L - 1) ranges[currtile].y = L;
 }
 
-void launch_identify_tile_ranges(int L, const uint64_t* keys, uint2* ranges, cudaStream_t s) {
+void launch_identify_tile_ranges(int L, const uint64_t* keys, uint2* ranges, cudaStream_t s, const uint32_t* n_dev) {
   if (L <= 0) return;
-  identify_tile_ranges_kernel<<<(L + 255) / 256, 256, 0, s>>>(L, keys, ranges);
+  identify_tile_ranges_kernel<<<(L + 255) / 256, 256, 0, s>>>(L, keys, ranges, n_dev);
   count_launch();
 }
 

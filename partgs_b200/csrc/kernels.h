@@ -41,22 +41,27 @@ size_t scan_temp_bytes(int n);
 void launch_inclusive_scan_u32(const uint32_t* in, uint32_t* out, int n, void* temp, cudaStream_t s);
 
 // reference duplicateWithKeys (rasterizer_impl.cu:70-111)
+// `capacity`: number of instances keys/values can hold; if offsets[P-1] exceeds it the launch does nothing
 void launch_duplicate_with_keys(int P, const float4* rec, const uint32_t* offsets, uint64_t* keys, uint32_t* values,
-                                const int* radii, int grid_x, int grid_y, cudaStream_t s);
+                                const int* radii, int grid_x, int grid_y, cudaStream_t s,
+                                uint32_t capacity = 0xffffffffu);
 
 // Stable LSD radix sort of (u64 key, u32 value) pairs on key bits [0, end_bit)
 // (reference: cub::DeviceRadixSort::SortPairs, rasterizer_impl.cu:304-309).
 // Buffers a/b ping-pong; returns 0 if the sorted result is in (keys_a, vals_a), 1 if in (keys_b, vals_b).
 size_t radix_sort_temp_bytes(int n, int end_bit);
+// n_dev != nullptr: `n` is only the capacity the launch is sized for, the element count is read on the device
+// (speculative launch before the host knows the count; does nothing if *n_dev > n)
 int launch_radix_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int n, int end_bit,
-                            void* temp, cudaStream_t s);
+                            void* temp, cudaStream_t s, const uint32_t* n_dev = nullptr);
 // 32-bit key variant (distCUDA2 Morton/cell sort)
 size_t radix_sort32_temp_bytes(int n, int end_bit);
 int launch_radix_sort_pairs32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, int n,
                               int end_bit, void* temp, cudaStream_t s);
 
 // reference identifyTileRanges (rasterizer_impl.cu:116-138); ranges must be zeroed first.
-void launch_identify_tile_ranges(int L, const uint64_t* keys, uint2* ranges, cudaStream_t s);
+void launch_identify_tile_ranges(int L, const uint64_t* keys, uint2* ranges, cudaStream_t s,
+                                 const uint32_t* n_dev = nullptr);
 
 // ---- render -----------------------------------------------------------------
 // tile ids sorted longest-list-first (launch order of the render kernels)

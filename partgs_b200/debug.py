@@ -13,9 +13,9 @@ import torch
 from . import _lib
 
 
-def layout(P: int, W: int, H: int, R: int) -> _lib.DsrLayout:
+def layout(P: int, W: int, H: int, binning_bytes: int = 0) -> _lib.DsrLayout:
     lay = _lib.DsrLayout()
-    _lib.check(_lib.load().pgs_dsr_get_layout(P, W, H, R, C.byref(lay)), "pgs_dsr_get_layout")
+    _lib.check(_lib.load().pgs_dsr_get_layout(P, W, H, int(binning_bytes), C.byref(lay)), "pgs_dsr_get_layout")
     return lay
 
 
@@ -36,7 +36,7 @@ def untile(x: torch.Tensor, W: int, H: int) -> torch.Tensor:
 
 
 def parse_state(geom: torch.Tensor, img: torch.Tensor, binning: torch.Tensor, P: int, W: int, H: int, R: int):
-    lay = layout(P, W, H, R)
+    lay = layout(P, W, H, binning.numel())
     gx, gy = (W + 15) // 16, (H + 15) // 16
     nt = gx * gy
     rf = lay.rec_floats

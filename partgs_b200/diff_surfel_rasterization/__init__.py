@@ -122,7 +122,7 @@ def _native_backward(bg, means3D, radii, colors, scales, rotations, scale_modifi
                 _lib.ptr(sh.contiguous()), _lib.ptr(colors.contiguous()), _lib.ptr(scales.contiguous()),
                 float(scale_modifier), _lib.ptr(rotations.contiguous()), _lib.ptr(transMat_precomp.contiguous()),
                 _lib.ptr(viewmatrix.contiguous()), _lib.ptr(projmatrix.contiguous()), _lib.ptr(campos.contiguous()),
-                float(tan_fovx), float(tan_fovy), _lib.ptr(radii), _lib.ptr(geomBuffer), _lib.ptr(binningBuffer),
+                float(tan_fovx), float(tan_fovy), _lib.ptr(radii), _lib.ptr(geomBuffer), _lib.ptr(binningBuffer), int(binningBuffer.numel()),
                 _lib.ptr(imageBuffer), _lib.ptr(dL_dout_color), _lib.ptr(dL_dout_others), _lib.ptr(dL_dmeans2D),
                 _lib.ptr(scratch), _lib.ptr(dL_dopacity), _lib.ptr(dL_dcolors), _lib.ptr(dL_dmeans3D),
                 _lib.ptr(dL_dtransMat), _lib.ptr(dL_dsh), _lib.ptr(dL_dscales), _lib.ptr(dL_drotations),

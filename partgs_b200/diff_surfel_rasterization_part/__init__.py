@@ -110,7 +110,7 @@ def _native_backward(bg, means3D, radii, colors, semantics, scales, rotations, s
             rc = lib.pgs_dsrp_backward(
                 P, int(degree), int(M), int(R), c(bg), W, H, S, c(means3D), c(sh), c(colors), c(semantics), c(scales),
                 float(scale_modifier), c(rotations), c(transMat_precomp), c(viewmatrix), c(projmatrix), c(campos),
-                float(tan_fovx), float(tan_fovy), _lib.ptr(radii), _lib.ptr(geomBuffer), _lib.ptr(binningBuffer),
+                float(tan_fovx), float(tan_fovy), _lib.ptr(radii), _lib.ptr(geomBuffer), _lib.ptr(binningBuffer), int(binningBuffer.numel()),
                 _lib.ptr(imageBuffer), _lib.ptr(dL_dout_color), _lib.ptr(dL_dout_semantic), _lib.ptr(dL_dout_others),
                 _lib.ptr(dL_dmeans2D), _lib.ptr(scratch), _lib.ptr(dL_dopacity), _lib.ptr(dL_dcolors),
                 _lib.ptr(dL_dsemantics), _lib.ptr(dL_dmeans3D), _lib.ptr(dL_dtransMat), _lib.ptr(dL_dsh),

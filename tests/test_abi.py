@@ -39,7 +39,7 @@ def test_version_and_msb(lib):
 def test_layout_query(lib):
     from partgs_b200 import _lib
     lay = _lib.DsrLayout()
-    assert lib.pgs_dsr_get_layout(1000, 400, 300, 5000, C.byref(lay)) == 0
+    assert lib.pgs_dsr_get_layout(1000, 400, 300, 0, C.byref(lay)) == 0
     assert lay.rec_floats == 20 and lay.tile_pixels == 256
     assert lay.geom_bytes > 1000 * 80 and lay.binning_bytes > 5000 * 24
     for off in (lay.geom_rec, lay.geom_bbox, lay.image_final_T, lay.image_ranges, lay.binning_point_list):
