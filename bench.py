@@ -40,10 +40,8 @@ def dist_setup(n_gpus: int):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from partgs_b200.dist import init_nccl
+        init_nccl(local)
     else:
         torch.cuda.set_device(0)
         local = 0
@@ -255,9 +253,23 @@ def run(args):
         import torch.distributed as dist
 
     pending = []
+    peer = None
+    if world > 1 and arm.name == "ours" and args.collective == "peer" and not args.no_allreduce:
+        # gradients are produced straight into peer-mapped memory and summed by copy-engine transfers over
+        # NVLink (partgs_b200.dist.PeerGradAllReducer): no NCCL kernel competes with the render kernels for SMs
+        from partgs_b200.dist import PeerGradAllReducer
+        from partgs_b200 import diff_surfel_rasterization as dsr
+        numel = sum((n + 63) // 64 * 64 for n in (P * 3, P * 16 * 3, P, P * 2, P * 4))
+        peer = PeerGradAllReducer(numel, dev)
+        dsr.set_grad_bucket_provider(peer.bucket_provider)
 
     def allreduce_grads(grads):
-        # one async NCCL all-reduce per parameter group; waited on before the grads are replaced
+        # one asynchronous all-reduce of the 232 B/surfel gradient bucket per step, overlapped with the next
+        # step's kernels; the previous step's collective is waited on before the next one is launched
+        if peer is not None:
+            peer.wait()
+            peer.launch(grads)
+            return
         for h in pending:
             h.wait()
         pending.clear()
@@ -266,6 +278,13 @@ def run(args):
             bucket = grad_bucket(grads)  # ours: the five gradients are views of one flat buffer
             for t in ([bucket] if bucket is not None else grads):
                 pending.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
+
+    def drain():
+        if peer is not None:
+            peer.wait()
+        for h in pending:
+            h.wait()
+        pending.clear()
 
     def one_step(i):
         cam = my_cams[i % len(my_cams)]
@@ -285,9 +304,7 @@ def run(args):
     views_per_rank = (len(all_cams) + world - 1) // world  # same count on every rank (collectives must match)
     for i in range(min(views_per_rank, 64) + n_warm):
         one_step(i)
-    for h in pending:
-        h.wait()
-    pending.clear()
+    drain()
     torch.cuda.synchronize()
 
     # ---- timed region: inputs resident in HBM ------------------------------------------
@@ -304,9 +321,7 @@ def run(args):
     e0.record()
     for i in range(args.steps):
         one_step(i)
-    for h in pending:
-        h.wait()
-    pending.clear()
+    drain()
     e1.record()
     barrier()
     t_ms = e0.elapsed_time(e1)
@@ -363,9 +378,7 @@ def run(args):
             allreduce_grads(grads)
             loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
             consumed[s].record(cur)
-        for h in pending:
-            h.wait()
-        pending.clear()
+        drain()
         torch.cuda.synchronize()
         return float(loss_host.item())
 
@@ -402,8 +415,10 @@ def run(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{name}: {P} surfels, {W}x{H}, fwd+bwd, all 10 output channels get gradient",
                    "views": cfg["views"], "views_per_rank": len(my_cams), "sharding": "by camera",
-                   "collective": ("nccl all-reduce of 232 B/surfel parameter gradients per step (one bucket)"
-                                  if world > 1 and not args.no_allreduce else "none"),
+                   "collective": ("none" if world == 1 or args.no_allreduce else
+                                  "all-reduce of the 232 B/surfel gradient bucket per step: " +
+                                  ("copy-engine reduce-scatter/all-gather over NVLink peer memory" if peer is not None
+                                   else "NCCL")),
                    "l2": "inputs (232 MB parameters + per-view state) exceed the 126 MB L2; views cycle every step",
                    "V_visible": V, "R_instances": int(R)},
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
@@ -461,6 +476,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="gradient all-reduce at N>1: copy-engine peer-memory collective (default) or NCCL")
     ap.add_argument("--no-allreduce", action="store_true",
                     help="diagnostic: skip the gradient all-reduce at N>1 (shows what the collective costs)")
     args = ap.parse_args()

@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "../../include/partgs_b200.h"
 #include "common.cuh"
@@ -373,7 +374,8 @@ static int forward_impl(bool part, int S, const float* semantics, float* out_sem
   };
 
   static std::atomic<size_t> capacity_hint[16];
-  const bool speculate = !debug && dev < 16 && capacity_hint[dev].load() > 0;
+  static const bool no_spec = getenv("PGS_NO_SPECULATE") != nullptr;  // diagnostic switch
+  const bool speculate = !debug && !no_spec && dev < 16 && capacity_hint[dev].load() > 0;
   size_t capacity = 0;
   if (speculate) {
     capacity = BinningState::capacity_for(capacity_hint[dev].load());

@@ -78,6 +78,17 @@ def _native_forward(bg, means3D, colors, opacity, scales, rotations, scale_modif
     return rendered, out_color, out_others, radii, sc.tensor(sc.GEOM), sc.tensor(sc.BINNING), sc.tensor(sc.IMAGE)
 
 
+_bucket_provider = None
+
+
+def set_grad_bucket_provider(fn):
+    """``fn(numel, device) -> flat float32 tensor or None``: where the backward pass puts its five parameter
+    gradients (one flat "bucket").  A data-parallel caller hands out peer-mapped memory here so that the
+    gradients are reduced in place (partgs_b200.dist.PeerGradAllReducer).  None restores torch.empty."""
+    global _bucket_provider
+    _bucket_provider = fn
+
+
 def _carve_bucket(dev, shapes, align_elems=64):
     """Views of the given shapes into one flat float32 buffer (each view 256-byte aligned).
     The views' ``_base`` is the bucket itself."""
@@ -88,7 +99,9 @@ def _carve_bucket(dev, shapes, align_elems=64):
             n *= int(d)
         offs.append((total, n))
         total += (n + align_elems - 1) // align_elems * align_elems
-    flat = torch.empty((max(total, 1),), dtype=torch.float32, device=dev)
+    flat = _bucket_provider(max(total, 1), dev) if _bucket_provider is not None else None
+    if flat is None:
+        flat = torch.empty((max(total, 1),), dtype=torch.float32, device=dev)
     return [flat[o:o + n].view(*shp) for (o, n), shp in zip(offs, shapes)]
 
 
