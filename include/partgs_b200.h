@@ -110,6 +110,40 @@ int pgs_dsrp_backward(int P, int D, int M, int R, const float* background, int w
                       float* dL_dsemantics, float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh, float* dL_dscale,
                       float* dL_drot, int debug, void* stream);
 
+/* ---- block-level (superquadric) rasteriser --------------------------------------------
+ * north_star (1): preprocess fused with the superquadric -> surfel placement.  Same pipeline as
+ * pgs_dsr_forward / pgs_dsr_backward, but surfel i = (block, face, sample) is GENERATED inside the
+ * preprocess kernels from the 13 parameters per superquadric (BlockGaussianModel.prepare_scaling_rot /
+ * get_xyz / get_scaling / get_rotation / get_opacity, games/block_mesh_splatting/scene/
+ * block_gaussian_model.py:98-109,189-256) instead of being read from means3D / scales / rotations /
+ * opacities; P = B*F*K.  `vertices` [B,Vt,3] is written by forward and read by backward.  out_xyz [P,3],
+ * out_scaling [P,2] (log), out_rotation [P,4], out_opacity [P] may be NULL (materialise only if a caller
+ * reads get_xyz etc.).  Backward returns the gradients of the block parameters (d_sq_* fully written;
+ * d_alpha [B*F,K,3] and d_scale_raw [B,F*K] optional) plus dL_dsh / dL_dcolor / dL_dmean2D as usual. */
+int pgs_dsr_forward_blocks(pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_alloc_fn binning_buffer,
+                           void* binning_user, pgs_alloc_fn image_buffer, void* image_user, int B, int Vt, int F, int K,
+                           const float* sq_r, const float* sq_s, const float* sq_t, const float* sq_eps,
+                           const float* sq_occ, const float* eta, const float* omega, const int* faces,
+                           const float* alpha, const float* scale_raw, float ratio, float scale_min, int D, int M,
+                           const float* background, int width, int height, const float* shs,
+                           const float* colors_precomp, float scale_modifier, const float* viewmatrix,
+                           const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                           float* vertices, float* out_xyz, float* out_scaling, float* out_rotation,
+                           float* out_opacity, float* out_color, float* out_others, int* radii, int debug,
+                           void* stream);
+size_t pgs_dsr_backward_blocks_scratch_bytes(int B, int Vt, int F, int K);
+int pgs_dsr_backward_blocks(int B, int Vt, int F, int K, const float* sq_r, const float* sq_s, const float* sq_t,
+                            const float* sq_eps, const float* sq_occ, const float* eta, const float* omega,
+                            const int* faces, const float* alpha, const float* scale_raw, float ratio, float scale_min,
+                            const float* vertices, int D, int M, int R, const float* background, int width, int height,
+                            const float* shs, const float* colors_precomp, float scale_modifier,
+                            const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
+                            float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer,
+                            size_t binning_bytes, char* image_buffer, const float* dL_dpix, const float* dL_dothers,
+                            float* dL_dmean2D, void* scratch, float* dL_dcolor, float* dL_dsh, float* d_sq_r,
+                            float* d_sq_s, float* d_sq_t, float* d_sq_eps, float* d_sq_occ, float* d_alpha,
+                            float* d_scale_raw, int debug, void* stream);
+
 /* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:24-29, rasterizer_impl.cu:141-153).
  * present: one byte per point (bool). */
 int pgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

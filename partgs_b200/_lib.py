@@ -59,6 +59,18 @@ SIGNATURES = {
     "pgs_sq2surfel_backward_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "pgs_sq2surfel_backward": (C.c_int, [C.c_int] * 4 + [_f32p] * 7 + [_vp, _f32p, _f32p, C.c_float, C.c_float] +
                                [_f32p] * 13 + [_vp, _vp]),
+    "pgs_dsr_forward_blocks": (C.c_int, [ALLOC_FN, _vp, ALLOC_FN, _vp, ALLOC_FN, _vp] + [C.c_int] * 4 + [_f32p] * 7 +
+                               [_vp, _f32p, _f32p, C.c_float, C.c_float, C.c_int, C.c_int, _f32p, C.c_int, C.c_int,
+                                _f32p, _f32p, C.c_float, _f32p, _f32p, _f32p, C.c_float, C.c_float] + [_f32p] * 7 +
+                               [_vp, C.c_int, _vp]),
+    "pgs_dsr_backward_blocks_scratch_bytes": (C.c_size_t, [C.c_int] * 4),
+    "pgs_dsr_backward_blocks": (C.c_int, [C.c_int] * 4 + [_f32p] * 7 + [_vp, _f32p, _f32p, C.c_float, C.c_float,
+                                                                        _f32p, C.c_int, C.c_int, C.c_int, _f32p,
+                                                                        C.c_int, C.c_int, _f32p, _f32p, C.c_float,
+                                                                        _f32p, _f32p, _f32p, C.c_float, C.c_float,
+                                                                        _vp, _vp, _vp, C.c_size_t, _vp, _f32p, _f32p,
+                                                                        _f32p, _vp, _f32p, _f32p] + [_f32p] * 7 +
+                                [C.c_int, _vp]),
     "pgs_knn_temp_bytes": (C.c_size_t, [C.c_int]),
     "pgs_knn_dist2": (C.c_int, [C.c_int, _f32p, _f32p, _vp, _vp]),
     "pgs_scan_temp_bytes": (C.c_size_t, [C.c_int]),

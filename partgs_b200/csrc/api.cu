@@ -251,7 +251,13 @@ int pgs_dsr_get_layout(int P, int width, int height, size_t binning_bytes, pgs_d
 }  // extern "C"
 
 // Shared host sequence of both forks (part == true: diff-surfel-rasterization_part).
-static int forward_impl(bool part, int S, const float* semantics, float* out_semantic,
+struct SqForward {        // block-level mode of forward_impl
+  SqArgs sq;
+  float* vertices;        // [B,Vt,3] out
+  float* out_xyz, *out_scaling, *out_rotation, *out_opacity;  // optional materialisation
+};
+
+static int forward_impl(const SqForward* sqf, bool part, int S, const float* semantics, float* out_semantic,
                         pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_alloc_fn binning_buffer,
                         void* binning_user, pgs_alloc_fn image_buffer, void* image_user, int P, int D, int M,
                         const float* background, int width, int height, const float* means3D, const float* shs,
@@ -271,12 +277,14 @@ static int forward_impl(bool part, int S, const float* semantics, float* out_sem
   cudaStream_t s = (cudaStream_t)stream;
   if (P <= 0 || width <= 0 || height <= 0) return set_error(PGS_ERR_INVALID_ARG, "P, width, height must be positive");
   if (!geometry_buffer || !binning_buffer || !image_buffer) return set_error(PGS_ERR_INVALID_ARG, "null allocator");
-  if (!means3D || !opacities || !background || !viewmatrix || !projmatrix || !out_color || !out_others)
+  if (!background || !viewmatrix || !projmatrix || !out_color || !out_others || (!sqf && (!means3D || !opacities)))
     return set_error(PGS_ERR_INVALID_ARG, "null required pointer");
+  if (sqf && (part || transMat_precomp || !sqf->vertices))
+    return set_error(PGS_ERR_INVALID_ARG, "block-level mode: base fork only, no transMat_precomp, vertices required");
   if (!shs && !colors_precomp)
     return set_error(PGS_ERR_INVALID_ARG, "provide SHs or precomputed colours");  // rasterizer_impl.cu:243-246
   if (shs && (!cam_pos || M <= 0)) return set_error(PGS_ERR_INVALID_ARG, "SH path needs campos and M > 0");
-  if (!transMat_precomp && (!scales || !rotations))
+  if (!sqf && !transMat_precomp && (!scales || !rotations))
     return set_error(PGS_ERR_INVALID_ARG, "provide scales+rotations or transMat_precomp");
   if (D < 0 || D > 3 || (shs && (D + 1) * (D + 1) > M)) return set_error(PGS_ERR_INVALID_ARG, "bad SH degree");
 
@@ -303,6 +311,14 @@ static int forward_impl(bool part, int S, const float* semantics, float* out_sem
   pa.radii = radii; pa.rec = geom.rec; pa.bbox = geom.bbox; pa.tiles_touched = geom.tiles_touched;
   pa.focal_y = height / (2.0f * tan_fovy);
   pa.focal_x = width / (2.0f * tan_fovx);
+  pa.use_sq = sqf != nullptr;
+  if (sqf) {
+    pa.sq = sqf->sq; pa.sq_vertices = sqf->vertices;
+    pa.sq_out_xyz = sqf->out_xyz; pa.sq_out_scaling = sqf->out_scaling; pa.sq_out_rotation = sqf->out_rotation;
+    pa.sq_out_opacity = sqf->out_opacity;
+    StageTimer t(PGS_STAGE_SQ_FWD, s);
+    launch_sq_vertices(sqf->sq, sqf->vertices, s);  // B*Vt threads; the per-surfel part runs inside preprocess
+  }
   {
     StageTimer t(PGS_STAGE_PREPROCESS_FWD, s);
     if (part) launch_preprocess_fwd_part(pa, s); else launch_preprocess_fwd(pa, s);
@@ -409,7 +425,7 @@ int pgs_dsr_forward(pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_alloc
                     const float* rotations, const float* transMat_precomp, const float* viewmatrix,
                     const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered,
                     float* out_color, float* out_others, int* radii, int debug, void* stream) {
-  return forward_impl(false, 0, nullptr, nullptr, geometry_buffer, geometry_user, binning_buffer, binning_user,
+  return forward_impl(nullptr, false, 0, nullptr, nullptr, geometry_buffer, geometry_user, binning_buffer, binning_user,
                       image_buffer, image_user, P, D, M, background, width, height, means3D, shs, colors_precomp,
                       opacities, scales, scale_modifier, rotations, transMat_precomp, viewmatrix, projmatrix, cam_pos,
                       tan_fovx, tan_fovy, prefiltered, out_color, out_others, radii, debug, stream);
@@ -423,7 +439,7 @@ int pgs_dsrp_forward(pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_allo
                      const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
                      float tan_fovy, int prefiltered, float* out_color, float* out_semantic, float* out_others,
                      int* radii, int debug, void* stream) {
-  return forward_impl(true, semantic_types, semantics, out_semantic, geometry_buffer, geometry_user, binning_buffer,
+  return forward_impl(nullptr, true, semantic_types, semantics, out_semantic, geometry_buffer, geometry_user, binning_buffer,
                       binning_user, image_buffer, image_user, P, D, M, background, width, height, means3D, shs,
                       colors_precomp, opacities, scales, scale_modifier, rotations, transMat_precomp, viewmatrix,
                       projmatrix, cam_pos, tan_fovx, tan_fovy, prefiltered, out_color, out_others, radii, debug, stream);
@@ -433,7 +449,8 @@ size_t pgs_dsr_backward_scratch_bytes(int P) { return (size_t)(P > 0 ? P : 0) * 
 
 }  // extern "C"
 
-static int backward_impl(bool part, int S, const float* semantics, const float* dL_dsemantic_pix, float* dL_dsemantics,
+static int backward_impl(const SqArgs* sq, const float* sq_vertices, bool part, int S, const float* semantics,
+                         const float* dL_dsemantic_pix, float* dL_dsemantics,
                          int P, int D, int M, int R, const float* background, int width, int height,
                          const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
                          float scale_modifier, const float* rotations, const float* transMat_precomp,
@@ -458,7 +475,7 @@ static int backward_impl(bool part, int S, const float* semantics, const float* 
   if (!dL_dpix || !dL_dothers || !scratch || !dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D ||
       !dL_dtransMat)
     return set_error(PGS_ERR_INVALID_ARG, "null gradient pointer");
-  if (!transMat_precomp && (!scales || !rotations || !dL_dscale || !dL_drot))
+  if (!transMat_precomp && ((!sq && (!scales || !rotations)) || !dL_dscale || !dL_drot))
     return set_error(PGS_ERR_INVALID_ARG, "scale/rotation path needs scales, rotations and their gradient arrays");
   if (shs && !dL_dsh) return set_error(PGS_ERR_INVALID_ARG, "SH path needs dL_dsh");
 
@@ -506,6 +523,8 @@ static int backward_impl(bool part, int S, const float* semantics, const float* 
   PreprocessBwdArgs pb;
   pb.P = P; pb.D = D; pb.M = M; pb.means3D = means3D; pb.radii = radii; pb.shs = shs;
   pb.scales = transMat_precomp ? nullptr : scales; pb.rotations = rotations; pb.scale_modifier = scale_modifier;
+  pb.use_sq = sq != nullptr;
+  if (sq) { pb.sq = *sq; pb.sq_vertices = sq_vertices; }
   pb.transMat_precomp = transMat_precomp; pb.viewmatrix = viewmatrix; pb.projmatrix = projmatrix;
   pb.focal_x = focal_x; pb.focal_y = focal_y; pb.tan_fovx = tan_fovx; pb.tan_fovy = tan_fovy; pb.cam_pos = campos;
   pb.rec = geom.rec; pb.grad = grad;
@@ -530,7 +549,7 @@ int pgs_dsr_backward(int P, int D, int M, int R, const float* background, int wi
                      char* image_buffer, const float* dL_dpix, const float* dL_dothers, float* dL_dmean2D, float* scratch,
                      float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh,
                      float* dL_dscale, float* dL_drot, int debug, void* stream) {
-  return backward_impl(false, 0, nullptr, nullptr, nullptr, P, D, M, R, background, width, height, means3D, shs,
+  return backward_impl(nullptr, nullptr, false, 0, nullptr, nullptr, nullptr, P, D, M, R, background, width, height, means3D, shs,
                        colors_precomp, scales, scale_modifier, rotations, transMat_precomp, viewmatrix, projmatrix,
                        campos, tan_fovx, tan_fovy, radii, geom_buffer, binning_buffer, binning_bytes, image_buffer,
                        dL_dpix, dL_dothers, dL_dmean2D, scratch, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dtransMat, dL_dsh,
@@ -547,7 +566,7 @@ int pgs_dsrp_backward(int P, int D, int M, int R, const float* background, int w
                       const float* dL_dothers, float* dL_dmean2D, float* scratch, float* dL_dopacity, float* dL_dcolor,
                       float* dL_dsemantics, float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh, float* dL_dscale,
                       float* dL_drot, int debug, void* stream) {
-  return backward_impl(true, semantic_types, semantics, dL_dsemantic_pix, dL_dsemantics, P, D, M, R, background,
+  return backward_impl(nullptr, nullptr, true, semantic_types, semantics, dL_dsemantic_pix, dL_dsemantics, P, D, M, R, background,
                        width, height, means3D, shs, colors_precomp, scales, scale_modifier, rotations,
                        transMat_precomp, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, radii, geom_buffer,
                        binning_buffer, binning_bytes, image_buffer, dL_dpix, dL_dothers, dL_dmean2D, scratch, dL_dopacity, dL_dcolor,
@@ -618,6 +637,82 @@ int pgs_sq2surfel_backward(int B, int Vt, int F, int K, const float* sq_r, const
     cudaMemcpyAsync(d_vertices, d_vertices_in, nv, cudaMemcpyDeviceToDevice, s);
   else
     cudaMemsetAsync(d_vertices, 0, nv, s);
+  cudaMemsetAsync(d_occ_acc, 0, (size_t)B * sizeof(float), s);
+  {
+    StageTimer t(PGS_STAGE_SQ_BWD, s);
+    launch_sq_backward(a, vertices, d_xyz, d_scaling, d_rotation, d_opacity, d_vertices, d_occ_acc, d_alpha,
+                       d_scale_raw, d_sq_r, d_sq_s, d_sq_t, d_sq_eps, d_sq_occ, s);
+  }
+  return check_cuda("sq2surfel_backward");
+}
+
+// ---- block-level (superquadric) rasteriser: surfels are generated inside preprocess -------------------
+size_t pgs_dsr_backward_blocks_scratch_bytes(int B, int Vt, int F, int K) {
+  const size_t P = (size_t)(B > 0 ? B : 0) * (F > 0 ? F : 0) * (K > 0 ? K : 0);
+  // render gradient records + per-surfel (xyz 3, log-scale 2, rotation 4, opacity 1, transMat 9) + sq scratch
+  return P * (GRAD_FLOATS + 3 + 2 + 4 + 1 + 9) * sizeof(float) + pgs_sq2surfel_backward_scratch_bytes(B, Vt) + 2048;
+}
+
+int pgs_dsr_forward_blocks(pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_alloc_fn binning_buffer,
+                           void* binning_user, pgs_alloc_fn image_buffer, void* image_user, int B, int Vt, int F, int K,
+                           const float* sq_r, const float* sq_s, const float* sq_t, const float* sq_eps,
+                           const float* sq_occ, const float* eta, const float* omega, const int* faces,
+                           const float* alpha, const float* scale_raw, float ratio, float scale_min, int D, int M,
+                           const float* background, int width, int height, const float* shs,
+                           const float* colors_precomp, float scale_modifier, const float* viewmatrix,
+                           const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                           float* vertices, float* out_xyz, float* out_scaling, float* out_rotation,
+                           float* out_opacity, float* out_color, float* out_others, int* radii, int debug,
+                           void* stream) {
+  SqForward f;
+  if (int e = sq_fill(f.sq, B, Vt, F, K, sq_r, sq_s, sq_t, sq_eps, sq_occ, eta, omega, faces, alpha, scale_raw, ratio,
+                      scale_min))
+    return e;
+  f.vertices = vertices; f.out_xyz = out_xyz; f.out_scaling = out_scaling; f.out_rotation = out_rotation;
+  f.out_opacity = out_opacity;
+  return forward_impl(&f, false, 0, nullptr, nullptr, geometry_buffer, geometry_user, binning_buffer, binning_user,
+                      image_buffer, image_user, B * F * K, D, M, background, width, height, nullptr, shs, colors_precomp,
+                      nullptr, nullptr, scale_modifier, nullptr, nullptr, viewmatrix, projmatrix, cam_pos, tan_fovx,
+                      tan_fovy, 0, out_color, out_others, radii, debug, stream);
+}
+
+int pgs_dsr_backward_blocks(int B, int Vt, int F, int K, const float* sq_r, const float* sq_s, const float* sq_t,
+                            const float* sq_eps, const float* sq_occ, const float* eta, const float* omega,
+                            const int* faces, const float* alpha, const float* scale_raw, float ratio, float scale_min,
+                            const float* vertices, int D, int M, int R, const float* background, int width, int height,
+                            const float* shs, const float* colors_precomp, float scale_modifier,
+                            const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
+                            float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer,
+                            size_t binning_bytes, char* image_buffer, const float* dL_dpix, const float* dL_dothers,
+                            float* dL_dmean2D, void* scratch, float* dL_dcolor, float* dL_dsh, float* d_sq_r,
+                            float* d_sq_s, float* d_sq_t, float* d_sq_eps, float* d_sq_occ, float* d_alpha,
+                            float* d_scale_raw, int debug, void* stream) {
+  SqArgs a;
+  if (int e = sq_fill(a, B, Vt, F, K, sq_r, sq_s, sq_t, sq_eps, sq_occ, eta, omega, faces, alpha, scale_raw, ratio,
+                      scale_min))
+    return e;
+  if (!vertices || !scratch || !d_sq_r || !d_sq_s || !d_sq_t || !d_sq_eps || !d_sq_occ)
+    return set_error(PGS_ERR_INVALID_ARG, "null block gradient pointer");
+  const size_t P = (size_t)B * F * K;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* base = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(scratch), 256));
+  float* grad = base;                       base += align_up(P * GRAD_FLOATS, 64);
+  float* d_xyz = base;                      base += align_up(P * 3, 64);
+  float* d_scaling = base;                  base += align_up(P * 2, 64);
+  float* d_rotation = base;                 base += align_up(P * 4, 64);
+  float* d_opacity = base;                  base += align_up(P, 64);
+  float* d_transMat = base;                 base += align_up(P * 9, 64);
+  float* d_vertices = base;                 base += align_up((size_t)B * Vt * 3, 64);
+  float* d_occ_acc = base;
+  // render backward + preprocess backward (regenerating the surfels), per-surfel gradients into scratch
+  if (int e = backward_impl(&a, vertices, false, 0, nullptr, nullptr, nullptr, (int)P, D, M, R, background, width, height,
+                            nullptr, shs, colors_precomp, nullptr, scale_modifier, nullptr, nullptr, viewmatrix,
+                            projmatrix, campos, tan_fovx, tan_fovy, radii, geom_buffer, binning_buffer, binning_bytes,
+                            image_buffer, dL_dpix, dL_dothers, dL_dmean2D, grad, d_opacity, dL_dcolor, d_xyz, d_transMat,
+                            dL_dsh, d_scaling, d_rotation, debug, stream))
+    return e;
+  // per-surfel -> per-face -> per-vertex -> 13 parameters per block
+  cudaMemsetAsync(d_vertices, 0, (size_t)B * Vt * 3 * sizeof(float), s);
   cudaMemsetAsync(d_occ_acc, 0, (size_t)B * sizeof(float), s);
   {
     StageTimer t(PGS_STAGE_SQ_BWD, s);

@@ -8,6 +8,22 @@ namespace pgs {
 // bookkeeping for pgs_launch_count(): every kernel launch of this library is counted
 void count_launch(int n = 1);
 
+// ---- superquadric -> surfel parameterisation (games/block_mesh_splatting) ------------
+struct SqArgs {
+  int B, Vt, F, K;
+  const float* sq_r;       // [B,4] raw quaternion (w,x,y,z)
+  const float* sq_s;       // [B,3] raw log-scale
+  const float* sq_t;       // [B,3]
+  const float* sq_eps;     // [B,2] raw
+  const float* sq_occ;     // [B,1] raw
+  const float* eta;        // [B,Vt]
+  const float* omega;      // [B,Vt]
+  const int* faces;        // [B,F,3] int32
+  const float* alpha;      // [B*F,K,3] normalised barycentrics
+  const float* scale_raw;  // [B,F*K]
+  float ratio, scale_min;
+};
+
 struct PreprocessFwdArgs {
   int P, D, M;
   const float* means3D;
@@ -29,6 +45,15 @@ struct PreprocessFwdArgs {
   float4* rec;    // [P][REC_QUADS]
   float4* bbox;   // [P][CULL_QUADS] cull records (box + conic)
   uint32_t* tiles_touched;
+  // block-level mode: surfel i is generated in the kernel from the superquadric parameters (means3D, scales,
+  // rotations, opacities are then ignored); sq_out_* optionally materialise what was generated
+  bool use_sq;
+  SqArgs sq;
+  const float* sq_vertices;  // [B,Vt,3] from launch_sq_vertices
+  float* sq_out_xyz;         // [P,3] or nullptr
+  float* sq_out_scaling;     // [P,2] log-scales or nullptr
+  float* sq_out_rotation;    // [P,4] or nullptr
+  float* sq_out_opacity;     // [P] or nullptr
 };
 void launch_preprocess_fwd(const PreprocessFwdArgs& a, cudaStream_t s);
 void launch_preprocess_fwd_part(const PreprocessFwdArgs& a, cudaStream_t s);
@@ -143,27 +168,18 @@ struct PreprocessBwdArgs {
   float* dL_dmean3D;    // [P][3]
   float* dL_dtransMat;  // [P][9]
   float* dL_dsh;        // [P][M][3]
-  float* dL_dscales;    // [P][2]
+  float* dL_dscales;    // [P][2]  (block-level mode: gradient w.r.t. the LOG scales sq_surfels would store)
   float* dL_drots;      // [P][4]
+  // block-level mode (see PreprocessFwdArgs)
+  bool use_sq;
+  SqArgs sq;
+  const float* sq_vertices;
 };
 void launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t s);
 void launch_preprocess_bwd_part(const PreprocessBwdArgs& a, cudaStream_t s);
 
-// ---- superquadric -> surfel parameterisation (games/block_mesh_splatting) ------------
-struct SqArgs {
-  int B, Vt, F, K;
-  const float* sq_r;       // [B,4] raw quaternion (w,x,y,z)
-  const float* sq_s;       // [B,3] raw log-scale
-  const float* sq_t;       // [B,3]
-  const float* sq_eps;     // [B,2] raw
-  const float* sq_occ;     // [B,1] raw
-  const float* eta;        // [B,Vt]
-  const float* omega;      // [B,Vt]
-  const int* faces;        // [B,F,3] int32
-  const float* alpha;      // [B*F,K,3] normalised barycentrics
-  const float* scale_raw;  // [B,F*K]
-  float ratio, scale_min;
-};
+// ---- superquadric -> surfel parameterisation: launchers (SqArgs is declared at the top) ----
+void launch_sq_vertices(const SqArgs& a, float* vertices, cudaStream_t s);
 void launch_sq_forward(const SqArgs& a, float* vertices, float* xyz, float* scaling, float* rotation, float* opacity,
                        cudaStream_t s);
 void launch_sq_backward(const SqArgs& a, const float* vertices, const float* d_xyz, const float* d_scaling,

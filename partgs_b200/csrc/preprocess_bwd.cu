@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "linalg.cuh"
 #include "kernels.h"
+#include "sq_device.cuh"
 
 namespace pgs {
 
@@ -72,9 +73,10 @@ __device__ __forceinline__ void zero_sh_row(float* o_sh, int M) {
 
 // SH -> RGB backward (reference backward.cu:20-139): writes dL/dsh[M] and returns the mean3D
 // gradient that flows through the view direction.
+template <bool DIRECT = false>
 __device__ __forceinline__ v3 sh_backward(int idx, int deg, int M, const v3* means, v3 campos, const float* shs,
-                                          unsigned clamped, v3 dL_dcolor, v3* dL_dsh_out) {
-  v3 pos = means[idx];
+                                          unsigned clamped, v3 dL_dcolor, v3* dL_dsh_out, v3 pos_direct = v3()) {
+  v3 pos = DIRECT ? pos_direct : means[idx];
   v3 dir_orig = pos - campos;
   v3 dir = dir_orig / length(dir_orig);
   // SH coefficients through registers: 12 x 128-bit loads / stores per surfel when M == 16
@@ -183,6 +185,10 @@ __device__ __forceinline__ v3 sh_backward(int idx, int deg, int M, const v3* mea
   return v3(dL_dmean.x, dL_dmean.y, dL_dmean.z);
 }
 
+// SQ = block-level mode: the surfel is regenerated from the superquadric parameters (as in the forward
+// kernel); dL_dscales then receives the gradient w.r.t. the LOG scale (= dL/dscale * scale), which is what the
+// superquadric backward kernels consume together with dL_dmean3D, dL_drots and dL_dopacity.
+template <bool SQ>
 __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.P) return;
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
 
   const int W = int(a.focal_x * a.tan_fovx * 2);
   const int H = int(a.focal_y * a.tan_fovy * 2);
-  const bool precomp = (a.scales == nullptr);
+  const bool precomp = !SQ && (a.scales == nullptr);
 
   const float4* rec = a.rec + (size_t)idx * REC_QUADS;
   const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q4 = rec[4];
@@ -236,9 +242,16 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
     T[2] = v3(q2.x, q2.y, q2.z);
     normal = {0.0f, 0.0f, 0.0f};
   } else {
-    p_orig = {a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]};
-    rot = ((const v4*)a.rotations)[idx];
-    scale = ((const v2*)a.scales)[idx];
+    if (SQ) {
+      const SqSurfel sf = sq_generate(a.sq, a.sq_vertices, idx);
+      p_orig = sf.mean;
+      rot = v4(sf.quat.x, sf.quat.y, sf.quat.z, sf.quat.w);
+      scale = v2(sf.scale.x, sf.scale.y);
+    } else {
+      p_orig = {a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]};
+      rot = ((const v4*)a.rotations)[idx];
+      scale = ((const v2*)a.scales)[idx];
+    }
     R = quat_to_rotmat_b(rot);
     m3 S = diag3(1.f);
     S[0][0] = 1.0f * scale.x;  // scale_modifier deliberately ignored (backward.cu:481)
@@ -321,8 +334,8 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
     a.dL_drots[idx * 4 + 1] = dq.y;
     a.dL_drots[idx * 4 + 2] = dq.z;
     a.dL_drots[idx * 4 + 3] = dq.w;
-    a.dL_dscales[idx * 2 + 0] = (float)dot(dL_dRS[0], R[0]);
-    a.dL_dscales[idx * 2 + 1] = (float)dot(dL_dRS[1], R[1]);
+    a.dL_dscales[idx * 2 + 0] = (float)dot(dL_dRS[0], R[0]) * (SQ ? scale.x : 1.0f);
+    a.dL_dscales[idx * 2 + 1] = (float)dot(dL_dRS[1], R[1]) * (SQ ? scale.y : 1.0f);
     dmean = xyz(dL_dM[2]);
   } else {
     if (a.dL_dscales) { a.dL_dscales[idx * 2] = 0.f; a.dL_dscales[idx * 2 + 1] = 0.f; }
@@ -331,8 +344,8 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
 
   // SH backward (backward.cu:20-139), incl. view-direction -> mean3D path
   if (a.shs) {
-    dmean += sh_backward(idx, a.D, M, (const v3*)a.means3D, *(const v3*)a.cam_pos, a.shs, __float_as_uint(q4.w),
-                         dL_dcolor, (v3*)o_sh);
+    dmean += sh_backward<SQ>(idx, a.D, M, (const v3*)a.means3D, *(const v3*)a.cam_pos, a.shs, __float_as_uint(q4.w),
+                             dL_dcolor, (v3*)o_sh, v3(p_orig.x, p_orig.y, p_orig.z));
   } else if (o_sh) {
     for (int i = 0; i < M * 3; i++) o_sh[i] = 0.f;
   }
@@ -474,7 +487,8 @@ void launch_preprocess_bwd_part(const PreprocessBwdArgs& a, cudaStream_t s) {
 
 void launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t s) {
   if (a.P <= 0) return;
-  preprocess_bwd_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a);
+  if (a.use_sq) preprocess_bwd_kernel<true><<<(a.P + 255) / 256, 256, 0, s>>>(a);
+  else preprocess_bwd_kernel<false><<<(a.P + 255) / 256, 256, 0, s>>>(a);
   count_launch();
 }
 

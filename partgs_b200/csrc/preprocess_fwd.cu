@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "linalg.cuh"
 #include "kernels.h"
+#include "sq_device.cuh"
 
 namespace pgs {
 
@@ -115,9 +116,10 @@ __device__ __forceinline__ void tile_rect(const float2 p, int max_radius, uint2&
 // NOTE: keep this function exactly in this shape — its FMA contraction (decided by nvcc from the
 // expression tree and its surroundings) is what makes `rgb` bit-identical to the reference build;
 // a variant that first copied the coefficients to registers with 128-bit loads changed it.
+template <bool DIRECT = false>
 __device__ __forceinline__ v3 color_from_sh(int idx, int deg, int max_coeffs, const v3* means, v3 campos,
-                                            const float* shs, unsigned& clamped_mask) {
-  v3 pos = means[idx];
+                                            const float* shs, unsigned& clamped_mask, v3 pos_direct = v3()) {
+  v3 pos = DIRECT ? pos_direct : means[idx];
   v3 dir = pos - campos;
   dir = dir / length(dir);
 
@@ -220,6 +222,9 @@ __device__ __forceinline__ void cull_record(const m3& T, float2 xy, float opa, f
   out[0] = make_float4(__double2float_rd(x0), __double2float_rd(y0), __double2float_ru(x1), __double2float_ru(y1));
 }
 
+// SQ = block-level mode: the surfel is generated here from the superquadric parameters
+// (sq_device.cuh: sq_generate) instead of being read from means3D / scales / rotations / opacities.
+template <bool SQ>
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessFwdArgs a) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.P) return;
@@ -231,16 +236,26 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessFwdArgs a
   const int W = a.W, H = a.H;
   const float* orig_points = a.means3D;
 
+  SqSurfel sf;
+  if (SQ) {
+    sf = sq_generate(a.sq, a.sq_vertices, idx);
+    if (a.sq_out_xyz) { a.sq_out_xyz[3 * idx] = sf.mean.x; a.sq_out_xyz[3 * idx + 1] = sf.mean.y; a.sq_out_xyz[3 * idx + 2] = sf.mean.z; }
+    if (a.sq_out_scaling) { a.sq_out_scaling[2 * idx] = sf.log_scale.x; a.sq_out_scaling[2 * idx + 1] = sf.log_scale.y; }
+    if (a.sq_out_rotation) reinterpret_cast<float4*>(a.sq_out_rotation)[idx] = sf.quat;
+    if (a.sq_out_opacity) a.sq_out_opacity[idx] = sf.opacity;
+  }
+
   // near cull (auxiliary.h:185-210): only p_view.z <= 0.2 rejects.
-  float3 p_orig = {orig_points[3 * idx], orig_points[3 * idx + 1], orig_points[3 * idx + 2]};
+  float3 p_orig = SQ ? sf.mean : make_float3(orig_points[3 * idx], orig_points[3 * idx + 1], orig_points[3 * idx + 2]);
   float3 p_view = xform_point4x3(p_orig, a.viewmatrix);
   if (p_view.z <= 0.2f) return;
 
   m3 T;
   float3 normal;
-  if (a.transMat_precomp == nullptr) {
-    compute_transmat(p_orig, ((const v2*)a.scales)[idx], a.scale_modifier, ((const v4*)a.rotations)[idx],
-                     a.projmatrix, a.viewmatrix, W, H, T, normal);
+  if (SQ || a.transMat_precomp == nullptr) {
+    const v2 scale_in = SQ ? v2(sf.scale.x, sf.scale.y) : ((const v2*)a.scales)[idx];
+    const v4 rot_in = SQ ? v4(sf.quat.x, sf.quat.y, sf.quat.z, sf.quat.w) : ((const v4*)a.rotations)[idx];
+    compute_transmat(p_orig, scale_in, a.scale_modifier, rot_in, a.projmatrix, a.viewmatrix, W, H, T, normal);
   } else {
     const v3* T_ptr = (const v3*)a.transMat_precomp;
     T = make_m3(T_ptr[idx * 3 + 0], T_ptr[idx * 3 + 1], T_ptr[idx * 3 + 2]);
@@ -271,7 +286,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessFwdArgs a
   float r, g, b;
   unsigned clamped = 0;
   if (a.colors_precomp == nullptr) {
-    v3 c = color_from_sh(idx, a.D, a.M, (const v3*)orig_points, *(const v3*)a.cam_pos, a.shs, clamped);
+    v3 c = color_from_sh<SQ>(idx, a.D, a.M, (const v3*)orig_points, *(const v3*)a.cam_pos, a.shs, clamped,
+                             v3(p_orig.x, p_orig.y, p_orig.z));
     r = c.x; g = c.y; b = c.z;
   } else {
     r = a.colors_precomp[idx * 3 + 0];
@@ -279,7 +295,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessFwdArgs a
     b = a.colors_precomp[idx * 3 + 2];
   }
 
-  const float opa = a.opacities[idx];
+  const float opa = SQ ? sf.opacity : a.opacities[idx];
   float4* rec = a.rec + (size_t)idx * REC_QUADS;
   rec[0] = make_float4(T[0].x, T[0].y, T[0].z, point_image.x);
   rec[1] = make_float4(T[1].x, T[1].y, T[1].z, point_image.y);
@@ -416,8 +432,13 @@ __global__ void __launch_bounds__(256) check_frustum_kernel(int P, const float* 
 }
 
 void launch_preprocess_fwd(const PreprocessFwdArgs& a, cudaStream_t s) {
+  if (a.P > 0 && a.use_sq) {
+    preprocess_fwd_kernel<true><<<(a.P + 255) / 256, 256, 0, s>>>(a);
+    count_launch();
+    return;
+  }
   if (a.P <= 0) return;
-  preprocess_fwd_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a);
+  preprocess_fwd_kernel<false><<<(a.P + 255) / 256, 256, 0, s>>>(a);
   count_launch();
 }
 void launch_check_frustum(int P, const float* means3D, const float* viewmatrix, unsigned char* present,

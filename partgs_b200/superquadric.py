@@ -187,3 +187,129 @@ class BlockSurfelModel(torch.nn.Module):
     @property
     def get_opacity(self):
         return self._opacity
+
+
+# =============================================================================================
+# Block-level rasteriser: superquadric -> surfel placement fused into the rasteriser's preprocess
+# =============================================================================================
+class _RasterizeBlocks(torch.autograd.Function):
+    """(superquadric parameters, SH) -> (color, radii, allmap) in one op.
+
+    Equivalent to ``sq_to_surfels`` + the model accessors (exp / sigmoid) + ``GaussianRasterizer``, but the
+    per-surfel centre / scale / rotation / opacity never exist in HBM: the preprocess kernels of forward and
+    backward generate them from the 13 parameters per block (pgs_dsr_forward_blocks / _backward_blocks), and
+    the backward pass hands the per-surfel gradients to the face -> vertex -> block reduction directly.
+    """
+
+    @staticmethod
+    def forward(ctx, sq_r, sq_s, sq_t, sq_eps, sq_occ, alpha, scale_raw, shs, means2D, eta, omega, faces, ratio,
+                scale_min, raster_settings, materialize):
+        lib = _lib.load()
+        dev = sq_r.device
+        if not sq_r.is_cuda:
+            raise RuntimeError("rasterize_blocks needs CUDA tensors (no CPU fallback)")
+        B, Vt = eta.shape
+        F = faces.shape[1]
+        K = alpha.shape[1]
+        P = B * F * K
+        if alpha.shape[0] != B * F or scale_raw.numel() != P:
+            raise RuntimeError("alpha must be [B*F,K,3] and scale_raw [B,F*K,1]")
+        if shs.shape[0] != P:
+            raise RuntimeError(f"shs must have one row per surfel ({P}), got {shs.shape[0]}")
+        f32 = dict(dtype=torch.float32, device=dev)
+        t = [x.detach().float().contiguous() for x in (sq_r, sq_s, sq_t, sq_eps, sq_occ, eta, omega)]
+        faces_i = faces.to(torch.int32).contiguous()
+        alpha_c = alpha.detach().float().contiguous()
+        scale_c = scale_raw.detach().float().contiguous()
+        shs_c = _lib.require_cuda_float(shs.detach(), "shs")
+        rs = raster_settings
+        H, W = int(rs.image_height), int(rs.image_width)
+        M = shs_c.size(1)
+        vertices = torch.empty((B, Vt, 3), **f32)
+        out_color = torch.empty((3, H, W), **f32)
+        out_others = torch.empty((7, H, W), **f32)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        mats = [None] * 4
+        if materialize:
+            mats = [torch.empty((P, 3), **f32), torch.empty((P, 2), **f32), torch.empty((P, 4), **f32),
+                    torch.empty((P, 1), **f32)]
+        cam = [_lib.require_cuda_float(x, n) for x, n in ((rs.bg, "bg"), (rs.viewmatrix, "viewmatrix"),
+                                                         (rs.projmatrix, "projmatrix"), (rs.campos, "campos"))]
+        sc = _lib.AllocScope(dev)
+        with torch.cuda.device(dev), sc:
+            rc = lib.pgs_dsr_forward_blocks(
+                _lib.ALLOC_CB, sc.GEOM, _lib.ALLOC_CB, sc.BINNING, _lib.ALLOC_CB, sc.IMAGE, B, Vt, F, K,
+                *[x.data_ptr() for x in t], faces_i.data_ptr(), alpha_c.data_ptr(), scale_c.data_ptr(), float(ratio),
+                float(scale_min), int(rs.sh_degree), int(M), cam[0].data_ptr(), W, H, shs_c.data_ptr(), None,
+                float(rs.scale_modifier), cam[1].data_ptr(), cam[2].data_ptr(), cam[3].data_ptr(), float(rs.tanfovx),
+                float(rs.tanfovy), vertices.data_ptr(), *[_lib.ptr(m) for m in mats], out_color.data_ptr(),
+                out_others.data_ptr(), radii.data_ptr(), int(bool(rs.debug)), _lib.current_stream(dev))
+        if sc.error is not None:
+            raise sc.error
+        rendered = _lib.check(rc, "pgs_dsr_forward_blocks")
+        ctx.save_for_backward(*t, faces_i, alpha_c, scale_c, vertices, shs_c, radii, *cam, sc.tensor(sc.GEOM),
+                              sc.tensor(sc.BINNING), sc.tensor(sc.IMAGE))
+        ctx.dims = (B, Vt, F, K, float(ratio), float(scale_min), M, H, W, rendered)
+        ctx.rs = rs
+        ctx.shapes = (sq_occ.shape, alpha.shape, scale_raw.shape)
+        ctx.mark_non_differentiable(radii)
+        outs = (out_color, radii, out_others, vertices)
+        if materialize:
+            for m in mats:
+                ctx.mark_non_differentiable(m)
+            outs = outs + tuple(mats)
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_color, _g_radii, g_others, g_vertices, *g_mats):
+        lib = _lib.load()
+        (sq_r, sq_s, sq_t, sq_eps, sq_occ, eta, omega, faces_i, alpha_c, scale_c, vertices, shs_c, radii, bg, view,
+         proj, campos, geom, binning, img) = ctx.saved_tensors
+        B, Vt, F, K, ratio, scale_min, M, H, W, R = ctx.dims
+        rs = ctx.rs
+        dev = sq_r.device
+        P = B * F * K
+        f32 = dict(dtype=torch.float32, device=dev)
+        if g_vertices is not None and bool((g_vertices != 0).any()):
+            raise RuntimeError("rasterize_blocks: gradients w.r.t. the returned vertices are not supported; use "
+                               "sq_to_surfels for losses on the mesh vertices")
+        g_color = _lib.require_cuda_float(g_color if g_color is not None else torch.zeros((3, H, W), **f32), "g")
+        g_others = _lib.require_cuda_float(g_others if g_others is not None else torch.zeros((7, H, W), **f32), "g")
+        need = ctx.needs_input_grad
+        d_r, d_s, d_t = torch.empty((B, 4), **f32), torch.empty((B, 3), **f32), torch.empty((B, 3), **f32)
+        d_e, d_o = torch.empty((B, 2), **f32), torch.empty((B,), **f32)
+        d_alpha = torch.empty((B * F, K, 3), **f32) if need[5] else None
+        d_scale = torch.empty((B, F * K), **f32) if need[6] else None
+        d_sh = torch.empty((P, M, 3), **f32)
+        d_m2d = torch.empty((P, 3), **f32)
+        d_col = torch.empty((P, 3), **f32)
+        scratch = torch.empty(lib.pgs_dsr_backward_blocks_scratch_bytes(B, Vt, F, K), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.pgs_dsr_backward_blocks(
+                B, Vt, F, K, sq_r.data_ptr(), sq_s.data_ptr(), sq_t.data_ptr(), sq_eps.data_ptr(), sq_occ.data_ptr(),
+                eta.data_ptr(), omega.data_ptr(), faces_i.data_ptr(), alpha_c.data_ptr(), scale_c.data_ptr(), ratio,
+                scale_min, vertices.data_ptr(), int(rs.sh_degree), int(M), int(R), bg.data_ptr(), W, H,
+                shs_c.data_ptr(), None, float(rs.scale_modifier), view.data_ptr(), proj.data_ptr(), campos.data_ptr(),
+                float(rs.tanfovx), float(rs.tanfovy), radii.data_ptr(), _lib.ptr(geom), _lib.ptr(binning),
+                int(binning.numel()), _lib.ptr(img), g_color.data_ptr(), g_others.data_ptr(), d_m2d.data_ptr(),
+                scratch.data_ptr(), d_col.data_ptr(), d_sh.data_ptr(), d_r.data_ptr(), d_s.data_ptr(), d_t.data_ptr(),
+                d_e.data_ptr(), d_o.data_ptr(), _lib.ptr(d_alpha), _lib.ptr(d_scale), int(bool(rs.debug)),
+                _lib.current_stream(dev))
+        _lib.check(rc, "pgs_dsr_backward_blocks")
+        occ_shape, alpha_shape, scale_shape = ctx.shapes
+        return (d_r, d_s, d_t, d_e, d_o.reshape(occ_shape),
+                d_alpha.reshape(alpha_shape) if d_alpha is not None else None,
+                d_scale.reshape(scale_shape) if d_scale is not None else None,
+                d_sh if need[7] else None, d_m2d if need[8] else None, None, None, None, None, None, None, None)
+
+
+def rasterize_blocks(raster_settings, sq_r, sq_s, sq_t, sq_eps, sq_occ, alpha, scale_raw, shs, eta, omega, faces,
+                     means2D=None, ratio_block_scene=0.25, scale_block_min=0.2, materialize=False):
+    """Render a block-level (superquadric) scene: ``(color[3,H,W], radii[P], allmap[7,H,W], vertices[B,Vt,3])``
+    (+ ``xyz, _scaling, _rotation, opacity`` when ``materialize``).  ``raster_settings`` is the
+    ``GaussianRasterizationSettings`` of the base rasteriser; ``means2D`` ([P,3], optional) receives the
+    screen-space densification gradient like in ``GaussianRasterizer``."""
+    if means2D is None:
+        means2D = torch.zeros((shs.shape[0], 3), dtype=torch.float32, device=shs.device)
+    return _RasterizeBlocks.apply(sq_r, sq_s, sq_t, sq_eps, sq_occ, alpha, scale_raw, shs, means2D, eta, omega, faces,
+                                  ratio_block_scene, scale_block_min, raster_settings, materialize)

@@ -77,6 +77,57 @@ def main():
         del scene, cams, g
         torch.cuda.empty_cache()
 
+    # block-level scenes (C1 / C5 shapes): superquadric -> surfel generation fused into preprocess vs the unfused
+    # composition sq_to_surfels -> accessors -> GaussianRasterizer
+    from partgs_b200.superquadric import BlockSurfelModel, rasterize_blocks, sq_to_surfels
+    from partgs_b200.diff_surfel_rasterization import GaussianRasterizer
+    for label, B, K, W, H in (("C1-blocks", 8, 8, 400, 300), ("C5-blocks", 8, 1172, 1920, 1080)):
+        if label.split("-")[0] not in a.cfgs.split(","):
+            continue
+        gen = torch.Generator().manual_seed(5)
+        model = BlockSurfelModel(B, K, device=dev, generator=gen)
+        P = B * model.per_gs_num
+        shs = torch.zeros(P, 16, 3); shs[:, 0] = synth.RGB2SH(torch.rand(P, 3, generator=gen))
+        shs = shs.to(dev).requires_grad_(True)
+        cams = synth.make_cameras(min(a.views, 4), W, H, synth.SEED_BASE, device=dev)
+        g = synth.upstream_grads(W, H, synth.SEED_BASE, device=dev)
+        bg = torch.zeros(3, device=dev)
+        prm = [model.sq_r, model.sq_s, model.sq_t, model.sq_eps, model.sq_occ]
+
+        def clear():
+            for p_ in prm + [shs]:
+                p_.grad = None
+
+        def unfused(cam):
+            clear()
+            _, xyz, scaling, rotation, opacity = sq_to_surfels(*prm, model.alpha, model._scale, model.sq_eta,
+                                                               model.sq_omega, model.faces)
+            m2d = torch.zeros_like(xyz, requires_grad=True)
+            col, _, am = GaussianRasterizer(pu.settings_from_cam(cam, bg))(
+                means3D=xyz, means2D=m2d, opacities=opacity, shs=shs, scales=torch.exp(scaling),
+                rotations=torch.nn.functional.normalize(rotation))
+            torch.autograd.backward([col, am], [g["color"], g["allmap"]])
+
+        def fused(cam):
+            clear()
+            out = rasterize_blocks(pu.settings_from_cam(cam, bg), *prm, model.alpha, model._scale, shs, model.sq_eta,
+                                   model.sq_omega, model.faces)
+            torch.autograd.backward([out[0], out[2]], [g["color"], g["allmap"]])
+
+        row = dict(cfg=label, P=P, W=W, H=H)
+        for name_, fn in (("unfused_ms", unfused), ("fused_ms", fused)):
+            for cam in cams:
+                fn(cam)
+            torch.cuda.synchronize()
+            ts = []
+            for cam in cams:
+                ts += timed(lambda: fn(cam), a.reps)
+            row[name_] = round(statistics.median(ts), 4)
+        row["speedup_fused"] = round(row["unfused_ms"] / row["fused_ms"], 3)
+        print(json.dumps(row), flush=True)
+        del model, shs
+        torch.cuda.empty_cache()
+
     # distCUDA2 and superquadric->surfel (C1 / C5 shapes)
     from partgs_b200.simple_knn._C import distCUDA2
     for n in (100_000, 1_000_000, 3_000_000):
