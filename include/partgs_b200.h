@@ -47,7 +47,7 @@ unsigned long long pgs_launch_count(void);
 enum {
   PGS_STAGE_PREPROCESS_FWD = 0, PGS_STAGE_SCAN, PGS_STAGE_DUP_KEYS, PGS_STAGE_SORT, PGS_STAGE_TILE_RANGES,
   PGS_STAGE_RENDER_FWD, PGS_STAGE_RENDER_BWD, PGS_STAGE_PREPROCESS_BWD, PGS_STAGE_KNN, PGS_STAGE_SQ_FWD,
-  PGS_STAGE_SQ_BWD, PGS_NUM_STAGES
+  PGS_STAGE_SQ_BWD, PGS_STAGE_SURFACE_FWD, PGS_STAGE_SURFACE_BWD, PGS_NUM_STAGES
 };
 void pgs_timing_enable(int on);
 int pgs_timing_read(double* ms, unsigned long long* counts, int reset);
@@ -143,6 +143,26 @@ int pgs_dsr_backward_blocks(int B, int Vt, int F, int K, const float* sq_r, cons
                             float* dL_dmean2D, void* scratch, float* dL_dcolor, float* dL_dsh, float* d_sq_r,
                             float* d_sq_s, float* d_sq_t, float* d_sq_eps, float* d_sq_occ, float* d_alpha,
                             float* d_scale_raw, int debug, void* stream);
+
+/* ---- renderer post-processing: surface maps -----------------------------------------------
+ * SURVEY.md section 8(f) rank 1.  What render() does with the rasteriser's allmap right after the call
+ * (renderer/gaussian_renderer/__init__.py:110-149 + utils/point_utils.py:4-33: normal view->world,
+ * nan_to_num, expected depth = depth/alpha, surf_depth blend, depth_to_normal stencil, x alpha), ~30 ATen
+ * kernels in the reference, as one kernel forward and two backward.
+ *   allmap [7,H,W]; view3x3 = world_view_transform[:3,:3] (row-major, 9 floats, DEVICE pointer);
+ *   rays_m1 = intrins.inverse().T, rays_m2 = c2w[:3,:3].T (9 floats each), rays_o = c2w[:3,3] (3 floats),
+ *   all device pointers prepared by the caller exactly like point_utils.depths_to_points does;
+ *   out: rend_normal [3,H,W], surf_depth [1,H,W], surf_normal [3,H,W].
+ * Backward: any of the three incoming gradients may be NULL (= zero); g_allmap [7,H,W] is fully written
+ * (channel 6 and the direct alpha view gradient are left to the caller's autograd, they are plain slices). */
+int pgs_surface_maps_forward(int width, int height, const float* allmap, const float* view3x3, const float* rays_m1,
+                             const float* rays_m2, const float* rays_o, float depth_ratio, float* rend_normal,
+                             float* surf_depth, float* surf_normal, void* stream);
+size_t pgs_surface_maps_backward_scratch_bytes(int width, int height);
+int pgs_surface_maps_backward(int width, int height, const float* allmap, const float* view3x3, const float* rays_m1,
+                              const float* rays_m2, const float* rays_o, float depth_ratio, const float* g_rend_normal,
+                              const float* g_surf_depth, const float* g_surf_normal, void* scratch, float* g_allmap,
+                              void* stream);
 
 /* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:24-29, rasterizer_impl.cu:141-153).
  * present: one byte per point (bool). */

@@ -722,6 +722,41 @@ int pgs_dsr_backward_blocks(int B, int Vt, int F, int K, const float* sq_r, cons
   return check_cuda("sq2surfel_backward");
 }
 
+// ---- renderer post-processing (surface maps) ----------------------------------------------------------
+int pgs_surface_maps_forward(int width, int height, const float* allmap, const float* view3x3, const float* rays_m1,
+                             const float* rays_m2, const float* rays_o, float depth_ratio, float* rend_normal,
+                             float* surf_depth, float* surf_normal, void* stream) {
+  if (width <= 0 || height <= 0 || !allmap || !view3x3 || !rays_m1 || !rays_m2 || !rays_o || !rend_normal ||
+      !surf_depth || !surf_normal)
+    return set_error(PGS_ERR_INVALID_ARG, "surface_maps_forward: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  {
+    StageTimer t(PGS_STAGE_SURFACE_FWD, s);
+    launch_surface_maps_fwd(width, height, allmap, view3x3, rays_m1, rays_m2, rays_o, depth_ratio, rend_normal,
+                            surf_depth, surf_normal, s);
+  }
+  return check_cuda("surface_maps_forward");
+}
+size_t pgs_surface_maps_backward_scratch_bytes(int width, int height) {
+  return (size_t)6 * (width > 0 ? width : 0) * (height > 0 ? height : 0) * sizeof(float) + 256;
+}
+int pgs_surface_maps_backward(int width, int height, const float* allmap, const float* view3x3, const float* rays_m1,
+                              const float* rays_m2, const float* rays_o, float depth_ratio, const float* g_rend_normal,
+                              const float* g_surf_depth, const float* g_surf_normal, void* scratch, float* g_allmap,
+                              void* stream) {
+  if (width <= 0 || height <= 0 || !allmap || !view3x3 || !rays_m1 || !rays_m2 || !rays_o || !g_allmap ||
+      (g_surf_normal && !scratch))
+    return set_error(PGS_ERR_INVALID_ARG, "surface_maps_backward: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* sc = scratch ? reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(scratch), 256)) : nullptr;
+  {
+    StageTimer t(PGS_STAGE_SURFACE_BWD, s);
+    launch_surface_maps_bwd(width, height, allmap, view3x3, rays_m1, rays_m2, rays_o, depth_ratio, g_rend_normal,
+                            g_surf_depth, g_surf_normal, sc, g_allmap, s);
+  }
+  return check_cuda("surface_maps_backward");
+}
+
 size_t pgs_knn_temp_bytes(int P) { return knn_temp_bytes(P > 0 ? P : 0) + 256; }
 int pgs_knn_dist2(int P, const float* points, float* mean_dist2, void* temp, void* stream) {
   if (P < 0 || (P > 0 && (!points || !mean_dist2 || !temp))) return set_error(PGS_ERR_INVALID_ARG, "bad args");

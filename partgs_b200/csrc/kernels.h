@@ -187,6 +187,15 @@ void launch_sq_backward(const SqArgs& a, const float* vertices, const float* d_x
                         float* d_alpha, float* d_scale_raw, float* d_sq_r, float* d_sq_s, float* d_sq_t,
                         float* d_sq_eps, float* d_sq_occ, cudaStream_t s);
 
+// ---- renderer post-processing: surface maps (surface_maps.cu) -----------------------------------
+void launch_surface_maps_fwd(int W, int H, const float* allmap, const float* A, const float* M1, const float* M2,
+                             const float* o, float ratio, float* rend_normal, float* surf_depth, float* surf_normal,
+                             cudaStream_t s);
+// scratch: 6*W*H floats (only touched when g_surf_normal != nullptr); g_allmap [7,H,W] is fully written
+void launch_surface_maps_bwd(int W, int H, const float* allmap, const float* A, const float* M1, const float* M2,
+                             const float* o, float ratio, const float* g_rend_normal, const float* g_surf_depth,
+                             const float* g_surf_normal, float* scratch, float* g_allmap, cudaStream_t s);
+
 // ---- distCUDA2 (simple-knn) ---------------------------------------------------
 size_t knn_temp_bytes(int P);
 // returns 0, or <0 with a message in err (does one stream sync for the bounding box)

@@ -148,6 +148,27 @@ class Camera:
         return Camera(self.image_width, self.image_height, self.tanfovx, self.tanfovy,
                       self.viewmatrix.to(device), self.projmatrix.to(device), self.campos.to(device))
 
+    # attribute names of the reference's scene/cameras.py:Camera (what render() and point_utils read)
+    @property
+    def world_view_transform(self):
+        return self.viewmatrix
+
+    @property
+    def full_proj_transform(self):
+        return self.projmatrix
+
+    @property
+    def camera_center(self):
+        return self.campos
+
+    @property
+    def FoVx(self):
+        return 2.0 * math.atan(self.tanfovx)
+
+    @property
+    def FoVy(self):
+        return 2.0 * math.atan(self.tanfovy)
+
 
 def projection_matrix(znear, zfar, tanx, tany):
     """utils/graphics_utils.py:42-62 (getProjectionMatrix) restated from tan(fov/2)."""

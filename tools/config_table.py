@@ -29,6 +29,8 @@ def main():
     a = ap.parse_args()
     dev = "cuda"
     for name in a.cfgs.split(","):
+        if name not in synth.CONFIGS:
+            continue
         cfg = dict(synth.CONFIGS[name]); nv = min(cfg["views"], a.views)
         cfg, scene, cams = synth.make_config(name, device=dev, views=nv)
         S, W, H = cfg["S"], cfg["W"], cfg["H"]
@@ -127,6 +129,37 @@ def main():
         print(json.dumps(row), flush=True)
         del model, shs
         torch.cuda.empty_cache()
+
+    # renderer post-processing: the reference's ATen sequence (oracle/post_oracle.py is the same
+    # torch code minus the hard-coded .cuda()) on the GPU vs the fused kernels, forward + backward
+    if "post" in a.cfgs.split(",") or a.cfgs == "C1,C2,C3,C4,C5":
+        from oracle import post_oracle
+        from partgs_b200.renderer import surface_maps, camera_constants
+        for (W, H) in ((400, 300), (1600, 1200)):
+            cfgp, scene, _ = synth.make_config("C1", device=dev, views=1)
+            cam = synth.make_cameras(1, W, H, synth.SEED_BASE, device=dev)[0]
+            allmap = pu.run_ours(scene, cam, torch.zeros(3, device=dev))["allmap"].detach()
+            gen = torch.Generator().manual_seed(3)
+            g = {k: torch.randn(sh, generator=gen).to(dev) for k, sh in (("rend_normal", (3, H, W)), ("surf_depth", (1, H, W)),
+                                                                        ("surf_normal", (3, H, W)))}
+            consts = camera_constants(cam)
+
+            def run(fn):
+                a_ = allmap.clone().requires_grad_(True)
+                out = fn(a_)
+                torch.autograd.backward([out[k] for k in g], [g[k] for k in g])
+
+            f_ref = lambda a_: post_oracle.surface_maps(a_, cam, 1.0)
+            f_ours = lambda a_: surface_maps(a_, cam, 1.0)
+            f_ours_c = lambda a_: surface_maps(a_, cam, 1.0, constants=consts)
+            row = dict(kernel="surface_maps fwd+bwd", W=W, H=H)
+            for nm, fn in (("reference_ms", f_ref), ("ours_ms", f_ours), ("ours_cached_camera_ms", f_ours_c)):
+                for _ in range(3):
+                    run(fn)
+                torch.cuda.synchronize()
+                row[nm] = round(statistics.median(timed(lambda: run(fn), 7)), 4)
+            row["speedup"] = round(row["reference_ms"] / row["ours_ms"], 1)
+            print(json.dumps(row), flush=True)
 
     # distCUDA2 and superquadric->surfel (C1 / C5 shapes)
     from partgs_b200.simple_knn._C import distCUDA2
