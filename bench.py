@@ -102,6 +102,22 @@ class ClockSampler:
                 pass
             self._stop.wait(0.25)
 
+    def sample_now(self):
+        """One sample taken synchronously by the caller (from inside the timed loop): the background thread can be
+        starved of the GIL by a launch-bound main thread for the ~100 ms a short timed region lasts."""
+        n = self.nvml
+        if n is None:
+            return
+        try:
+            h = n.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.samples.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+            try:
+                self.mask |= int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                self.mask |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        except Exception:
+            pass
+
     def start(self):
         try:
             import pynvml
@@ -321,6 +337,8 @@ def run(args):
     e0.record()
     for i in range(args.steps):
         one_step(i)
+        if rank == 0 and (i & 7) == 3:
+            clocks.sample_now()   # ~20 us of host time, GPU queue stays full
     drain()
     e1.record()
     barrier()

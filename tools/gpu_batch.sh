@@ -15,6 +15,7 @@ tail -c 3000 $out/${tag}_bench_ref.json; tail -c 4000 $out/${tag}_bench_ours.jso
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 320 -c 64 --csv \
    --log-file $out/${tag}_launches_bench.csv python bench.py --steps 4 --warmup 3 --no-cpu > $out/${tag}_launches_bench.log 2>&1
 # full capture of the second C3 step (all kernels of one fwd+bwd)
-timeout 900 ncu --set full --clock-control none --import-source on -s 16 -c 16 -f -o $out/${tag}_c3_step \
+timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:^(render_|preprocess_|rs_|scan_k|duplicate_|identify_|tile_order)' -s 16 -c 16 -f -o $out/${tag}_c3_step \
    python tools/profile_step.py --cfg C3 --iters 2 > $out/${tag}_ncu_full.log 2>&1
+python tools/config_table.py > $out/${tag}_configs.jsonl 2> $out/${tag}_configs.err; cat $out/${tag}_configs.jsonl | cut -c1-200
 ls -la $out | tail -20
