@@ -302,9 +302,15 @@ def run(args):
             h.wait()
         pending.clear()
 
+    schedule = None  # balanced per-step view assignment (N > 1), built after the first pass over the views
+
+    def cam_of_step(i):
+        if schedule is not None:
+            return all_cams[schedule[i % len(schedule)][rank]]
+        return my_cams[i % len(my_cams)]
+
     def one_step(i):
-        cam = my_cams[i % len(my_cams)]
-        loss, grads = arm.step(cam, bg, g)
+        loss, grads = arm.step(cam_of_step(i), bg, g)
         allreduce_grads(grads)
         return loss
 
@@ -318,8 +324,26 @@ def run(args):
     # view's size, then W more warm-up steps let the caching allocator settle before the timed region
     n_warm = max(args.warmup, 3)
     views_per_rank = (len(all_cams) + world - 1) // world  # same count on every rank (collectives must match)
-    for i in range(min(views_per_rank, 64) + n_warm):
-        one_step(i)
+    if world > 1 and args.schedule == "balanced":
+        # first pass: every rank renders its round-robin share once and times each view; the costs are shared and
+        # the views re-dealt so that the N views of one step cost about the same (dist.balanced_view_schedule)
+        from partgs_b200.dist import balanced_view_schedule
+        cost = torch.zeros(len(all_cams), device=dev)
+        for vi in range(rank, len(all_cams), world):
+            arm.step(all_cams[vi], bg, g)          # allocator / arena warm-up for this view
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            arm.step(all_cams[vi], bg, g)
+            ev1.record()
+            torch.cuda.synchronize()
+            cost[vi] = ev0.elapsed_time(ev1)
+        dist.all_reduce(cost)
+        schedule = balanced_view_schedule(cost.tolist(), world)
+        for i in range(len(schedule) + n_warm):
+            one_step(i)
+    else:
+        for i in range(min(views_per_rank, 64) + n_warm):
+            one_step(i)
     drain()
     torch.cuda.synchronize()
 
@@ -388,7 +412,7 @@ def run(args):
             if i + 1 < n:
                 upload(1 - s)
             cur.wait_event(ready[s])
-            cam = my_cams[i % len(my_cams)]
+            cam = cam_of_step(i)
             prm = slots[s]
             if arm.name == "ours":
                 prm = {k: v.detach().requires_grad_(True) for k, v in prm.items()}
@@ -415,7 +439,7 @@ def run(args):
         return
 
     # ---- R of the last view (needed by the byte model); taken outside the timed region --
-    cam = my_cams[(args.steps - 1) % len(my_cams)]
+    cam = cam_of_step(args.steps - 1)
     if arm.name == "ours":
         from partgs_b200.diff_surfel_rasterization import _C
         e = torch.empty(0, device=dev)
@@ -432,7 +456,8 @@ def run(args):
         "warmup": max(args.warmup, 3), "ms_per_step": round(t_ms / args.steps, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{name}: {P} surfels, {W}x{H}, fwd+bwd, all 10 output channels get gradient",
-                   "views": cfg["views"], "views_per_rank": len(my_cams), "sharding": "by camera",
+                   "views": cfg["views"], "views_per_rank": len(my_cams),
+                   "sharding": "by camera" + (", steps dealt from the cost-sorted view list" if schedule is not None else ""),
                    "collective": ("none" if world == 1 or args.no_allreduce else
                                   "all-reduce of the 232 B/surfel gradient bucket per step: " +
                                   ("copy-engine reduce-scatter/all-gather over NVLink peer memory" if peer is not None
@@ -494,6 +519,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--schedule", default="balanced", choices=["balanced", "roundrobin"],
+                    help="N>1: which views share a lock-step (cost-sorted groups, or plain round-robin)")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="gradient all-reduce at N>1: copy-engine peer-memory collective (default) or NCCL")
     ap.add_argument("--no-allreduce", action="store_true",

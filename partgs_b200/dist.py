@@ -45,6 +45,33 @@ def shard_views(n_views: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_views, world))
 
 
+def balanced_view_schedule(costs: Sequence[float], world: int) -> List[List[int]]:
+    """Lock-step data parallelism ends every step with the slowest rank, and views differ a lot in cost (instance
+    count, depth complexity).  Given a per-view cost (measured step time), return steps of `world` view indices
+    with similar cost: views sorted by cost, dealt in consecutive groups; when the view count is not a multiple
+    of `world` the last group is completed with its cheapest neighbours (every view still appears); expensive and
+    cheap steps alternate.  Rank r renders ``schedule[k % len(schedule)][r]`` in step k."""
+    n = len(costs)
+    if n == 0 or world <= 0:
+        raise ValueError("need at least one view and one rank")
+    order = sorted(range(n), key=lambda i: -float(costs[i]))
+    steps = []
+    for s in range(0, n, world):
+        grp = order[s:s + world]
+        if len(grp) < world:                      # complete the last step with the views just before it
+            fill = order[max(0, s - (world - len(grp))):s] or order[:1]
+            grp = (fill + grp + fill * world)[:world] if len(fill) + len(grp) < world else fill[-(world - len(grp)):] + grp
+        steps.append(grp)
+    # alternate expensive and cheap steps so that any window of consecutive steps sees an average mix
+    lo, hi, mixed = 0, len(steps) - 1, []
+    while lo <= hi:
+        mixed.append(steps[lo])
+        if hi != lo:
+            mixed.append(steps[hi])
+        lo, hi = lo + 1, hi - 1
+    return mixed
+
+
 def grad_bucket(grads: Iterable[torch.Tensor]):
     """If all gradients live in one allocation (the rasteriser's backward carves its five parameter
     gradients out of a single flat buffer), return one flat tensor covering them so that a single

@@ -71,3 +71,23 @@ def test_shard_views_validation():
     assert shard_views(2, 5, 8) == []
     with pytest.raises(ValueError):
         shard_views(4, 2, 2)
+
+
+def test_balanced_view_schedule():
+    from partgs_b200.dist import balanced_view_schedule
+    import random
+    rnd = random.Random(0)
+    for n, world in ((49, 8), (64, 8), (7, 2), (3, 4), (1, 1), (10, 4)):
+        costs = [rnd.random() for _ in range(n)]
+        steps = balanced_view_schedule(costs, world)
+        assert all(len(s) == world for s in steps)
+        assert sorted(set(v for s in steps for v in s)) == list(range(n))       # every view is rendered
+        if n >= world:
+            spread = max(max(costs[v] for v in s) - min(costs[v] for v in s) for s in steps)
+            assert spread <= max(costs) - min(costs)
+        # the most expensive view is in the first step, the cheapest in the second (expensive / cheap alternate)
+        assert max(range(n), key=lambda i: costs[i]) in steps[0]
+        if len(steps) > 1:
+            assert min(range(n), key=lambda i: costs[i]) in steps[1]
+    with pytest.raises(ValueError):
+        balanced_view_schedule([], 2)
