@@ -47,7 +47,8 @@ unsigned long long pgs_launch_count(void);
 enum {
   PGS_STAGE_PREPROCESS_FWD = 0, PGS_STAGE_SCAN, PGS_STAGE_DUP_KEYS, PGS_STAGE_SORT, PGS_STAGE_TILE_RANGES,
   PGS_STAGE_RENDER_FWD, PGS_STAGE_RENDER_BWD, PGS_STAGE_PREPROCESS_BWD, PGS_STAGE_KNN, PGS_STAGE_SQ_FWD,
-  PGS_STAGE_SQ_BWD, PGS_STAGE_SURFACE_FWD, PGS_STAGE_SURFACE_BWD, PGS_NUM_STAGES
+  PGS_STAGE_SQ_BWD, PGS_STAGE_SURFACE_FWD, PGS_STAGE_SURFACE_BWD, PGS_STAGE_PHOTO_FWD,
+  PGS_STAGE_PHOTO_BWD, PGS_NUM_STAGES
 };
 void pgs_timing_enable(int on);
 int pgs_timing_read(double* ms, unsigned long long* counts, int reset);
@@ -163,6 +164,19 @@ int pgs_surface_maps_backward(int width, int height, const float* allmap, const 
                               const float* rays_m2, const float* rays_o, float depth_ratio, const float* g_rend_normal,
                               const float* g_surf_depth, const float* g_surf_normal, void* scratch, float* g_allmap,
                               void* stream);
+
+/* ---- photometric loss: L1 + SSIM ----------------------------------------------------------
+ * SURVEY.md section 8(f) rank 2.  loss = (1 - lambda) * mean|image - gt| + lambda * (1 - ssim(image, gt))
+ * (train.py:230-231; utils/loss_utils.py:6-7 l1_loss, :12-54 ssim with the 11x11 sigma-1.5 Gaussian window,
+ * zero padding).  Forward leaves {sum of the SSIM map, sum |image - gt|} in `sums` (2 doubles, device) and three
+ * derivative maps in `dmaps` ([3][C][H][W] floats) for backward; the caller forms the scalar from the sums
+ * (N = C*H*W).  Backward reads the upstream gradient of the scalar from DEVICE memory (g_loss, 1 float) and writes
+ * d loss / d image [C][H][W]. */
+int pgs_photometric_forward(int channels, int height, int width, const float* image, const float* gt, double* sums,
+                            float* dmaps, void* stream);
+int pgs_photometric_backward(int channels, int height, int width, const float* image, const float* gt,
+                             const float* dmaps, const float* g_loss, float lambda_dssim, float* g_image,
+                             void* stream);
 
 /* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:24-29, rasterizer_impl.cu:141-153).
  * present: one byte per point (bool). */

@@ -75,6 +75,9 @@ SIGNATURES = {
     "pgs_surface_maps_backward_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "pgs_surface_maps_backward": (C.c_int, [C.c_int, C.c_int] + [_f32p] * 5 + [C.c_float] + [_f32p] * 3 +
                                   [_vp, _f32p, _vp]),
+    "pgs_photometric_forward": (C.c_int, [C.c_int, C.c_int, C.c_int, _f32p, _f32p, _vp, _f32p, _vp]),
+    "pgs_photometric_backward": (C.c_int, [C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, C.c_float, _f32p,
+                                           _vp]),
     "pgs_knn_temp_bytes": (C.c_size_t, [C.c_int]),
     "pgs_knn_dist2": (C.c_int, [C.c_int, _f32p, _f32p, _vp, _vp]),
     "pgs_scan_temp_bytes": (C.c_size_t, [C.c_int]),
@@ -198,7 +201,7 @@ def require_cuda_float(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 STAGES = ("preprocess_fwd", "scan", "dup_keys", "sort", "tile_ranges", "render_fwd", "render_bwd", "preprocess_bwd",
-          "knn", "sq_fwd", "sq_bwd", "surface_fwd", "surface_bwd")
+          "knn", "sq_fwd", "sq_bwd", "surface_fwd", "surface_bwd", "photo_fwd", "photo_bwd")
 
 
 def timing_enable(on: bool = True):

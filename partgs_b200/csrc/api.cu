@@ -757,6 +757,31 @@ int pgs_surface_maps_backward(int width, int height, const float* allmap, const 
   return check_cuda("surface_maps_backward");
 }
 
+// ---- photometric loss (L1 + SSIM) -----------------------------------------------------------------------
+int pgs_photometric_forward(int channels, int height, int width, const float* image, const float* gt, double* sums,
+                            float* dmaps, void* stream) {
+  if (channels <= 0 || height <= 0 || width <= 0 || !image || !gt || !sums || !dmaps)
+    return set_error(PGS_ERR_INVALID_ARG, "photometric_forward: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  {
+    StageTimer t(PGS_STAGE_PHOTO_FWD, s);
+    launch_photometric_fwd(channels, height, width, image, gt, sums, dmaps, s);
+  }
+  return check_cuda("photometric_forward");
+}
+int pgs_photometric_backward(int channels, int height, int width, const float* image, const float* gt,
+                             const float* dmaps, const float* g_loss, float lambda_dssim, float* g_image,
+                             void* stream) {
+  if (channels <= 0 || height <= 0 || width <= 0 || !image || !gt || !dmaps || !g_loss || !g_image)
+    return set_error(PGS_ERR_INVALID_ARG, "photometric_backward: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  {
+    StageTimer t(PGS_STAGE_PHOTO_BWD, s);
+    launch_photometric_bwd(channels, height, width, image, gt, dmaps, g_loss, lambda_dssim, g_image, s);
+  }
+  return check_cuda("photometric_backward");
+}
+
 size_t pgs_knn_temp_bytes(int P) { return knn_temp_bytes(P > 0 ? P : 0) + 256; }
 int pgs_knn_dist2(int P, const float* points, float* mean_dist2, void* temp, void* stream) {
   if (P < 0 || (P > 0 && (!points || !mean_dist2 || !temp))) return set_error(PGS_ERR_INVALID_ARG, "bad args");

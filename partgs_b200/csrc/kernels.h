@@ -196,6 +196,13 @@ void launch_surface_maps_bwd(int W, int H, const float* allmap, const float* A, 
                              const float* o, float ratio, const float* g_rend_normal, const float* g_surf_depth,
                              const float* g_surf_normal, float* scratch, float* g_allmap, cudaStream_t s);
 
+// ---- photometric loss: L1 + SSIM (photometric.cu) ------------------------------------------------
+// sums: 2 doubles {sum of the SSIM map, sum |img - gt|} (zeroed inside); dmaps: [3][C][H][W] derivative maps
+void launch_photometric_fwd(int C, int H, int W, const float* img, const float* gt, double* sums, float* dmaps,
+                            cudaStream_t s);
+void launch_photometric_bwd(int C, int H, int W, const float* img, const float* gt, const float* dmaps,
+                            const float* g_loss, float lambda, float* g_img, cudaStream_t s);
+
 // ---- distCUDA2 (simple-knn) ---------------------------------------------------
 size_t knn_temp_bytes(int P);
 // returns 0, or <0 with a message in err (does one stream sync for the bounding box)

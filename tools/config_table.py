@@ -161,6 +161,28 @@ def main():
             row["speedup"] = round(row["reference_ms"] / row["ours_ms"], 1)
             print(json.dumps(row), flush=True)
 
+    # photometric loss: the reference's conv2d-based L1 + SSIM on the GPU vs the fused kernels
+    if "post" in a.cfgs.split(",") or a.cfgs == "C1,C2,C3,C4,C5":
+        from oracle import loss_oracle
+        from partgs_b200.losses import photometric_loss
+        for (W, H) in ((400, 300), (1600, 1200)):
+            gen = torch.Generator().manual_seed(1)
+            gt = torch.rand(3, H, W, generator=gen).to(dev)
+            base = (gt + 0.1 * torch.randn(3, H, W, generator=gen).to(dev)).clamp(0, 1)
+
+            def run(fn):
+                x = base.clone().requires_grad_(True)
+                fn(x, gt, 0.2).backward()
+
+            row = dict(kernel="photometric loss (L1+SSIM) fwd+bwd", W=W, H=H)
+            for nm, fn in (("reference_ms", loss_oracle.photometric_loss), ("ours_ms", photometric_loss)):
+                for _ in range(3):
+                    run(fn)
+                torch.cuda.synchronize()
+                row[nm] = round(statistics.median(timed(lambda: run(fn), 7)), 4)
+            row["speedup"] = round(row["reference_ms"] / row["ours_ms"], 1)
+            print(json.dumps(row), flush=True)
+
     # distCUDA2 and superquadric->surfel (C1 / C5 shapes)
     from partgs_b200.simple_knn._C import distCUDA2
     for n in (100_000, 1_000_000, 3_000_000):
