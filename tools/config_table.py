@@ -183,6 +183,72 @@ def main():
             row["speedup"] = round(row["reference_ms"] / row["ours_ms"], 1)
             print(json.dumps(row), flush=True)
 
+    # one PartGS-style training iteration (train.py:225-257): render -> surface maps -> L1+SSIM + normal-consistency
+    # + distortion losses -> backward.  "reference" = unmodified reference CUDA rasteriser + the reference's ATen code
+    # for the rest (oracle/post_oracle.py, oracle/loss_oracle.py are that code), "ours" = this package end to end.
+    if "post" in a.cfgs.split(",") or a.cfgs == "C1,C2,C3,C4,C5":
+        from oracle import post_oracle, loss_oracle
+        from partgs_b200.renderer import surface_maps
+        from partgs_b200.losses import photometric_loss
+        from partgs_b200.diff_surfel_rasterization import GaussianRasterizer
+
+        class _RefRaster(torch.autograd.Function):   # reference CUDA behind autograd, like its own __init__.py
+            @staticmethod
+            def forward(ctx, means3D, shs, opac, scales, rots, cam, bg, scene):
+                f = ref_cuda.forward(dict(scene, means3D=means3D, shs=shs, opacities=opac, scales=scales, rotations=rots), cam, bg)
+                ctx.f, ctx.cam, ctx.bg = f, cam, bg
+                ctx.scene = dict(scene, means3D=means3D, shs=shs, opacities=opac, scales=scales, rotations=rots)
+                return f["color"], f["allmap"]
+            @staticmethod
+            def backward(ctx, gc, ga):
+                gr = ref_cuda.backward(ctx.f, ctx.scene, ctx.cam, ctx.bg, gc.contiguous(), ga.contiguous())
+                return gr["means3D"], gr["sh"], gr["opacity"], gr["scales"], gr["rotations"], None, None, None
+
+        for name in ("C2", "C3"):
+            cfgt, scene, cams = synth.make_config(name, device=dev, views=min(4, a.views))
+            W, H = cfgt["W"], cfgt["H"]
+            bg = torch.zeros(3, device=dev)
+            gen = torch.Generator().manual_seed(9)
+            gt = torch.rand(3, H, W, generator=gen).to(dev)
+            leaf = {k: scene[k].clone().requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+
+            def losses(color, sm, photo):
+                normal_error = (1 - (sm["rend_normal"] * sm["surf_normal"]).sum(dim=0))[None]
+                return photo(color, gt, 0.2) + 0.05 * normal_error.mean() + 1000.0 * sm["rend_dist"].mean()
+
+            def ours(cam):
+                for t_ in leaf.values():
+                    t_.grad = None
+                m2d = torch.zeros_like(leaf["means3D"], requires_grad=True)
+                color, _, allmap = GaussianRasterizer(pu.settings_from_cam(cam, bg))(
+                    means3D=leaf["means3D"], means2D=m2d, opacities=leaf["opacities"], shs=leaf["shs"],
+                    scales=leaf["scales"], rotations=leaf["rotations"])
+                losses(color, surface_maps(allmap, cam, 1.0), photometric_loss).backward()
+
+            def ref(cam):
+                for t_ in leaf.values():
+                    t_.grad = None
+                color, allmap = _RefRaster.apply(leaf["means3D"], leaf["shs"], leaf["opacities"], leaf["scales"],
+                                                 leaf["rotations"], cam, bg, scene)
+                losses(color, post_oracle.surface_maps(allmap, cam, 1.0), loss_oracle.photometric_loss).backward()
+
+            row = dict(kernel="training iteration (render + surface maps + losses + backward)", cfg=name, W=W, H=H)
+            for nm, fn in (("reference_ms", ref), ("ours_ms", ours)):
+                if nm == "reference_ms" and not ref_cuda.available("ref_dsr_C"):
+                    continue
+                for cam in cams:
+                    fn(cam)
+                torch.cuda.synchronize()
+                ts = []
+                for cam in cams:
+                    ts += timed(lambda: fn(cam), a.reps)
+                row[nm] = round(statistics.median(ts), 4)
+            if "reference_ms" in row:
+                row["speedup"] = round(row["reference_ms"] / row["ours_ms"], 2)
+            print(json.dumps(row), flush=True)
+            del scene, leaf
+            torch.cuda.empty_cache()
+
     # distCUDA2 and superquadric->surfel (C1 / C5 shapes)
     from partgs_b200.simple_knn._C import distCUDA2
     for n in (100_000, 1_000_000, 3_000_000):
