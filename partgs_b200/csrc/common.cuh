@@ -71,6 +71,11 @@ __device__ __forceinline__ unsigned lane_id() {
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
+// fire-and-forget float add into global memory (RED.ADD.F32: no return value, no generic-address check)
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
 // 16-byte async global->shared copy (LDGSTS).
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));

@@ -95,7 +95,6 @@ void launch_tile_order(const uint2* ranges, int ntiles, uint32_t* order, cudaStr
 struct RenderFwdArgs {
   const uint2* ranges;
   const uint32_t* tile_order;  // [ntiles] or nullptr (identity)
-  int tile_begin;              // this launch covers tile_order[tile_begin + blockIdx.x] (set by the launcher)
   const uint32_t* point_list;
   int W, H;
   int grid_x, grid_y;
@@ -123,7 +122,6 @@ void launch_render_fwd_part(const RenderFwdArgs& a, cudaStream_t s);
 struct RenderBwdArgs {
   const uint2* ranges;
   const uint32_t* tile_order;  // [ntiles] or nullptr (identity)
-  int tile_begin;              // this launch covers tile_order[tile_begin + blockIdx.x] (set by the launcher)
   const uint32_t* point_list;
   int W, H;
   int grid_x, grid_y;

@@ -19,7 +19,8 @@
 //     loop, so a warp never waits for a sibling with more work, and a surfel costs ALU time
 //     only in the warps whose footprint it can touch;
 //   * tiles are issued longest-list-first (tile_order, built by tile_order_kernel) so the
-//     heavy tiles do not form the tail of the launch;
+//     heavy tiles do not form the tail of the launch (giving the deepest tiles SMs of their own, on a forked
+//     high-priority stream, was measured too: no gain — their warps are bound by their own dependency chains);
 //   * warp-level early termination (all 32 pixels saturated) in forward;
 //   * the forward pass records, per warp and list position, the 32-bit mask of pixels that
 //     actually blended the surfel (`frag_mask`, 4 B per warp x instance, written coalesced).
@@ -45,13 +46,9 @@ namespace pgs {
 constexpr unsigned RFULL = 0xffffffffu;
 constexpr int NWARP = TILE_PIX / 32;
 constexpr int CHUNK = 32;  // candidates per warp step (one per lane)
-#ifndef PGS_FWD_ILP
-#define PGS_FWD_ILP 2
-#endif
-#ifndef PGS_FWD_MINB
-#define PGS_FWD_MINB 4
-#endif
-constexpr int FWD_ILP = PGS_FWD_ILP;  // fragments evaluated ahead of the in-order blend
+// Fragments evaluated ahead of the in-order blend.  Measured on C3: 2 -> 1.11 ms, 4 -> 1.14-1.23 ms, 8 -> 1.37-1.43 ms
+// (a deeper look-ahead evaluates up to ILP-1 slots past the end of every step and costs registers).
+constexpr int FWD_ILP = 2;
 
 struct __align__(16) WarpStage {
   float4 rec[CHUNK][REC_QUADS];  // 32 x 80 B
@@ -152,7 +149,7 @@ void launch_tile_order(const uint2* ranges, int ntiles, uint32_t* order, cudaStr
 // forward
 // =============================================================================
 template <bool PART>
-__global__ void __launch_bounds__(TILE_PIX, PART ? 2 : PGS_FWD_MINB) render_fwd_kernel(RenderFwdArgs a) {
+__global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 4) render_fwd_kernel(RenderFwdArgs a) {
   // dynamic shared memory: WarpStage [2][nw], then (PART) the semantic staging [2][nw][CHUNK][MAX_SEMANTIC];
   // nw = warps per CTA (8 = whole tile; 4/2/1 when the image has too few tiles to fill the GPU)
   extern __shared__ __align__(16) unsigned char fwd_smem[];
@@ -166,7 +163,7 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : PGS_FWD_MINB) render_fwd_
   const unsigned wid = (blockIdx.x % groups) * nw + lw;           // footprint (0..7) within the tile
   const int tid = wid * 32 + lane;                                // pixel slot within the tile
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int tile_slot = blockIdx.x / groups + a.tile_begin;
+  const int tile_slot = blockIdx.x / groups;
   const int tile_id = a.tile_order ? (int)a.tile_order[tile_slot] : tile_slot;
   const int tile_x = tile_id % a.grid_x, tile_y = tile_id / a.grid_x;
   const int fx0 = tile_x * TILE_X + (wid & 1) * WARP_FX;
@@ -429,7 +426,7 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(Rend
   const unsigned wid = (blockIdx.x % groups) * nw + lw;
   const int tid = wid * 32 + lane;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int tile_slot = blockIdx.x / groups + a.tile_begin;
+  const int tile_slot = blockIdx.x / groups;
   const int tile_id = a.tile_order ? (int)a.tile_order[tile_slot] : tile_slot;
   const int tile_x = tile_id % a.grid_x, tile_y = tile_id / a.grid_x;
   const int fx0 = tile_x * TILE_X + (wid & 1) * WARP_FX;
@@ -529,6 +526,9 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(Rend
   load_cand(2 * CHUNK, id_n2, mk_n2);
 
   const float fis = PART ? (float)(1 / (0.7071067811865476 * 0.7071067811865476)) : PGS_FILTER_INV_SQUARE;
+  // which float of the surfel's gradient record this lane adds to (see the reduction below)
+  const int red_off = (lane & 1) ? 17 + (int)(lane >> 4) : (int)(lane >> 1) + (lane == 30 ? 1 : 0);
+  const bool red_on = !(lane & 1) || lane == 1 || lane == 17;
 
   for (int base = 0, buf = 0; base < total; base += CHUNK, buf ^= 1) {
     int n_n = 0;
@@ -665,11 +665,11 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(Rend
         r2 += __shfl_xor_sync(RFULL, r2, 1);
       }
       __syncwarp();  // `red` is rewritten by the next fragment
+      // One reduction instruction per fragment: even lanes own dL/dT[9], dL/dmean2D[2], dL/dopacity, dL/dnormal[3]
+      // (lane 30: colour 0); lanes 1 and 17 carry the other two colour sums (every lane of a half holds its r2).
       const uint32_t gid = st.id[j];
-      float* dst = a.grad + (size_t)gid * GRAD_FLOATS;
-      // lanes 0,2,..,28 own dL/dT[9], dL/dmean2D[2], dL/dopacity, dL/dnormal[3]; lane 30 owns colour 0
-      if ((lane & 1) == 0) atomicAdd(dst + (lane >> 1) + (lane == 30 ? 1 : 0), r16);
-      if ((lane & 15) == 0) atomicAdd(dst + 17 + (lane >> 4), r2);
+      float* dst = a.grad + (size_t)gid * GRAD_FLOATS + red_off;
+      if (red_on) red_add_f32(dst, (lane & 1) ? r2 : r16);
       if (PART && S > 0) {
         // dL/dsem[ch] = sum_pixels alpha*T * dL/dpixel_sem[ch]  (no alpha gradient in the reference fork)
         float gs[16];
@@ -689,24 +689,6 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 3) render_bwd_kernel(Rend
 // =============================================================================
 // launchers
 // =============================================================================
-// Heavy tiles (the head of tile_order: depth complexity in the thousands) are the critical path of the
-// launch: their warps advance at 1/8 of an SM sub-partition's issue rate while the SM is full, and then
-// finish alone.  They are therefore launched first, on a forked stream, with extra dynamic shared memory
-// so that an SM hosting one of them takes at most one more CTA; the remaining tiles follow on the caller's
-// stream and fill the other SMs.  Fork/join are events, so the sequence stays graph-capturable.
-struct ForkJoin {
-  cudaStream_t side = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
-  bool init() {
-    if (side) return true;
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if (cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
-    cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
-    return true;
-  }
-};
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -724,46 +706,26 @@ static int warps_per_cta(int ntiles) {
   return 1;
 }
 
-template <bool PART> static void launch_fwd(const RenderFwdArgs& a0, cudaStream_t s) {
-  RenderFwdArgs a = a0;
+template <bool PART> static void launch_fwd(const RenderFwdArgs& a, cudaStream_t s) {
   const int ntiles = a.grid_x * a.grid_y;
   const int nw = warps_per_cta(ntiles);
   const int groups = NWARP / nw;
   const size_t smem = (size_t)2 * nw * sizeof(WarpStage) +
                       (PART ? (size_t)2 * nw * CHUNK * MAX_SEMANTIC * sizeof(float) : 0);
-  static const int heavy_k = env_int("PGS_HEAVY_TILES", 0);
-  static const int heavy_smem = env_int("PGS_HEAVY_SMEM_KB", 64) * 1024;
   static bool attr_set = false;
   if (!attr_set) {
     const size_t mx = (size_t)2 * NWARP * sizeof(WarpStage) +
-                      (PART ? (size_t)2 * NWARP * CHUNK * MAX_SEMANTIC * sizeof(float) : 0) + heavy_smem;
+                      (PART ? (size_t)2 * NWARP * CHUNK * MAX_SEMANTIC * sizeof(float) : 0);
     cudaFuncSetAttribute(render_fwd_kernel<PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
     attr_set = true;
   }
-  static thread_local ForkJoin fj[16];
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const int K = (a.tile_order && heavy_k > 0 && ntiles >= 4 * heavy_k && dev < 16 && fj[dev].init()) ? heavy_k : 0;
-  if (K > 0) {
-    ForkJoin& f = fj[dev];
-    cudaEventRecord(f.fork, s);
-    cudaStreamWaitEvent(f.side, f.fork, 0);
-    a.tile_begin = 0;
-    render_fwd_kernel<PART><<<K * groups, 32 * nw, smem + heavy_smem, f.side>>>(a);
-    cudaEventRecord(f.join, f.side);
-    count_launch();
-  }
-  a.tile_begin = K;
-  render_fwd_kernel<PART><<<(ntiles - K) * groups, 32 * nw, smem, s>>>(a);
+  render_fwd_kernel<PART><<<ntiles * groups, 32 * nw, smem, s>>>(a);
   count_launch();
-  if (K > 0) cudaStreamWaitEvent(s, fj[dev].join, 0);
 }
 void launch_render_fwd(const RenderFwdArgs& a, cudaStream_t s) { launch_fwd<false>(a, s); }
 void launch_render_fwd_part(const RenderFwdArgs& a, cudaStream_t s) { launch_fwd<true>(a, s); }
 
-template <bool PART> static void launch_bwd(const RenderBwdArgs& a0, cudaStream_t s) {
-  RenderBwdArgs a = a0;
-  a.tile_begin = 0;
+template <bool PART> static void launch_bwd(const RenderBwdArgs& a, cudaStream_t s) {
   const int ntiles = a.grid_x * a.grid_y;
   const int nw = warps_per_cta(ntiles);
   static bool attr_set = false;
