@@ -75,19 +75,19 @@ __device__ __forceinline__ bool conic_hits(const float4 c1, const float4 c2, flo
   float fmin_ = fminf(fminf(f(X0, Y0), f(X1, Y0)), fminf(f(X0, Y1), f(X1, Y1)));
   // edges Y = const: a X^2 + 2 (bY + d) X + ...,  vertex at X = -(bY + d)/a when a > 0
   if (a > 0.f) {
-    const float ia = __frcp_rn(a);
+    const float ia = rcp_approx(a);
     const float xa = fminf(fmaxf(-(b * Y0 + d) * ia, X0), X1), xb = fminf(fmaxf(-(b * Y1 + d) * ia, X0), X1);
     fmin_ = fminf(fmin_, fminf(f(xa, Y0), f(xb, Y1)));
   }
   if (c > 0.f) {
-    const float ic = __frcp_rn(c);
+    const float ic = rcp_approx(c);
     const float ya = fminf(fmaxf(-(b * X0 + e) * ic, Y0), Y1), yb = fminf(fmaxf(-(b * X1 + e) * ic, Y0), Y1);
     fmin_ = fminf(fmin_, fminf(f(X0, ya), f(X1, yb)));
   }
   // interior critical point (global minimum when the quadratic part is positive definite)
   const float det = a * c - b * b;
   if (a > 0.f && det > 0.f) {
-    const float idet = __frcp_rn(det);
+    const float idet = rcp_approx(det);
     const float xc = (b * e - c * d) * idet, yc = (b * d - a * e) * idet;
     if (xc >= X0 && xc <= X1 && yc >= Y0 && yc <= Y1) fmin_ = fminf(fmin_, f(xc, yc));
   }
@@ -327,17 +327,16 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 4) render_fwd_kernel(Rend
       // of this chain, not by issue slots.
       for (int j = 0; j < n_c; j += FWD_ILP) {
         float alpha[FWD_ILP], depth[FWD_ILP];
-        unsigned ok = 0;
+        bool ok[FWD_ILP];
 #pragma unroll
         for (int u = 0; u < FWD_ILP; u++) {
           const int ju = min(j + u, CHUNK - 1);
-          if (frag_eval<PART>(pixf, st.rec[ju][0], st.rec[ju][1], st.rec[ju][2], alpha[u], depth[u]) && (j + u < n_c))
-            ok |= 1u << u;
+          ok[u] = frag_eval<PART>(pixf, st.rec[ju][0], st.rec[ju][1], st.rec[ju][2], alpha[u], depth[u]) && (j + u < n_c);
         }
 #pragma unroll
         for (int u = 0; u < FWD_ILP; u++) {
           bool b = false;
-          if (((ok >> u) & 1u) && !done) b = blend(j + u, alpha[u], depth[u]);
+          if (ok[u] && !done) b = blend(j + u, alpha[u], depth[u]);
           const unsigned m = __ballot_sync(RFULL, b);
           if ((int)lane == j + u) my_mask = m;
         }
