@@ -102,6 +102,10 @@ class ClockSampler:
                 pass
             self._stop.wait(0.25)
 
+    def reset(self):
+        self.samples = []
+        self.mask = 0
+
     def sample_now(self):
         """One sample taken synchronously by the caller (from inside the timed loop): the background thread can be
         starved of the GIL by a launch-bound main thread for the ~100 ms a short timed region lasts."""
@@ -325,6 +329,11 @@ def run(args):
     # every camera of this rank is rendered once (untimed) so that the instance arena has seen each
     # view's size, then W more warm-up steps let the caching allocator settle before the timed region
     n_warm = max(args.warmup, 3)
+    # NVML attaches to the device on its first query (100-300 ms during which this process's kernel launches
+    # stall): start the clock sampler before the warm-up, its samples are reset when the timed region starts
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     if arm.name == "ours":
         # the library's per-stage timers draw their CUDA events from a pool that is filled on first use: run them
         # during warm-up already, so that no cudaEventCreate (slow on some hosts) lands inside the timed steps
@@ -370,11 +379,9 @@ def run(args):
     sync_us = (time.perf_counter() - t0) * 1e6 / 20
 
     # ---- timed region: inputs resident in HBM ------------------------------------------
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-
     def timed_pass():
+        if rank == 0:
+            clocks.reset()     # clock / throttle samples of THIS pass only
         if arm.name == "ours":
             arm._lib.timing_enable(True)
             arm._lib.timing_read(reset=True)
