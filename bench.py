@@ -539,6 +539,14 @@ def run(args):
         out["roofline"] = {"bound": "hbm", "kernel": "render_bwd_kernel", "achieved": round(ach, 1), "peak": peak,
                            "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic,
                            "peak_source": peak_src, "avg_launch_ms": round(ms / max(n, 1), 4)}
+        # the kernel is charged against the HBM roofline as the metric asks, but it is bound by instruction issue:
+        # attach the issue / pipe utilisation of the committed ncu capture (profiles/issue.json)
+        ip = ROOT / "profiles" / "issue.json"
+        if ip.exists():
+            try:
+                out["roofline"]["ncu_issue"] = json.loads(ip.read_text()).get("render_bwd_kernel")
+            except Exception:
+                pass
         out["stage_ms_per_step"] = {k: round(v[0] / args.steps, 4) for k, v in stage.items() if v[1]}
 
     # ---- CPU baseline: the oracle port on the host cores, bounded sample ------------------

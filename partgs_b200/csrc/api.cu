@@ -411,6 +411,12 @@ static int forward_impl(const SqForward* sqf, bool part, int S, const float* sem
     }
     capacity = BinningState::capacity_for(debug ? (size_t)num_rendered : want);
     if (int e = launch_rest(capacity, nullptr, num_rendered)) return e;
+  } else if (dev < 16 && (size_t)num_rendered * 2 < capacity_hint[dev].load()) {
+    // the arena is more than twice what this frame needed: let the remembered capacity decay (3 % per such
+    // frame, never below 1.25 x this frame), so that one exceptional frame does not size every later arena
+    size_t cur = capacity_hint[dev].load();
+    const size_t floor_ = (size_t)num_rendered + (size_t)num_rendered / 4;
+    capacity_hint[dev].store(std::max(floor_, cur - cur / 32));
   }
   if (debug) if (int e = check_sync(s, "render_fwd")) return e;
   return num_rendered;

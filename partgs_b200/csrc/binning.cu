@@ -402,10 +402,9 @@ static int rs_sort(KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_
   count_launch();
 
   const size_t smem = sizeof(KeyT) * RS_TILE + 4 * RS_TILE + 4 * (RS_WARPS * RS_RADIX + 2 * RS_RADIX);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(rs_onesweep_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
   }
   KeyT* kin = keys_a;
   uint32_t* vin = vals_a;

@@ -54,6 +54,17 @@ constexpr int CULL_QUADS = 3;
 constexpr int GRAD_FLOATS = 20;
 
 // ---- helpers ----------------------------------------------------------------
+// Function attributes (opt-in dynamic shared memory) are per device: `flags` is a per-kernel array of 64
+// "already set on device d" markers.  Returns true exactly once per device.
+inline bool first_use_on_device(bool (&flags)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
+
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 template <typename T>

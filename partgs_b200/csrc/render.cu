@@ -711,12 +711,11 @@ template <bool PART> static void launch_fwd(const RenderFwdArgs& a, cudaStream_t
   const int groups = NWARP / nw;
   const size_t smem = (size_t)2 * nw * sizeof(WarpStage) +
                       (PART ? (size_t)2 * nw * CHUNK * MAX_SEMANTIC * sizeof(float) : 0);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     const size_t mx = (size_t)2 * NWARP * sizeof(WarpStage) +
                       (PART ? (size_t)2 * NWARP * CHUNK * MAX_SEMANTIC * sizeof(float) : 0);
     cudaFuncSetAttribute(render_fwd_kernel<PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
-    attr_set = true;
   }
   render_fwd_kernel<PART><<<ntiles * groups, 32 * nw, smem, s>>>(a);
   count_launch();
@@ -727,11 +726,10 @@ void launch_render_fwd_part(const RenderFwdArgs& a, cudaStream_t s) { launch_fwd
 template <bool PART> static void launch_bwd(const RenderBwdArgs& a, cudaStream_t s) {
   const int ntiles = a.grid_x * a.grid_y;
   const int nw = warps_per_cta(ntiles);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(render_bwd_kernel<PART>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)bwd_smem_bytes(NWARP));
-    attr_set = true;
   }
   render_bwd_kernel<PART><<<ntiles * (NWARP / nw), 32 * nw, bwd_smem_bytes(nw), s>>>(a);
   count_launch();
