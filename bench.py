@@ -561,6 +561,41 @@ def run(args):
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": round(1.0 / dt, 4), "unit": UNIT, "cores": cpu_oracle.load().oracle_num_threads(),
                                "kind": "port", "sample": f"1 frame (view 0) of {name} fwd+bwd, oracle/surfel_oracle.c + OpenMP"}
+        # north_star also asks for the repo's PyTorch superquadric -> surfel path on the host cores: the torch-CPU
+        # restatement of BlockGaussianModel.prepare_scaling_rot (oracle/sq_oracle.py), C1 shape, forward + backward
+        try:
+            from oracle import sq_oracle
+            from partgs_b200.superquadric import BlockSurfelModel, sq_to_surfels
+            torch.set_num_threads(os.cpu_count() or 1)
+            m = BlockSurfelModel(8, 8, device=dev, generator=torch.Generator().manual_seed(1))
+            names = ("sq_r", "sq_s", "sq_t", "sq_eps", "sq_occ")
+            cpu_p = [getattr(m, k).detach().cpu().requires_grad_(True) for k in names]
+            cpu_c = [t.detach().cpu() for t in (m.alpha, m._scale, m.sq_eta, m.sq_omega, m.faces)]
+
+            def sq_cpu():
+                o = sq_oracle.sq_to_surfels(*cpu_p, *cpu_c)
+                sum(x.sum() for x in o[1:]).backward()
+
+            def sq_gpu():
+                o = sq_to_surfels(*[getattr(m, k) for k in names], m.alpha, m._scale, m.sq_eta, m.sq_omega, m.faces)
+                sum(x.sum() for x in o[1:]).backward()
+
+            def best_ms(fn, sync):
+                ts = []
+                for _ in range(5):
+                    t0 = time.perf_counter()
+                    fn()
+                    if sync:
+                        torch.cuda.synchronize()
+                    ts.append((time.perf_counter() - t0) * 1e3)
+                return min(ts[1:])
+
+            out["cpu_baseline"]["superquadric_to_surfel"] = {
+                "shape": "C1: 8 superquadrics x 320 faces x 8 = 20480 surfels, fwd+bwd",
+                "torch_cpu_ms": round(best_ms(sq_cpu, False), 3), "cores": os.cpu_count(),
+                "ours_gpu_ms": round(best_ms(sq_gpu, True), 3)}
+        except Exception as ex:  # the baseline is informative; never fail the bench line over it
+            out["cpu_baseline"]["superquadric_to_surfel"] = {"error": str(ex)[:200]}
     if args.impl == "reference":
         out["cpu_baseline"] = {"value": out["value"], "unit": UNIT, "cores": 0, "kind": "reference",
                                "sample": "unmodified reference CUDA rasteriser (oracle/_ref) on the same GPU, same steps"}
