@@ -178,6 +178,20 @@ int pgs_photometric_backward(int channels, int height, int width, const float* i
                              const float* dmaps, const float* g_loss, float lambda_dssim, float* g_image,
                              void* stream);
 
+/* ---- optimiser step / densification statistics ---------------------------------------------
+ * SURVEY.md section 8(f) rank 3 (partial).  pgs_adam_step: torch.optim.Adam's update (no amsgrad / weight decay;
+ * scene/gaussian_model.py:266 uses eps = 1e-15) for up to 16 tensors in ONE launch.  The tables are HOST arrays of
+ * device pointers; step_size[i] = lr_i / (1 - beta1^step) and bias_correction2_sqrt = sqrt(1 - beta2^step) are
+ * computed by the caller in double precision exactly like torch/optim/adam.py; the betas and eps travel as doubles so
+ * that (1 - beta) is formed in double too (1.f - 0.999f is off by 5e-5).
+ * pgs_densify_stats: for surfels with radii > 0: max_radii2D = max(max_radii2D, radii) (optional, may be NULL),
+ * grad_accum += |grad_means2D.xy|, denom += 1  (scene/gaussian_model.py:515-517, train.py:295-297). */
+int pgs_adam_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                  float* const* exp_avg_sq, const size_t* numel, const float* step_size, double beta1, double beta2,
+                  double eps, double bias_correction2_sqrt, void* stream);
+int pgs_densify_stats(int P, const int* radii, const float* grad_means2D, float* max_radii2D, float* grad_accum,
+                      float* denom, void* stream);
+
 /* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:24-29, rasterizer_impl.cu:141-153).
  * present: one byte per point (bool). */
 int pgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

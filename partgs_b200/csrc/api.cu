@@ -788,6 +788,33 @@ int pgs_photometric_backward(int channels, int height, int width, const float* i
   return check_cuda("photometric_backward");
 }
 
+// ---- optimiser step / densification statistics -----------------------------------------------------------
+int pgs_adam_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                  float* const* exp_avg_sq, const size_t* numel, const float* step_size, double beta1, double beta2,
+                  double eps, double bias_correction2_sqrt, void* stream) {
+  if (n_tensors < 0 || n_tensors > PGS_ADAM_MAX_TENSORS)
+    return set_error(PGS_ERR_INVALID_ARG, "adam_step: at most %d tensors per call", PGS_ADAM_MAX_TENSORS);
+  if (n_tensors > 0 && (!params || !grads || !exp_avg || !exp_avg_sq || !numel || !step_size))
+    return set_error(PGS_ERR_INVALID_ARG, "adam_step: null table");
+  AdamTable t;
+  t.n = n_tensors;
+  for (int i = 0; i < n_tensors; i++) {
+    if (numel[i] > 0 && (!params[i] || !grads[i] || !exp_avg[i] || !exp_avg_sq[i]))
+      return set_error(PGS_ERR_INVALID_ARG, "adam_step: null tensor %d", i);
+    t.param[i] = params[i]; t.grad[i] = grads[i]; t.exp_avg[i] = exp_avg[i]; t.exp_avg_sq[i] = exp_avg_sq[i];
+    t.numel[i] = numel[i]; t.step_size[i] = step_size[i];
+  }
+  launch_adam_multi(t, beta1, beta2, eps, bias_correction2_sqrt, (cudaStream_t)stream);
+  return check_cuda("adam_step");
+}
+int pgs_densify_stats(int P, const int* radii, const float* grad_means2D, float* max_radii2D, float* grad_accum,
+                      float* denom, void* stream) {
+  if (P < 0 || (P > 0 && (!radii || !grad_means2D || !grad_accum || !denom)))
+    return set_error(PGS_ERR_INVALID_ARG, "densify_stats: bad arguments");
+  launch_densify_stats(P, radii, grad_means2D, max_radii2D, grad_accum, denom, (cudaStream_t)stream);
+  return check_cuda("densify_stats");
+}
+
 size_t pgs_knn_temp_bytes(int P) { return knn_temp_bytes(P > 0 ? P : 0) + 256; }
 int pgs_knn_dist2(int P, const float* points, float* mean_dist2, void* temp, void* stream) {
   if (P < 0 || (P > 0 && (!points || !mean_dist2 || !temp))) return set_error(PGS_ERR_INVALID_ARG, "bad args");

@@ -201,6 +201,23 @@ void launch_photometric_fwd(int C, int H, int W, const float* img, const float* 
 void launch_photometric_bwd(int C, int H, int W, const float* img, const float* gt, const float* dmaps,
                             const float* g_loss, float lambda, float* g_img, cudaStream_t s);
 
+// ---- optimiser step / densification statistics (optim.cu) -----------------------------------------
+#define PGS_ADAM_MAX_TENSORS 16
+struct AdamTable {
+  int n;
+  float* param[PGS_ADAM_MAX_TENSORS];
+  const float* grad[PGS_ADAM_MAX_TENSORS];
+  float* exp_avg[PGS_ADAM_MAX_TENSORS];
+  float* exp_avg_sq[PGS_ADAM_MAX_TENSORS];
+  size_t numel[PGS_ADAM_MAX_TENSORS];
+  float step_size[PGS_ADAM_MAX_TENSORS];
+  int block_start[PGS_ADAM_MAX_TENSORS];
+};
+int launch_adam_multi(AdamTable& t, double beta1, double beta2, double eps, double bias_correction2_sqrt,
+                      cudaStream_t s);
+void launch_densify_stats(int P, const int* radii, const float* grad_means2D, float* max_radii2D, float* accum,
+                          float* denom, cudaStream_t s);
+
 // ---- distCUDA2 (simple-knn) ---------------------------------------------------
 size_t knn_temp_bytes(int P);
 // returns 0, or <0 with a message in err (does one stream sync for the bounding box)
