@@ -192,6 +192,39 @@ int pgs_adam_step(int n_tensors, float* const* params, const float* const* grads
 int pgs_densify_stats(int P, const int* radii, const float* grad_means2D, float* max_radii2D, float* grad_accum,
                       float* denom, void* stream);
 
+/* ---- densification (clone / split / prune) as one planned compaction ---------------------------
+ * SURVEY.md section 8(f) rank 3.  Replaces TwoGaussianModel.densify_and_prune
+ * (games/block_mesh_splatting/scene/two_gaussian_model.py:341-423 prune_points / densification_postfix /
+ * densify_and_split / densify_and_clone; scene/gaussian_model.py:384-436 _prune_optimizer / cat_tensors_to_optimizer,
+ * :495-509 densify_and_prune).  Row order of the result = the reference's:
+ *     [surviving originals | surviving clones | surviving split children, replica-major].
+ * 1. pgs_densify_plan classifies the P surfels.  Thresholds are the reference's Python scalars: max_grad,
+ *    dense_threshold = percent_dense * extent, min_opacity, world_size_threshold = 0.1 * extent (tested only when
+ *    use_world_size_test != 0, i.e. when the reference's max_screen_size is truthy; its screen-size test itself can
+ *    never fire because densification_postfix zeroes max_radii2D first), split_divisor = 0.8 * N.
+ *    scaling [P,2] and opacity [P] are the stored (pre-activation) parameters.  Outputs (device): code [P] bytes,
+ *    block_offsets [4 * pgs_densify_blocks(P)] u32, counts [8] u32 = {surviving originals, surviving clones, rows
+ *    selected for splitting (Ns: the caller draws z [N*Ns,3] standard normals, the reference's
+ *    torch.normal(0, stds)), surviving children per replica, rows selected for cloning, 0, 0, 0}.  The caller
+ *    reads counts back to size the outputs: n_out = counts[0] + counts[1] + N * counts[3].
+ * 2. pgs_densify_map writes src_row [n_out] (output row -> source row) and sample_row [N * counts[3]].
+ * 3. pgs_densify_gather moves up to 24 row-major float tensors in one launch: dst[t][r, :] = src[t][src_row[r], :],
+ *    or zeros for r >= n_keep when zero_new[t] != 0 (Adam moments of new surfels).  Tables are HOST arrays.
+ * 4. pgs_densify_children overwrites xyz / scaling of the split children:
+ *    xyz = R(rotation) @ (z * [exp(scaling), 0]) + xyz_parent, scaling = log(exp(scaling_parent) / split_divisor). */
+int pgs_densify_blocks(int P);
+int pgs_densify_plan(int P, const float* grad_accum, const float* denom, const float* scaling, const float* opacity,
+                     double max_grad, double dense_threshold, double min_opacity, int use_world_size_test,
+                     double world_size_threshold, double split_divisor, unsigned char* code,
+                     unsigned int* block_offsets, unsigned int* counts, void* stream);
+int pgs_densify_map(int P, const unsigned char* code, const unsigned int* block_offsets, const unsigned int* counts,
+                    int n_split, int* src_row, int* sample_row, void* stream);
+int pgs_densify_gather(int n_tensors, const float* const* src, float* const* dst, const int* widths,
+                       const int* zero_new, int n_out, int n_keep, const int* src_row, void* stream);
+int pgs_densify_children(int n_children, const unsigned int* counts, const int* src_row, const int* sample_row,
+                         const float* z, const float* xyz_in, const float* scaling_in, const float* rotation_in,
+                         double split_divisor, float* xyz_out, float* scaling_out, void* stream);
+
 /* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:24-29, rasterizer_impl.cu:141-153).
  * present: one byte per point (bool). */
 int pgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

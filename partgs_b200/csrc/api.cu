@@ -815,6 +815,64 @@ int pgs_densify_stats(int P, const int* radii, const float* grad_means2D, float*
   return check_cuda("densify_stats");
 }
 
+// ---- densification as one planned compaction -----------------------------------------------------------------
+int pgs_densify_blocks(int P) { return densify_blocks(P); }
+
+int pgs_densify_plan(int P, const float* grad_accum, const float* denom, const float* scaling, const float* opacity,
+                     double max_grad, double dense_threshold, double min_opacity, int use_world_size_test,
+                     double world_size_threshold, double split_divisor, unsigned char* code,
+                     unsigned int* block_offsets, unsigned int* counts, void* stream) {
+  if (P < 0 || !counts || (P > 0 && (!grad_accum || !denom || !scaling || !opacity || !code || !block_offsets)))
+    return set_error(PGS_ERR_INVALID_ARG, "densify_plan: bad arguments");
+  if (!(split_divisor > 0.0)) return set_error(PGS_ERR_INVALID_ARG, "densify_plan: split_divisor must be positive");
+  // ATen compares float tensors with Python scalars in float, and divides by a scalar as x * (1.f / scalar)
+  launch_densify_plan(P, grad_accum, denom, scaling, opacity, (float)max_grad, (float)dense_threshold,
+                      (float)min_opacity, use_world_size_test, (float)world_size_threshold,
+                      1.0f / (float)split_divisor, code, block_offsets, counts, (cudaStream_t)stream);
+  return check_cuda("densify_plan");
+}
+
+int pgs_densify_map(int P, const unsigned char* code, const unsigned int* block_offsets, const unsigned int* counts,
+                    int n_split, int* src_row, int* sample_row, void* stream) {
+  if (P < 0 || n_split < 1 || !counts || (P > 0 && (!code || !block_offsets)))
+    return set_error(PGS_ERR_INVALID_ARG, "densify_map: bad arguments");
+  launch_densify_map(P, code, block_offsets, counts, n_split, src_row, sample_row, (cudaStream_t)stream);
+  return check_cuda("densify_map");
+}
+
+int pgs_densify_gather(int n_tensors, const float* const* src, float* const* dst, const int* widths,
+                       const int* zero_new, int n_out, int n_keep, const int* src_row, void* stream) {
+  if (n_tensors < 0 || n_tensors > PGS_GATHER_MAX_TENSORS)
+    return set_error(PGS_ERR_INVALID_ARG, "densify_gather: at most %d tensors per call", PGS_GATHER_MAX_TENSORS);
+  if (n_out < 0 || n_keep < 0 || n_keep > n_out || (n_tensors > 0 && (!src || !dst || !widths || !zero_new)))
+    return set_error(PGS_ERR_INVALID_ARG, "densify_gather: bad arguments");
+  if (n_out == 0 || n_tensors == 0) return 0;
+  if (!src_row) return set_error(PGS_ERR_INVALID_ARG, "densify_gather: null row map");
+  GatherTable t;
+  t.n = n_tensors;
+  for (int i = 0; i < n_tensors; i++) {
+    if (!src[i] || !dst[i] || widths[i] < 1)
+      return set_error(PGS_ERR_INVALID_ARG, "densify_gather: null tensor or bad width at %d", i);
+    t.src[i] = src[i]; t.dst[i] = dst[i]; t.width[i] = widths[i]; t.zero_new[i] = zero_new[i];
+    t.numel[i] = (size_t)n_out * (size_t)widths[i];
+  }
+  launch_densify_gather(t, n_keep, src_row, (cudaStream_t)stream);
+  return check_cuda("densify_gather");
+}
+
+int pgs_densify_children(int n_children, const unsigned int* counts, const int* src_row, const int* sample_row,
+                         const float* z, const float* xyz_in, const float* scaling_in, const float* rotation_in,
+                         double split_divisor, float* xyz_out, float* scaling_out, void* stream) {
+  if (n_children < 0) return set_error(PGS_ERR_INVALID_ARG, "densify_children: bad arguments");
+  if (n_children == 0) return 0;
+  if (!counts || !src_row || !sample_row || !z || !xyz_in || !scaling_in || !rotation_in || !xyz_out || !scaling_out ||
+      !(split_divisor > 0.0))
+    return set_error(PGS_ERR_INVALID_ARG, "densify_children: bad arguments");
+  launch_densify_children(n_children, counts, src_row, sample_row, z, xyz_in, scaling_in, rotation_in,
+                          1.0f / (float)split_divisor, xyz_out, scaling_out, (cudaStream_t)stream);
+  return check_cuda("densify_children");
+}
+
 size_t pgs_knn_temp_bytes(int P) { return knn_temp_bytes(P > 0 ? P : 0) + 256; }
 int pgs_knn_dist2(int P, const float* points, float* mean_dist2, void* temp, void* stream) {
   if (P < 0 || (P > 0 && (!points || !mean_dist2 || !temp))) return set_error(PGS_ERR_INVALID_ARG, "bad args");

@@ -218,6 +218,31 @@ int launch_adam_multi(AdamTable& t, double beta1, double beta2, double eps, doub
 void launch_densify_stats(int P, const int* radii, const float* grad_means2D, float* max_radii2D, float* accum,
                           float* denom, cudaStream_t s);
 
+// ---- densification as one planned compaction (densify.cu) -------------------------------------------
+#define PGS_GATHER_MAX_TENSORS 24
+struct GatherTable {
+  int n;
+  const float* src[PGS_GATHER_MAX_TENSORS];
+  float* dst[PGS_GATHER_MAX_TENSORS];
+  size_t numel[PGS_GATHER_MAX_TENSORS];  // output elements = output rows x width
+  int width[PGS_GATHER_MAX_TENSORS];     // floats per row
+  int zero_new[PGS_GATHER_MAX_TENSORS];  // rows >= n_keep are written as zeros (Adam moments of new surfels)
+  int block_start[PGS_GATHER_MAX_TENSORS];
+};
+int densify_blocks(int P);
+// counts (device, 8 x u32): [0] surviving originals, [1] surviving clones, [2] rows selected for splitting,
+// [3] surviving split children per replica, [4] rows selected for cloning
+void launch_densify_plan(int P, const float* accum, const float* denom, const float* scaling, const float* opacity,
+                         float max_grad, float dense_thr, float min_opacity, int use_ws, float ws_thr,
+                         float inv_divisor, unsigned char* code, uint32_t* block_off, uint32_t* counts,
+                         cudaStream_t s);
+void launch_densify_map(int P, const unsigned char* code, const uint32_t* block_off, const uint32_t* counts,
+                        int n_split, int* src_row, int* sample_row, cudaStream_t s);
+void launch_densify_gather(GatherTable& t, int n_keep, const int* src_row, cudaStream_t s);
+void launch_densify_children(int n_children, const uint32_t* counts, const int* src_row, const int* sample_row,
+                             const float* z, const float* xyz_in, const float* scaling_in, const float* rotation_in,
+                             float inv_divisor, float* xyz_out, float* scaling_out, cudaStream_t s);
+
 // ---- distCUDA2 (simple-knn) ---------------------------------------------------
 size_t knn_temp_bytes(int P);
 // returns 0, or <0 with a message in err (does one stream sync for the bounding box)

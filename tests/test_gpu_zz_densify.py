@@ -1,0 +1,155 @@
+"""GPU parity of the planned-compaction densification (csrc/densify.cu) against the torch restatement of the
+reference (oracle/densify_oracle.py, itself pinned bit-exactly by golden vectors of the unmodified reference classes).
+
+STATUS: these kernels were written after this round's GPU budget was spent — they compile for sm_100a and the
+algorithm is checked on CPU (tests/test_densify_plan_model.py), but this file has not yet run on a B200.  Until it
+has, its tests are non-strict xfail (a pass shows up as XPASS, a failure cannot hide the verified suites) and the
+file sorts after every other GPU test.  Remove the marker once green on hardware.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import densify_oracle
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
+              pytest.mark.xfail(strict=False, reason="densify kernels not yet run on a B200 (round-1 GPU budget spent)")]
+DEV = "cuda"
+NAMES = densify_oracle.PARAM_NAMES
+GOLDEN = sorted((Path(__file__).parent / "golden").glob("densify_*.npz"))
+
+
+def _compare(ours, ref, n_keep_plus_clones):
+    (p_o, m_o, s_o, info), (p_r, m_r, s_r, info_r) = ours, ref
+    assert info["n_out"] == info_r["n_out"]
+    assert info["n_split_selected"] == info_r["n_split_selected"]
+    assert info["n_clone_selected"] == info_r["n_clone_selected"]
+    c = n_keep_plus_clones
+    for k in NAMES:
+        assert p_o[k].shape == p_r[k].shape, k
+        if k in ("xyz", "scaling"):
+            assert torch.equal(p_o[k][:c], p_r[k][:c]), k
+            # children: tolerance stated here — 1e-5 relative to the scene scale (fp32, different summation order
+            # in the 3x3 product; build_rotation is FMA-contracted in the kernel)
+            scale = float(p_r[k].abs().max()) + 1e-12
+            assert float((p_o[k][c:] - p_r[k][c:]).abs().max()) <= 1e-5 * scale if p_r[k][c:].numel() else True, k
+        else:
+            assert torch.equal(p_o[k], p_r[k]), k
+        if m_r[k] is None:
+            assert m_o[k] is None
+        else:
+            assert torch.equal(m_o[k][0], m_r[k][0]) and torch.equal(m_o[k][1], m_r[k][1]), k
+    assert torch.equal(s_o, s_r)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[p.stem for p in GOLDEN])
+def test_cuda_matches_reference_golden(path):
+    from partgs_b200 import densify
+    z = np.load(path)
+    t = {k: torch.from_numpy(z[k]).to(DEV) for k in z.files if z[k].ndim > 0}
+    mss = None if float(z["max_screen_size"]) < 0 else float(z["max_screen_size"])
+    args = (float(z["max_grad"]), float(z["min_opacity"]), float(z["extent"]), mss, float(z["percent_dense"]))
+    params = {k: t["in_" + k] for k in NAMES}
+    moments = {k: (t["in_m_" + k], t["in_v_" + k]) for k in NAMES}
+    p, m, s, info = densify.densify_and_prune(params, moments, t["in_semantic"], t["in_accum"], t["in_denom"], *args,
+                                              N=2, z=t["z"])
+    c = info["n_kept"] + info["n_clones"]
+    for k in NAMES:
+        want = t["out_" + k]
+        if k in ("xyz", "scaling"):
+            assert torch.equal(p[k][:c], want[:c]), k
+            assert float((p[k][c:] - want[c:]).abs().max()) <= 1e-5 * float(want.abs().max()), k
+        else:
+            assert torch.equal(p[k], want), k
+        assert torch.equal(m[k][0], t["out_m_" + k]) and torch.equal(m[k][1], t["out_v_" + k]), k
+    assert torch.equal(s, t["out_semantic"])
+
+
+def _random_model(P, S, deg, seed, extent):
+    g = torch.Generator().manual_seed(seed)
+    n_rest = (deg + 1) ** 2 - 1
+    params = {"xyz": torch.randn(P, 3, generator=g), "f_dc": torch.randn(P, 1, 3, generator=g),
+              "f_rest": torch.randn(P, n_rest, 3, generator=g) * 0.1, "opacity": torch.randn(P, 1, generator=g) * 3 - 2,
+              "scaling": torch.log(extent * 10 ** (torch.rand(P, 2, generator=g) * 3.0 - 3.2)),
+              "rotation": torch.randn(P, 4, generator=g)}
+    moments = {k: (torch.randn(v.shape, generator=g) * 1e-3, torch.rand(v.shape, generator=g) * 1e-6)
+               for k, v in params.items()}
+    sem = torch.rand(P, S, generator=g)
+    denom = torch.randint(0, 4, (P, 1), generator=g).float()
+    accum = torch.rand(P, 1, generator=g) * 6e-4 * denom
+    to = lambda x: x.to(DEV)
+    return ({k: to(v) for k, v in params.items()}, {k: (to(a), to(b)) for k, (a, b) in moments.items()}, to(sem),
+            to(accum), to(denom))
+
+
+@pytest.mark.parametrize("P,S,deg,N,mss", [(100_003, 16, 3, 2, 20), (5_000, 1, 0, 2, None), (70_001, 4, 1, 3, 20),
+                                           (1, 2, 1, 2, 20), (255, 3, 2, 2, 20), (257, 3, 2, 2, None)])
+def test_cuda_matches_oracle_on_random_models(P, S, deg, N, mss):
+    from partgs_b200 import densify
+    extent = 3.7
+    params, moments, sem, accum, denom = _random_model(P, S, deg, 1000 + P, extent)
+    args = (0.0002, 0.005, extent, mss, 0.01)
+    _, split = densify_oracle.split_selection(accum.clone(), denom, params["scaling"], args[0], extent, 0.01)
+    z = torch.randn(N * int(split.sum()), 3, generator=torch.Generator().manual_seed(5)).to(DEV)
+    ref = densify_oracle.densify_and_prune(params, moments, sem, accum.clone(), denom, *args, z, N=N)
+    ours = densify.densify_and_prune(params, moments, sem, accum, denom, *args, N=N, z=z)
+    _compare(ours, ref, ours[3]["n_kept"] + ours[3]["n_clones"])
+    assert ours[3]["n_out"] > 0 or P == 1
+
+
+def test_nothing_selected_and_everything_pruned():
+    from partgs_b200 import densify
+    params, moments, sem, accum, denom = _random_model(3000, 2, 1, 7, 2.0)
+    # thresholds nobody reaches: pure copy
+    p, m, s, info = densify.densify_and_prune(params, moments, sem, accum, denom, 1e9, -1.0, 2.0, None, 0.01)
+    assert info["n_out"] == 3000 and info["n_children"] == 0 and info["n_clones"] == 0
+    for k in NAMES:
+        assert torch.equal(p[k], params[k]) and torch.equal(m[k][0], moments[k][0])
+    # min_opacity above every sigmoid: empty model
+    p, m, s, info = densify.densify_and_prune(params, moments, sem, accum, denom, 0.0002, 2.0, 2.0, 20, 0.01)
+    assert info["n_out"] == 0 and p["f_rest"].shape == (0, 3, 3) and s.shape == (0, 2)
+
+
+def test_model_level_drop_in_matches_seeded_reference_flow():
+    """densify_and_prune_model on a reference-style model object: parameters re-wrapped, optimiser state moved,
+    statistics zeroed; with the generator seeded like the reference the children use the reference's draws."""
+    from types import SimpleNamespace
+    from partgs_b200 import densify
+    extent = 3.0
+    params, moments, sem, accum, denom = _random_model(20_000, 4, 2, 99, extent)
+    model = SimpleNamespace(percent_dense=0.01, _semantic=sem, xyz_gradient_accum=accum, denom=denom,
+                            max_radii2D=torch.zeros(20_000, device=DEV))
+    groups = []
+    for k, attr in densify._MODEL_ATTR.items():
+        prm = torch.nn.Parameter(params[k].clone())
+        setattr(model, attr, prm)
+        groups.append({"params": [prm], "lr": 1e-3, "name": k})
+    model.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+    for g in model.optimizer.param_groups:
+        p = g["params"][0]
+        model.optimizer.state[p] = {"step": torch.tensor(5.0), "exp_avg": moments[g["name"]][0].clone(),
+                                    "exp_avg_sq": moments[g["name"]][1].clone()}
+    _, split = densify_oracle.split_selection(accum.clone(), denom, params["scaling"], 0.0002, extent, 0.01)
+    torch.manual_seed(123)
+    z = torch.empty(2 * int(split.sum()), 3, device=DEV).normal_()
+    ref = densify_oracle.densify_and_prune(params, moments, sem, accum.clone(), denom, 0.0002, 0.005, extent, 20, 0.01, z)
+    torch.manual_seed(123)
+    info = densify.densify_and_prune_model(model, 0.0002, 0.005, extent, 20)
+    n = info["n_out"]
+    assert n == ref[3]["n_out"]
+    for g in model.optimizer.param_groups:
+        k, p = g["name"], g["params"][0]
+        assert p is getattr(model, densify._MODEL_ATTR[k]) and isinstance(p, torch.nn.Parameter) and p.requires_grad
+        st = model.optimizer.state[p]
+        assert float(st["step"]) == 5.0 and len(model.optimizer.state) == 6
+        scale = float(ref[0][k].abs().max())
+        assert float((p.detach() - ref[0][k]).abs().max()) <= 1e-5 * scale, k
+        assert torch.equal(st["exp_avg"], ref[1][k][0]) and torch.equal(st["exp_avg_sq"], ref[1][k][1])
+    assert torch.equal(model._semantic, ref[2])
+    assert model.xyz_gradient_accum.shape == (n, 1) and model.denom.shape == (n, 1) and model.max_radii2D.shape == (n,)
+    assert not model.xyz_gradient_accum.any() and not model.max_radii2D.any()
+    for g in model.optimizer.param_groups:  # the optimiser keeps working on the new tensors
+        g["params"][0].grad = torch.ones_like(g["params"][0])
+    model.optimizer.step()
