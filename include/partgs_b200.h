@@ -225,6 +225,15 @@ int pgs_densify_children(int n_children, const unsigned int* counts, const int* 
                          const float* z, const float* xyz_in, const float* scaling_in, const float* rotation_in,
                          double split_divisor, float* xyz_out, float* scaling_out, void* stream);
 
+/* ---- per-view epilogue of the multi-view extraction loop ---------------------------------------
+ * SURVEY.md section 8(f) rank 4.  GaussianExtractor.reconstruction (utils/mesh_utils.py:102-129) per rendered view:
+ * part_rgb = partmap_to_rgbmap(render_semantic) (:77-89: clamp to [0,1], argmax over the S part channels -> palette
+ * colour, pixels whose clamped channels sum to < 0.1 -> white) and normal_unit = F.normalize(rend_normal, dim=0)
+ * (:113).  semantic [S,H,W]; palette: (S+1) rows of palette_stride >= 3 floats (get_fancy_color(S+1), DEVICE
+ * memory); either output (and its input) may be NULL to skip that half. */
+int pgs_extract_maps(int width, int height, int n_parts, const float* semantic, const float* palette,
+                     int palette_stride, const float* rend_normal, float* part_rgb, float* normal_unit, void* stream);
+
 /* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:24-29, rasterizer_impl.cu:141-153).
  * present: one byte per point (bool). */
 int pgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

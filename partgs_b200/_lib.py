@@ -88,6 +88,7 @@ SIGNATURES = {
     "pgs_densify_gather": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "pgs_densify_children": (C.c_int, [C.c_int, _vp, _vp, _vp, _f32p, _f32p, _f32p, _f32p, C.c_double, _f32p, _f32p,
                                        _vp]),
+    "pgs_extract_maps": (C.c_int, [C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_int, _f32p, _f32p, _f32p, _vp]),
     "pgs_knn_temp_bytes": (C.c_size_t, [C.c_int]),
     "pgs_knn_dist2": (C.c_int, [C.c_int, _f32p, _f32p, _vp, _vp]),
     "pgs_scan_temp_bytes": (C.c_size_t, [C.c_int]),

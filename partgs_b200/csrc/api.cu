@@ -815,6 +815,19 @@ int pgs_densify_stats(int P, const int* radii, const float* grad_means2D, float*
   return check_cuda("densify_stats");
 }
 
+// ---- per-view epilogue of the extraction loop --------------------------------------------------------------
+int pgs_extract_maps(int width, int height, int n_parts, const float* semantic, const float* palette,
+                     int palette_stride, const float* rend_normal, float* part_rgb, float* normal_unit, void* stream) {
+  if (width < 0 || height < 0 || n_parts < 0 || (long long)width * height > 0x7fffffffLL)
+    return set_error(PGS_ERR_INVALID_ARG, "extract_maps: bad image size");
+  if (part_rgb && n_parts > 0 && (!semantic || !palette || palette_stride < 3))
+    return set_error(PGS_ERR_INVALID_ARG, "extract_maps: part map needs semantic, palette and palette_stride >= 3");
+  if (normal_unit && !rend_normal) return set_error(PGS_ERR_INVALID_ARG, "extract_maps: rend_normal is null");
+  launch_extract_maps(width * height, n_parts, semantic, palette, palette_stride, rend_normal, part_rgb, normal_unit,
+                      (cudaStream_t)stream);
+  return check_cuda("extract_maps");
+}
+
 // ---- densification as one planned compaction -----------------------------------------------------------------
 int pgs_densify_blocks(int P) { return densify_blocks(P); }
 

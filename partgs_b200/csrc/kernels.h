@@ -243,6 +243,10 @@ void launch_densify_children(int n_children, const uint32_t* counts, const int* 
                              const float* z, const float* xyz_in, const float* scaling_in, const float* rotation_in,
                              float inv_divisor, float* xyz_out, float* scaling_out, cudaStream_t s);
 
+// ---- per-view epilogue of the extraction loop (extract.cu) -----------------------------------------
+void launch_extract_maps(int npix, int S, const float* semantic, const float* palette, int palette_stride,
+                         const float* rend_normal, float* part_rgb, float* normal_unit, cudaStream_t s);
+
 // ---- distCUDA2 (simple-knn) ---------------------------------------------------
 size_t knn_temp_bytes(int P);
 // returns 0, or <0 with a message in err (does one stream sync for the bounding box)

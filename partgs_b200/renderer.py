@@ -127,3 +127,40 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
             "radii": radii}
     rets.update(surface_maps(allmap, viewpoint_camera, pipe.depth_ratio))
     return rets
+
+
+def render_part(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None):
+    """Mirror of the reference render_part() (renderer/gaussian_renderer_2d/__init__.py:11-147): the `_part`
+    rasteriser (semantics in, ``render_semantic`` out, 8-channel allmap) followed by the same surface-map
+    post-processing as render()."""
+    from .diff_surfel_rasterization_part import GaussianRasterizationSettings as PartSettings
+    from .diff_surfel_rasterization_part import GaussianRasterizer as PartRasterizer
+    screenspace_points = torch.zeros_like(pc.get_xyz, dtype=pc.get_xyz.dtype, requires_grad=True) + 0
+    try:
+        screenspace_points.retain_grad()
+    except Exception:
+        pass
+    raster_settings = PartSettings(
+        image_height=int(viewpoint_camera.image_height), image_width=int(viewpoint_camera.image_width),
+        tanfovx=math.tan(viewpoint_camera.FoVx * 0.5), tanfovy=math.tan(viewpoint_camera.FoVy * 0.5), bg=bg_color,
+        scale_modifier=scaling_modifier, viewmatrix=viewpoint_camera.world_view_transform,
+        projmatrix=viewpoint_camera.full_proj_transform, sh_degree=pc.active_sh_degree,
+        campos=viewpoint_camera.camera_center, prefiltered=False, debug=False)
+    rasterizer = PartRasterizer(raster_settings=raster_settings)
+    if getattr(pipe, "compute_cov3D_python", False):
+        raise NotImplementedError("compute_cov3D_python: transMat_precomp is unusable in the reference's `_part` fork "
+                                  "(DESIGN.md §8); pass scales / rotations")
+    shs, colors_precomp = (pc.get_features, None) if override_color is None else (None, override_color)
+    means3D = pc.get_xyz
+    try:
+        means3D.retain_grad()
+    except Exception:
+        pass
+    rendered_image, semantic, radii, allmap = rasterizer(
+        means3D=means3D, means2D=screenspace_points, shs=shs, colors_precomp=colors_precomp,
+        opacities=pc.get_opacity, semantics=pc.get_semantic, scales=pc.get_scaling, rotations=pc.get_rotation,
+        cov3D_precomp=None)
+    rets = {"render": rendered_image, "render_semantic": semantic, "viewspace_points": screenspace_points,
+            "visibility_filter": radii > 0, "radii": radii}
+    rets.update(surface_maps(allmap, viewpoint_camera, pipe.depth_ratio))
+    return rets

@@ -1,0 +1,99 @@
+"""GPU parity of the extraction epilogue kernel and the camera-sharded extraction loop (partgs_b200/extract.py)
+against the torch restatement (oracle/extract_oracle.py, pinned by golden vectors of the reference's own
+partmap_to_rgbmap) and against view-by-view calls of render_part.
+
+STATUS: written after this round's GPU budget was spent; compiles for sm_100a, CPU-side logic tested
+(tests/test_extract.py), not yet run on a B200 -> non-strict xfail, sorted after every verified GPU suite.  Remove
+the marker once green on hardware."""
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import extract_oracle
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
+              pytest.mark.xfail(strict=False, reason="extraction kernels not yet run on a B200 (round-1 GPU budget spent)")]
+DEV = "cuda"
+Z = np.load(Path(__file__).parent / "golden" / "extract_maps.npz")
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_part_colours_match_reference_golden(name):
+    from partgs_b200.extract import extract_maps
+    part = torch.from_numpy(Z[f"{name}_part"]).to(DEV)
+    pal = torch.from_numpy(Z[f"{name}_palette"]).to(DEV)
+    rgb, nrm = extract_maps(part, None, pal)
+    assert nrm is None
+    want = torch.from_numpy(Z[f"{name}_rgb"]).to(DEV)
+    # the background test compares a float sum with 0.1: pixels within 1e-6 of the threshold may fall either way
+    s = part.clamp(0, 1).sum(0)
+    decided = (s - 0.1).abs() > 1e-6
+    assert torch.equal(rgb[:, decided], want[:, decided])
+
+
+def test_epilogue_matches_oracle_on_a_large_image():
+    from partgs_b200.extract import extract_maps
+    g = torch.Generator().manual_seed(0)
+    S, H, W = 16, 1200, 1600
+    part = (torch.rand(S, H, W, generator=g) * 1.4 - 0.2).to(DEV)
+    part[:, :200] *= 0.005
+    part[3, 300, :] = float("nan")
+    nrm_in = torch.randn(3, H, W, generator=g).to(DEV)
+    nrm_in[:, 0, :5] = 0  # zero-length normals: divided by the 1e-12 floor
+    pal = torch.rand(S + 1, 4, generator=g).to(DEV)  # RGBA rows, stride 4
+    rgb, nrm = extract_maps(part, nrm_in, pal)
+    want = extract_oracle.partmap_to_rgbmap(part, pal)
+    s = part.clamp(0, 1).sum(0)
+    decided = ((s - 0.1).abs() > 1e-5) | s.isnan()
+    assert torch.equal(rgb[:, decided], want[:, decided])
+    assert float((nrm - extract_oracle.unit_normals(nrm_in)).abs().max()) <= 1e-6
+    assert not nrm[:, 0, :5].any()
+
+
+def _scene(P=20_000, S=6, views=5):
+    from partgs_b200 import synth
+    scene = synth.make_point_scene(P, seed=4, S=S, device=DEV)
+    cams = synth.make_cameras(views, 200, 152, seed=9, device=DEV)
+    pc = SimpleNamespace(get_xyz=scene["means3D"], get_opacity=scene["opacities"], get_scaling=scene["scales"],
+                         get_rotation=scene["rotations"], get_features=scene["shs"], get_semantic=scene["semantics"],
+                         active_sh_degree=3)
+    pipe = SimpleNamespace(depth_ratio=1.0, compute_cov3D_python=False, convert_SHs_python=False)
+    return pc, pipe, cams
+
+
+def test_render_part_mirror_returns_reference_keys():
+    from partgs_b200.renderer import render_part
+    pc, pipe, cams = _scene(views=1)
+    r = render_part(cams[0], pc, pipe, torch.zeros(3, device=DEV))
+    assert set(r) == {"render", "render_semantic", "viewspace_points", "visibility_filter", "radii", "rend_alpha",
+                      "rend_normal", "rend_dist", "surf_depth", "surf_normal"}
+    H, W = cams[0].image_height, cams[0].image_width
+    assert r["render_semantic"].shape == (6, H, W) and r["surf_normal"].shape == (3, H, W)
+    assert bool(torch.isfinite(r["surf_depth"]).all())
+
+
+def test_reconstruction_equals_view_by_view_rendering():
+    from partgs_b200.extract import GaussianExtractor, fancy_palette
+    from partgs_b200.renderer import render_part
+    pc, pipe, cams = _scene()
+    ex = GaussianExtractor(pc, render_part, pipe, bg_color=[1, 1, 1])
+    ex.reconstruction(cams)
+    V = len(cams)
+    assert ex.rgbmaps.shape == (V, 3, 152, 200) and ex.rgbmaps.is_pinned() and not ex.rgbmaps.is_cuda
+    pal = fancy_palette(7).to(DEV)
+    bg = torch.ones(3, device=DEV)
+    with torch.no_grad():
+        for i, cam in enumerate(cams):
+            r = render_part(cam, pc, pipe, bg)
+            assert torch.equal(ex.rgbmaps[i], r["render"].cpu())
+            assert torch.equal(ex.depthmaps[i], r["surf_depth"].cpu())
+            assert torch.equal(ex.alphamaps[i], r["rend_alpha"].cpu())
+            assert torch.equal(ex.depth_normals[i], r["surf_normal"].cpu())
+            want_n = extract_oracle.unit_normals(r["rend_normal"]).cpu()
+            assert float((ex.normals[i] - want_n).abs().max()) <= 1e-6
+            want_p = extract_oracle.partmap_to_rgbmap(r["render_semantic"], pal).cpu()
+            assert float((ex.partrgbs[i] != want_p).float().mean()) <= 1e-4
+    assert abs(ex.radius - 2.5) < 1e-3 and ex.center.shape == (3,)
