@@ -60,8 +60,8 @@ def test_emulated_adam_matches_torch(emu):
         for i, p in enumerate(ref_p):
             st = opt.state[p]
             np.testing.assert_allclose(ours_p[i], p.detach().numpy(), rtol=3e-6, atol=5e-7, err_msg=f"param {i} step {step}")
-            np.testing.assert_allclose(ours_m[i], st["exp_avg"].numpy(), rtol=3e-6, atol=1e-9)
-            np.testing.assert_allclose(ours_v[i], st["exp_avg_sq"].numpy(), rtol=3e-6, atol=1e-12)
+            np.testing.assert_allclose(ours_m[i], st["exp_avg"].numpy(), rtol=3e-6, atol=2e-6 * float(st["exp_avg"].abs().max()))
+            np.testing.assert_allclose(ours_v[i], st["exp_avg_sq"].numpy(), rtol=3e-6, atol=2e-6 * float(st["exp_avg_sq"].abs().max()))
     assert np.array_equal(ours_p[-1], ref_p[-1].detach().numpy())  # lr 0: untouched
 
 
