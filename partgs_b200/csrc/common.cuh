@@ -74,6 +74,7 @@ inline void carve(char*& p, T*& out, size_t count) {
   p = reinterpret_cast<char*>(out + count);
 }
 
+#ifndef PGS_EMU
 __device__ __forceinline__ unsigned lane_id() {
   unsigned r;
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(r));
@@ -96,5 +97,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
+#else
+// CPU lock-step emulator (tests/cuda_emu): the same helpers without PTX.  Test builds only — nvcc never defines
+// PGS_EMU.  cp.async completes immediately, so the emulator checks data flow, not the wait_group placement.
+inline unsigned lane_id() { return emu::t_lane; }
+inline float4 ldg4(const float4* p) { return *p; }
+inline void red_add_f32(float* addr, float v) { atomicAdd(addr, v); }
+inline void cp_async16(void* smem, const void* gmem) { memcpy(smem, gmem, 16); }
+inline void cp_async_commit() {}
+template <int N> inline void cp_async_wait() {}
+#endif
 
 }  // namespace pgs

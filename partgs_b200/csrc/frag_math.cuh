@@ -23,6 +23,7 @@
 namespace pgs {
 
 // MUFU approximations (~1 ulp) for the backward pass, where no decision depends on the values.
+#ifndef PGS_EMU
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -33,6 +34,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+#else  // CPU lock-step emulator (tests/cuda_emu): exact stand-ins for the MUFU approximations
+inline float rcp_approx(float x) { return 1.0f / x; }
+inline float ex2_approx(float x) { return exp2f(x); }
+#endif
 
 struct FragGeom {
   float3 k, l, p;

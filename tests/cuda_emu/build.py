@@ -15,6 +15,7 @@ CSRC = ROOT / "partgs_b200" / "csrc"
 OUT = HERE / "_build"
 CUDA_INC = "/usr/local/cuda/include"
 
+_DYN_SMEM = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w ]+?)\s+(\w+)\[\];")
 _LAUNCH = re.compile(r"(\w+(?:<[^<>;]*>)?)\s*<<<\s*(.*?)\s*>>>\s*\((.*?)\)\s*;", re.S)
 
 
@@ -37,8 +38,11 @@ def _split_args(s: str):
 def rewrite_launches(src: str) -> str:
     def sub(m):
         cfg = _split_args(m.group(2))
-        return f"EMU_LAUNCH({m.group(1)}, {cfg[0]}, {cfg[1]}, {m.group(3)});"
-    return _LAUNCH.sub(sub, src)
+        smem = cfg[2] if len(cfg) > 2 else "0"
+        return f"EMU_LAUNCH(({m.group(1)}), {cfg[0]}, {cfg[1]}, {smem}, {m.group(3)});"
+    src = _LAUNCH.sub(sub, src)
+    # extern __shared__ [__align__(n)] T name[];  ->  T* name = (T*)emu::g_dyn_smem;
+    return _DYN_SMEM.sub(lambda m: f"{m.group(1)}* {m.group(2)} = ({m.group(1)}*)emu::g_dyn_smem;", src)
 
 
 def build(cu_name: str, exports: str) -> Path:
@@ -56,9 +60,55 @@ def build(cu_name: str, exports: str) -> Path:
         return so
     cpp = OUT / f"{Path(cu_name).stem}_{tag}.cpp"
     cpp.write_text(tu)
-    cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-w", "-ffp-contract=off", f"-I{HERE}",
+    cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-Wl,-Bsymbolic", "-w", "-ffp-contract=off", f"-I{HERE}",
            f"-I{CSRC}", f"-I{CUDA_INC}", str(cpp), "-o", str(so)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("emulator build failed:\n" + res.stderr[-4000:])
+    return so
+
+
+def build_full() -> Path:
+    """The WHOLE product library (every partgs_b200/csrc/*.cu, including the C-ABI layer api.cu) for the emulator:
+    same exported `pgs_*` symbols as libpartgs_b200.so, host memory instead of device memory, synchronous streams."""
+    from concurrent.futures import ThreadPoolExecutor
+    srcs = sorted(CSRC.glob("*.cu"))
+    hdrs = sorted(list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [ROOT / "include" / "partgs_b200.h",
+                                                                      HERE / "emu.h", HERE / "emu_runtime.cpp"])
+    h = hashlib.sha1()
+    for f in srcs + hdrs:
+        h.update(f.read_bytes())
+    tag = h.hexdigest()[:16]
+    OUT.mkdir(exist_ok=True)
+    so = OUT / f"libpartgs_b200_emu_{tag}.so"
+    if so.exists():
+        return so
+    work = OUT / f"full_{tag}"
+    work.mkdir(exist_ok=True)
+    flags = ["-std=c++17", "-O1", "-fPIC", "-pthread", "-w", "-ffp-contract=off", "-DPGS_EMU", f"-I{HERE}", f"-I{CSRC}",
+             f"-I{CUDA_INC}", "-include", "emu.h"]
+
+    def compile_one(src: Path) -> Path:
+        body = rewrite_launches(src.read_text())
+        assert "<<<" not in body, f"unconverted kernel launch in {src.name}"
+        body = body.replace('"../../include/partgs_b200.h"', f'"{ROOT / "include" / "partgs_b200.h"}"')
+        cpp = work / (src.stem + ".cpp")
+        cpp.write_text(body)
+        obj = work / (src.stem + ".o")
+        res = subprocess.run(["g++", *flags, "-c", str(cpp), "-o", str(obj)], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"emulator build of {src.name} failed:\n" + res.stderr[-3000:])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    rt = work / "emu_runtime.o"
+    res = subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-w", f"-I{CUDA_INC}", "-c", str(HERE / "emu_runtime.cpp"),
+                          "-o", str(rt)], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("emulator runtime build failed:\n" + res.stderr[-3000:])
+    res = subprocess.run(["g++", "-shared", "-pthread", "-Wl,-Bsymbolic", "-o", str(so), *map(str, objs), str(rt)], capture_output=True,
+                         text=True)
+    if res.returncode != 0:
+        raise RuntimeError("emulator link failed:\n" + res.stderr[-3000:])
     return so

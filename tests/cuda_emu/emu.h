@@ -4,8 +4,10 @@
 // `kernel<<<grid, block, smem, stream>>>(args)` launch statements into EMU_LAUNCH).  Every CUDA thread of a block is
 // an OS thread; blocks run one after the other; __syncthreads is a block barrier, warp collectives (__ballot_sync,
 // __shfl_*_sync) rendezvous the 32 lanes of a warp.  `__shared__` becomes `static` (one instance per kernel, which
-// is what a block sees because blocks are sequential).  Supported: 1-D grids / blocks that are multiples of 32,
-// static shared memory, atomicAdd, the arithmetic intrinsics below.  NOT a performance model and not bit-exact for
+// is what a block sees because blocks are sequential).  Supported: 1-D to 3-D grids / blocks (warps are 32 consecutive
+// linear thread ids), static and dynamic shared memory, the atomics / intrinsics below, cp.async as an immediate copy
+// (the product headers select their non-PTX helper bodies under PGS_EMU), and — for whole-library builds — a stub CUDA
+// runtime (emu_runtime.cpp: memcpy/memset, no-op events and streams).  NOT a performance model and not bit-exact for
 // transcendental functions (glibc expf/logf vs the GPU's) — it checks indexing, scans, barriers and data movement.
 #pragma once
 #include <cuda_runtime.h>  // vector types, dim3, cudaStream_t (host-compilable header of the toolkit)
@@ -47,6 +49,7 @@ struct WarpState {
 inline Barrier g_block_bar;
 inline std::vector<WarpState>* g_warps = nullptr;
 inline thread_local WarpState* t_warp = nullptr;
+inline unsigned char* g_dyn_smem = nullptr;  // dynamic shared memory of the running block
 inline thread_local unsigned t_lane = 0;
 }  // namespace emu
 
@@ -97,6 +100,24 @@ template <typename T> inline T __shfl_xor_sync(unsigned, T v, int mask) {
   memcpy(&r, &all[(emu::t_lane ^ mask) & 31], 4);
   return r;
 }
+template <typename T> inline unsigned __match_any_sync(unsigned, T v) {
+  static_assert(sizeof(T) == 4, "4-byte values only");
+  unsigned all[32], u;
+  memcpy(&u, &v, 4);
+  emu_exchange(u, all);
+  unsigned m = 0;
+  for (int i = 0; i < 32; i++) m |= (unsigned)(all[i] == u) << i;
+  return m;
+}
+template <typename T> inline T __shfl_down_sync(unsigned, T v, unsigned delta) {
+  unsigned all[32], u;
+  memcpy(&u, &v, 4);
+  emu_exchange(u, all);
+  const unsigned src = emu::t_lane + delta;
+  T r;
+  memcpy(&r, &all[src > 31 ? emu::t_lane : src], 4);
+  return r;
+}
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __ffs(int x) { return __builtin_ffs(x); }
 inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
@@ -105,10 +126,39 @@ inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
+inline float __double2float_rd(double d) {  // round towards -inf
+  float f = (float)d;
+  return ((double)f > d) ? nextafterf(f, -INFINITY) : f;
+}
+inline float __double2float_ru(double d) {  // round towards +inf
+  float f = (float)d;
+  return ((double)f < d) ? nextafterf(f, INFINITY) : f;
+}
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+inline float saturate(float x) { return fminf(fmaxf(x, 0.f), 1.f); }
+using std::isfinite;
+using std::isnan;
 template <typename T> inline T __ldg(const T* p) { return *p; }
 inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }  // only so that unused helpers parse
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicExch(unsigned* p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicExch(unsigned long long* p, unsigned long long v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicMin(int* p, int v) { int o = *p; while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
+inline int atomicMax(int* p, int v) { int o = *p; while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
+inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
+inline double atomicAdd(double* p, double v) {
+  double old = *p, want;
+  do { want = old + v; } while (!__atomic_compare_exchange(p, &old, &want, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+  return old;
+}
 inline float atomicAdd(float* p, float v) {
   float old = *p, want;
   do { want = old + v; } while (!__atomic_compare_exchange(p, &old, &want, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
@@ -116,30 +166,49 @@ inline float atomicAdd(float* p, float v) {
 }
 using std::max;
 using std::min;
+// CUDA's mixed-type overloads (the int operand is converted like the hardware min/max do)
+inline unsigned min(unsigned a, int b) { return a < (unsigned)b ? a : (unsigned)b; }
+inline unsigned min(int a, unsigned b) { return (unsigned)a < b ? (unsigned)a : b; }
+inline unsigned max(unsigned a, int b) { return a > (unsigned)b ? a : (unsigned)b; }
+inline unsigned max(int a, unsigned b) { return (unsigned)a > b ? (unsigned)a : b; }
+inline float max(float a, float b) { return fmaxf(a, b); }
+inline float min(float a, float b) { return fminf(a, b); }
+inline double max(float a, double b) { return fmax((double)a, b); }
+inline double max(double a, float b) { return fmax(a, (double)b); }
+inline double min(float a, double b) { return fmin((double)a, b); }
+inline double min(double a, float b) { return fmin(a, (double)b); }
 
 #define cudaMemsetAsync(p, v, n, s) (memset((p), (v), (n)), cudaSuccess)
+template <class T> inline cudaError_t cudaFuncSetAttribute(T*, cudaFuncAttribute, int) { return cudaSuccess; }
 
-// Run `body` for every thread of a 1-D grid of 1-D blocks.
-inline void emu_run(unsigned grid, unsigned block, const std::function<void()>& body) {
-  if (block % 32 != 0 || block == 0) throw std::runtime_error("emu: block size must be a multiple of 32");
-  blockDim = dim3(block, 1, 1);
-  gridDim = dim3(grid, 1, 1);
-  std::vector<emu::WarpState> warps(block / 32);
+// Run `body` for every thread of the grid; blocks one after the other in x-fastest order.
+inline void emu_run(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+  const unsigned nthreads = block.x * block.y * block.z;
+  if (nthreads % 32 != 0 || nthreads == 0) throw std::runtime_error("emu: block size must be a multiple of 32");
+  blockDim = block;
+  gridDim = grid;
+  std::vector<emu::WarpState> warps(nthreads / 32);
   for (auto& w : warps) w.bar.reset(32);
-  for (unsigned b = 0; b < grid; b++) {
-    emu::g_block_bar.reset((int)block);
-    std::vector<std::thread> ts;
-    ts.reserve(block);
-    for (unsigned t = 0; t < block; t++) {
-      ts.emplace_back([&, t, b] {
-        threadIdx = {t, 0, 0};
-        blockIdx = {b, 0, 0};
-        emu::t_warp = &warps[t / 32];
-        emu::t_lane = t % 32;
-        body();
-      });
-    }
-    for (auto& th : ts) th.join();
-  }
+  std::vector<unsigned char> dyn(smem + 64);
+  emu::g_dyn_smem = (unsigned char*)(((size_t)dyn.data() + 63) & ~(size_t)63);
+  for (unsigned bz = 0; bz < grid.z; bz++)
+    for (unsigned by = 0; by < grid.y; by++)
+      for (unsigned bx = 0; bx < grid.x; bx++) {
+        emu::g_block_bar.reset((int)nthreads);
+        std::vector<std::thread> ts;
+        ts.reserve(nthreads);
+        for (unsigned t = 0; t < nthreads; t++) {
+          ts.emplace_back([&, t, bx, by, bz] {
+            threadIdx = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+            blockIdx = {bx, by, bz};
+            emu::t_warp = &warps[t / 32];
+            emu::t_lane = t % 32;
+            body();
+          });
+        }
+        for (auto& th : ts) th.join();
+      }
+  emu::g_dyn_smem = nullptr;
 }
-#define EMU_LAUNCH(kernel, grid, block, ...) emu_run((unsigned)(grid), (unsigned)(block), [&] { kernel(__VA_ARGS__); })
+#define EMU_LAUNCH(kernel, grid, block, smem, ...) \
+  emu_run(dim3(grid), dim3(block), (size_t)(smem), [&] { kernel(__VA_ARGS__); })
