@@ -1,0 +1,126 @@
+"""GPU-less functional tests of the remaining kernels through the real C ABI of the emulator build of the whole
+library (tests/cuda_emu): distCUDA2 vs float64 brute force, the surface-map kernels vs oracle/post_oracle.py, the
+photometric loss vs oracle/loss_oracle.py (values and gradients), mark_visible.  Hardware parity lives in
+tests/test_gpu_*.py; here the same source runs on the CPU."""
+import ctypes as C
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, str(Path(__file__).parent / "cuda_emu"))
+import build as emu_build  # noqa: E402
+
+from partgs_b200 import _lib, synth  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emu():
+    lib = C.CDLL(str(emu_build.build_full()))
+    for name, (res, args) in _lib.SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def f32(t):
+    return np.ascontiguousarray(t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else t, dtype=np.float32)
+
+
+@pytest.mark.parametrize("P", [1, 3, 4, 700])
+def test_emulated_dist2_matches_brute_force(emu, P):
+    g = np.random.default_rng(P)
+    pts = np.concatenate([g.normal(size=(P - P // 3, 3)), g.normal(size=(P // 3, 3)) * 0.01 + 2.0]).astype(np.float32)
+    out = np.full(P, np.nan, np.float32)
+    temp = np.zeros(emu.pgs_knn_temp_bytes(P) + 256, np.uint8)
+    rc = emu.pgs_knn_dist2(P, _p(pts), _p(out), (temp.ctypes.data + 255) // 256 * 256, None)
+    assert rc >= 0, emu.pgs_last_error()
+    d = ((pts[:, None, :].astype(np.float64) - pts[None, :, :]) ** 2).sum(-1)
+    np.fill_diagonal(d, np.inf)
+    if P < 4:
+        # fewer than three neighbours: the reference's FLT_MAX placeholders stay in the sum (simple_knn.cu:131-183)
+        assert (out > 1e37).all()
+        return
+    want = np.sort(d, axis=1)[:, :3].sum(1) / 3
+    np.testing.assert_allclose(out, want, rtol=2e-5, atol=1e-12)
+
+
+def test_emulated_surface_maps_match_the_oracle(emu):
+    from oracle import post_oracle
+    from partgs_b200.renderer import _camera_constants
+    W, H = 37, 23
+    cam = synth.make_cameras(1, W, H, seed=3, device="cpu")[0]
+    gen = torch.Generator().manual_seed(0)
+    allmap = torch.rand(7, H, W, generator=gen)
+    allmap[0] = allmap[0] * 2 + 1.5          # depth * alpha
+    allmap[5] = allmap[5] * 2 + 1.5
+    allmap[1, :3] = 0                        # alpha 0 rows: depth/alpha -> nan_to_num
+    allmap.requires_grad_(True)
+    ref = post_oracle.surface_maps(allmap, cam, 0.3)
+    g = {k: torch.randn(ref[k].shape, generator=gen) for k in ("rend_normal", "surf_depth", "surf_normal")}
+    (sum((ref[k] * g[k]).sum() for k in g)).backward()
+    A, M1, M2, o = (f32(t) for t in _camera_constants(cam))
+    am = f32(allmap)
+    rn, sd, sn = (np.full(s, np.nan, np.float32) for s in ((3, H, W), (1, H, W), (3, H, W)))
+    assert emu.pgs_surface_maps_forward(W, H, _p(am), _p(A), _p(M1), _p(M2), _p(o), 0.3, _p(rn), _p(sd), _p(sn), None) >= 0
+    for got, k in ((rn, "rend_normal"), (sd, "surf_depth"), (sn, "surf_normal")):
+        want = ref[k].detach().numpy()
+        assert float(np.abs(got - want).max()) <= 2e-4 * (float(np.abs(want).max()) + 1e-6), k
+    scratch = np.zeros(emu.pgs_surface_maps_backward_scratch_bytes(W, H) + 256, np.uint8)
+    g_all = np.full((7, H, W), np.nan, np.float32)
+    rc = emu.pgs_surface_maps_backward(W, H, _p(am), _p(A), _p(M1), _p(M2), _p(o), 0.3, _p(f32(g["rend_normal"])),
+                                       _p(f32(g["surf_depth"])), _p(f32(g["surf_normal"])),
+                                       (scratch.ctypes.data + 255) // 256 * 256, _p(g_all), None)
+    assert rc >= 0, emu.pgs_last_error()
+    want = allmap.grad.numpy().copy()
+    # rend_alpha / rend_dist are plain slices handled by autograd in the product; the kernel covers the derived maps
+    # where alpha == 0 the reference's autograd yields NaN (0/0 through nan_to_num); the kernel writes finite values
+    assert np.isfinite(g_all).all()
+    for ch in (0, 2, 3, 4, 5):
+        ok = np.isfinite(want[ch])
+        assert ok.mean() > 0.8
+        scale = float(np.abs(want[ch][ok]).max()) + 1e-9
+        assert float(np.quantile(np.abs(g_all[ch] - want[ch])[ok], 0.99)) <= 2e-3 * scale, ch
+
+
+@pytest.mark.parametrize("shape", [(3, 40, 52), (1, 16, 16), (3, 19, 33)])
+def test_emulated_photometric_loss_matches_the_oracle(emu, shape):
+    from oracle import loss_oracle
+    Cc, H, W = shape
+    gen = torch.Generator().manual_seed(7)
+    img = torch.rand(shape, generator=gen, requires_grad=True)
+    gt = torch.rand(shape, generator=gen)
+    lam = 0.2
+    ref = loss_oracle.photometric_loss(img, gt, lam)
+    ref.backward()
+    im, g_ = f32(img), f32(gt)
+    sums = np.zeros(2, np.float64)
+    dmaps = np.full((3,) + shape, np.nan, np.float32)
+    assert emu.pgs_photometric_forward(Cc, H, W, _p(im), _p(g_), _p(sums), _p(dmaps), None) >= 0
+    n = float(Cc * H * W)
+    loss = (1 - lam) * sums[1] / n + lam * (1 - sums[0] / n)
+    assert abs(loss - float(ref)) <= 2e-6 * abs(float(ref))
+    g_loss = np.ones(1, np.float32)
+    g_img = np.full(shape, np.nan, np.float32)
+    assert emu.pgs_photometric_backward(Cc, H, W, _p(im), _p(g_), _p(dmaps), _p(g_loss), lam, _p(g_img), None) >= 0
+    want = img.grad.numpy()
+    assert float(np.abs(g_img - want).max()) <= 5e-5 * float(np.abs(want).max())
+
+
+def test_emulated_mark_visible(emu):
+    scene = synth.make_point_scene(500, seed=3, device="cpu")
+    cam = synth.make_cameras(1, 64, 48, seed=4, device="cpu")[0]
+    pts = f32(scene["means3D"])
+    pts[::7] *= 40.0                                   # some far outside / behind
+    present = np.full(500, 7, np.uint8)
+    assert emu.pgs_mark_visible(500, _p(pts), _p(f32(cam.viewmatrix)), _p(f32(cam.projmatrix)), _p(present), None) >= 0
+    ph = np.concatenate([pts, np.ones((500, 1), np.float32)], 1) @ f32(cam.viewmatrix)
+    want = ph[:, 2] > 0.2                              # in_frustum: p_view.z <= 0.2 culls (auxiliary.h:185-211)
+    assert np.array_equal(present.astype(bool), want)
+    assert want.any() and (~want).any()
