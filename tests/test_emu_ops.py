@@ -124,3 +124,50 @@ def test_emulated_mark_visible(emu):
     want = ph[:, 2] > 0.2                              # in_frustum: p_view.z <= 0.2 culls (auxiliary.h:185-211)
     assert np.array_equal(present.astype(bool), want)
     assert want.any() and (~want).any()
+
+
+GOLD_SQ = sorted((Path(__file__).resolve().parent / "golden").glob("sq2surfel_*.npz"))
+
+
+@pytest.mark.parametrize("path", GOLD_SQ, ids=lambda p: p.stem)
+def test_emulated_sq2surfel_matches_reference_golden(emu, path):
+    """Superquadric -> surfel kernels (forward and backward) against golden vectors of the reference Python."""
+    z = dict(np.load(path))
+    B, Vt = z["eta"].shape
+    F = z["faces"].shape[1]
+    K = z["alpha"].shape[1]
+    P = B * F * K
+    c = lambda k: np.ascontiguousarray(z[k], dtype=np.float32)
+    faces = np.ascontiguousarray(z["faces"], dtype=np.int32)
+    ins = [c("sq_r"), c("sq_s"), c("sq_t"), c("sq_eps"), c("sq_occ"), c("eta"), c("omega")]
+    alpha, scale_raw = c("alpha"), c("scale_raw")
+    out = dict(vertices=np.full((B, Vt, 3), np.nan, np.float32), xyz=np.full((P, 3), np.nan, np.float32),
+               scaling=np.full((P, 2), np.nan, np.float32), rotation=np.full((P, 4), np.nan, np.float32),
+               opacity=np.full((P,), np.nan, np.float32))
+    rc = emu.pgs_sq2surfel_forward(B, Vt, F, K, *[_p(a) for a in ins], _p(faces), _p(alpha), _p(scale_raw), 0.25, 0.2,
+                                   _p(out["vertices"]), _p(out["xyz"]), _p(out["scaling"]), _p(out["rotation"]),
+                                   _p(out["opacity"]), None)
+    assert rc >= 0, emu.pgs_last_error()
+
+    def close(a, b, tol, name):
+        err = float(np.abs(a - b.reshape(a.shape)).max()) / (float(np.abs(b).max()) + 1e-30)
+        assert err <= tol, (name, err)
+    close(out["vertices"], z["vertices"], 2e-6, "vertices")
+    close(out["xyz"], z["xyz"], 2e-6, "xyz")
+    close(out["scaling"], z["scaling_log"], 1e-5, "scaling")
+    close(out["rotation"], z["rotation_raw"], 2e-5, "rotation")
+    close(out["opacity"], z["opacity"], 1e-6, "opacity")
+    g = {k: np.full(z[k].shape, np.nan, np.float32) for k in ("sq_r", "sq_s", "sq_t", "sq_eps", "sq_occ")}
+    d_alpha = np.full(alpha.shape, np.nan, np.float32)
+    d_scale = np.full(scale_raw.shape, np.nan, np.float32)
+    scratch = np.zeros(emu.pgs_sq2surfel_backward_scratch_bytes(B, Vt) + 256, np.uint8)
+    rc = emu.pgs_sq2surfel_backward(B, Vt, F, K, *[_p(a) for a in ins], _p(faces), _p(alpha), _p(scale_raw), 0.25, 0.2,
+                                    _p(out["vertices"]), _p(c("g_xyz")), _p(c("g_scaling")), _p(c("g_rotation")),
+                                    _p(c("g_opacity")), _p(c("g_vertices")), _p(g["sq_r"]), _p(g["sq_s"]),
+                                    _p(g["sq_t"]), _p(g["sq_eps"]), _p(g["sq_occ"]), _p(d_alpha), _p(d_scale),
+                                    (scratch.ctypes.data + 255) // 256 * 256, None)
+    assert rc >= 0, emu.pgs_last_error()
+    for k in g:
+        close(g[k], z["d_" + k], 1e-4, "d_" + k)
+    close(d_alpha, z["d_alpha"], 1e-4, "d_alpha")
+    close(d_scale, z["d_scale_raw"], 1e-4, "d_scale_raw")
