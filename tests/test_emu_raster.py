@@ -50,18 +50,20 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def run_emulated(emu, scene, cam, g_color, g_allmap):
+def run_emulated(emu, scene, cam, g_color, g_allmap, degree=3, colors_precomp=None):
     f32 = lambda t: np.ascontiguousarray(t.detach().cpu().numpy(), dtype=np.float32)
     m3, sc, rot, op, sh = (f32(scene[k]) for k in ("means3D", "scales", "rotations", "opacities", "shs"))
     vm, pm, cp = f32(cam.viewmatrix), f32(cam.projmatrix), f32(cam.campos)
     bg = np.zeros(3, np.float32)
     P, M = m3.shape[0], sh.shape[1]
+    cpre = None if colors_precomp is None else f32(colors_precomp)
+    sh_arg = None if cpre is not None else sh
     W, H = cam.image_width, cam.image_height
     color = np.full((3, H, W), np.nan, np.float32)
     allmap = np.full((7, H, W), np.nan, np.float32)
     radii = np.full(P, -7, np.int32)
     al = HostAlloc()
-    R = emu.pgs_dsr_forward(al.cb, 1, al.cb, 2, al.cb, 3, P, 3, M, _p(bg), W, H, _p(m3), _p(sh), None, _p(op), _p(sc),
+    R = emu.pgs_dsr_forward(al.cb, 1, al.cb, 2, al.cb, 3, P, degree, M, _p(bg), W, H, _p(m3), _p(sh_arg), _p(cpre), _p(op), _p(sc),
                             1.0, _p(rot), None, _p(vm), _p(pm), _p(cp), cam.tanfovx, cam.tanfovy, 0, _p(color),
                             _p(allmap), _p(radii), 1, None)
     assert R >= 0, emu.pgs_last_error()
@@ -78,7 +80,7 @@ def run_emulated(emu, scene, cam, g_color, g_allmap):
              scales=np.full((P, 2), np.nan, np.float32), rotations=np.full((P, 4), np.nan, np.float32))
     scratch = np.zeros(emu.pgs_dsr_backward_scratch_bytes(P) + 256, np.uint8)
     gc, ga = f32(g_color), f32(g_allmap)
-    rc = emu.pgs_dsr_backward(P, 3, M, R, _p(bg), W, H, _p(m3), _p(sh), None, _p(sc), 1.0, _p(rot), None, _p(vm),
+    rc = emu.pgs_dsr_backward(P, degree, M, R, _p(bg), W, H, _p(m3), _p(sh_arg), _p(cpre), _p(sc), 1.0, _p(rot), None, _p(vm),
                               _p(pm), _p(cp), cam.tanfovx, cam.tanfovy, _p(radii), al.ptr(1), al.ptr(2), al.nbytes(2),
                               al.ptr(3), _p(gc), _p(ga), _p(g["means2D"]), (scratch.ctypes.data + 255) // 256 * 256,
                               _p(g["opacity"]), _p(g["colors"]), _p(g["means3D"]), _p(g["transMat"]), _p(g["sh"]),
@@ -116,3 +118,62 @@ def test_emulated_forward_backward_match_the_c_oracle(emu, P, W, H, seed):
         assert rel(ours["grads"][k], gr[k]) <= 2e-4, k
     assert rel(ours["grads"]["means2D"][:, :2], gr["means2D"][:, :2]) <= 2e-4
     assert np.isfinite(ours["grads"]["means3D"]).all()
+
+
+@pytest.mark.parametrize("degree", [0, 1, 2])
+def test_emulated_lower_sh_degrees(emu, degree):
+    scene = synth.make_point_scene(250, seed=21, device="cpu")
+    scene["scales"] = scene["scales"] * 3.0
+    cam = synth.make_cameras(1, 32, 32, seed=22, device="cpu")[0]
+    g = synth.upstream_grads(32, 32, 6, device="cpu")
+    ours = run_emulated(emu, scene, cam, g["color"], g["allmap"], degree=degree)
+    f = cpu_oracle.forward_scene(scene, cam, keep_state=True, sh_degree=degree)
+    gr = cpu_oracle.backward(f, g["color"], g["allmap"])
+    assert ours["R"] == f["num_rendered"] and ours["R"] > 30
+    assert rel(ours["color"], f["color"]) <= 2e-5
+    assert rel(ours["grads"]["sh"], gr["sh"]) <= 2e-4
+    n_active = (degree + 1) ** 2
+    assert not ours["grads"]["sh"][:, n_active:].any()      # coefficients above the active degree get zero gradient
+    assert rel(ours["grads"]["means3D"], gr["means3D"]) <= 2e-4
+
+
+def test_emulated_precomputed_colours(emu):
+    scene = synth.make_point_scene(250, seed=31, device="cpu")
+    scene["scales"] = scene["scales"] * 3.0
+    cam = synth.make_cameras(1, 32, 32, seed=32, device="cpu")[0]
+    g = synth.upstream_grads(32, 32, 7, device="cpu")
+    colors = torch.rand(250, 3, generator=torch.Generator().manual_seed(1))
+    ours = run_emulated(emu, scene, cam, g["color"], g["allmap"], colors_precomp=colors)
+    # exactly one of SHs / precomputed colours, as the reference API enforces
+    f = cpu_oracle.forward(scene["means3D"], scene["scales"], scene["rotations"], scene["opacities"], None,
+                           cam.viewmatrix, cam.projmatrix, cam.campos, 32, 32, cam.tanfovx, cam.tanfovy,
+                           colors_precomp=colors, keep_state=True)
+    gr = cpu_oracle.backward(f, g["color"], g["allmap"])
+    assert ours["R"] == f["num_rendered"] and ours["R"] > 30
+    assert rel(ours["color"], f["color"]) <= 2e-5 and rel(ours["allmap"], f["allmap"]) <= 2e-5
+    assert rel(ours["grads"]["colors"], gr["colors"]) <= 2e-4
+    assert rel(ours["grads"]["means3D"], gr["means3D"]) <= 2e-4
+
+
+def test_emulated_nothing_visible_and_tiny_image(emu):
+    scene = synth.make_point_scene(100, seed=41, device="cpu")
+    g = synth.upstream_grads(5, 3, 8, device="cpu")
+    cam = synth.make_cameras(1, 5, 3, seed=42, device="cpu")[0]
+    # everything behind the camera: no instance, background image, zero gradients
+    far = dict(scene)
+    far["means3D"] = scene["means3D"] + cam.campos * 3.0
+    ours = run_emulated(emu, far, cam, g["color"], g["allmap"])
+    assert ours["R"] == 0 and not ours["radii"].any()
+    assert not ours["color"].any() and not ours["allmap"].any()
+    for k in ("means3D", "opacity", "scales", "rotations", "sh"):
+        assert not ours["grads"][k].any(), k
+    # a 5x3 image (one ragged tile) with splats covering it
+    scene["scales"] = scene["scales"] * 30.0
+    ours = run_emulated(emu, scene, cam, g["color"], g["allmap"])
+    f = cpu_oracle.forward_scene(scene, cam, keep_state=True)
+    gr = cpu_oracle.backward(f, g["color"], g["allmap"])
+    assert ours["R"] == f["num_rendered"]
+    assert np.array_equal(ours["radii"], f["radii"])
+    if ours["R"]:
+        assert rel(ours["color"], f["color"]) <= 2e-5
+        assert rel(ours["grads"]["means3D"], gr["means3D"]) <= 2e-4
