@@ -50,6 +50,7 @@ def _split_args(s: str):
 
 
 def rewrite_launches(src: str) -> str:
+    src = src.replace("<< <", "<<<").replace(">> >", ">>>")   # the reference spells its launches with spaces
     def sub(m):
         cfg = _split_args(m.group(2))
         smem = cfg[2] if len(cfg) > 2 else "0"
@@ -127,4 +128,55 @@ def build_full() -> Path:
                          text=True)
     if res.returncode != 0:
         raise RuntimeError("emulator link failed:\n" + res.stderr[-3000:])
+    return so
+
+
+def build_reference(fork: str = "part") -> Path:
+    """The UNMODIFIED reference rasteriser (cuda_rasterizer/{forward,backward,rasterizer_impl}.cu of the chosen fork,
+    read from /root/reference where they lie) compiled for the emulator, with host stand-ins for CUB, cooperative
+    groups (ref_shim/) and GLM (oracle/glm_shim), plus ref_wrap_<fork>.cpp: extern "C" entry points over
+    CudaRasterizer::Rasterizer::forward / backward.  Build container only; used by tools/make_golden_ref_emu.py."""
+    from concurrent.futures import ThreadPoolExecutor
+    _require_toolchain()
+    sub = {"part": "diff-surfel-rasterization_part", "base": "diff-surfel-rasterization"}[fork]
+    ref = Path("/root/reference/submodules") / sub / "cuda_rasterizer"
+    if not ref.is_dir():
+        raise EmuUnavailable(f"{ref} not found (reference tree not mounted)")
+    srcs = [ref / n for n in ("forward.cu", "backward.cu", "rasterizer_impl.cu")]
+    wrap = HERE / f"ref_wrap_{fork}.cpp"
+    h = hashlib.sha1()
+    for f in srcs + sorted(ref.glob("*.h")) + [wrap, HERE / "emu.h", HERE / "emu_runtime.cpp"] + \
+            sorted((HERE / "ref_shim").rglob("*.*")):
+        h.update(f.read_bytes())
+    tag = h.hexdigest()[:16]
+    OUT.mkdir(exist_ok=True)
+    so = OUT / f"libref_{fork}_emu_{tag}.so"
+    if so.exists():
+        return so
+    work = OUT / f"ref_{fork}_{tag}"
+    work.mkdir(exist_ok=True)
+    flags = ["-std=c++17", "-O1", "-fPIC", "-pthread", "-w", "-ffp-contract=off", f"-I{HERE}", f"-I{HERE / 'ref_shim'}",
+             f"-I{ROOT / 'oracle' / 'glm_shim'}", f"-I{ref}", f"-I{CUDA_INC}", "-include", "emu.h", "-include", "cstdint",
+             "-include", "cfloat"]
+
+    def compile_one(src: Path) -> Path:
+        body = rewrite_launches(src.read_text()) if src.suffix == ".cu" else src.read_text()
+        assert "<<<" not in body, f"unconverted kernel launch in {src.name}"
+        cpp = work / (src.stem + ".cpp")
+        cpp.write_text(body)
+        obj = work / (src.stem + ".o")
+        res = subprocess.run(["g++", *flags, "-c", str(cpp), "-o", str(obj)], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"emulator build of reference {src.name} failed:\n" + res.stderr[-3000:])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        objs = list(ex.map(compile_one, srcs + [wrap]))
+    rt = work / "emu_runtime.o"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-w", f"-I{CUDA_INC}", "-c", str(HERE / "emu_runtime.cpp"), "-o",
+                    str(rt)], check=True)
+    res = subprocess.run(["g++", "-shared", "-pthread", "-Wl,-Bsymbolic", "-o", str(so), *map(str, objs), str(rt)],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("emulator link of the reference failed:\n" + res.stderr[-3000:])
     return so

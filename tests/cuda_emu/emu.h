@@ -58,6 +58,16 @@ inline dim3 blockDim, gridDim;
 
 inline void __syncthreads() { emu::g_block_bar.wait(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::t_warp->bar.wait(); }
+namespace emu { inline std::atomic<int> g_block_count{0}; }
+inline int __syncthreads_count(int pred) {
+  if (pred) emu::g_block_count.fetch_add(1);
+  emu::g_block_bar.wait();
+  const int n = emu::g_block_count.load();
+  emu::g_block_bar.wait();
+  if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) emu::g_block_count.store(0);
+  emu::g_block_bar.wait();
+  return n;
+}
 
 inline unsigned emu_exchange(unsigned v, unsigned (&out)[32]) {
   emu::WarpState& w = *emu::t_warp;
@@ -118,6 +128,7 @@ template <typename T> inline T __shfl_down_sync(unsigned, T v, unsigned delta) {
   memcpy(&r, &all[src > 31 ? emu::t_lane : src], 4);
   return r;
 }
+inline void __trap() { abort(); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __ffs(int x) { return __builtin_ffs(x); }
 inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }

@@ -18,6 +18,11 @@ cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) {
   memset(p, v, n);
   return cudaSuccess;
 }
+cudaError_t cudaMemset(void* p, int v, size_t n) {
+  memset(p, v, n);
+  return cudaSuccess;
+}
+cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
 cudaError_t cudaMalloc(void** p, size_t n) {
   *p = malloc(n ? n : 1);
   return *p ? cudaSuccess : cudaErrorMemoryAllocation;
