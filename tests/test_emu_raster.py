@@ -53,11 +53,11 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def run_emulated(emu, scene, cam, g_color, g_allmap, degree=3, colors_precomp=None):
+def run_emulated(emu, scene, cam, g_color, g_allmap, degree=3, colors_precomp=None, bg=None):
     f32 = lambda t: np.ascontiguousarray(t.detach().cpu().numpy(), dtype=np.float32)
     m3, sc, rot, op, sh = (f32(scene[k]) for k in ("means3D", "scales", "rotations", "opacities", "shs"))
     vm, pm, cp = f32(cam.viewmatrix), f32(cam.projmatrix), f32(cam.campos)
-    bg = np.zeros(3, np.float32)
+    bg = np.zeros(3, np.float32) if bg is None else np.ascontiguousarray(bg, dtype=np.float32)
     P, M = m3.shape[0], sh.shape[1]
     cpre = None if colors_precomp is None else f32(colors_precomp)
     sh_arg = None if cpre is not None else sh
