@@ -178,6 +178,23 @@ int pgs_photometric_backward(int channels, int height, int width, const float* i
                              const float* dmaps, const float* g_loss, float lambda_dssim, float* g_image,
                              void* stream);
 
+/* ---- per-pixel regularisers of the training step -------------------------------------------------
+ * SURVEY.md section 8(f) rank 2 (second half).  train.py:234-251 on the maps render() returns:
+ *   mask entropy   -(mask * log(a) + (1 - mask) * log(1 - a)).mean(),  a = rend_alpha.clamp(1e-6, 1 - 1e-6)
+ *   normal error   (1 - (rend_normal * surf_normal).sum(0)).mean()
+ *   distortion     rend_dist.mean()
+ * Forward leaves the three SUMS in `sums` (3 doubles, device; the caller divides by width*height and applies the
+ * lambdas); a NULL mask / NULL normals / NULL dist skips that term.  Backward reads the upstream gradient of the
+ * weighted scalar from DEVICE memory (g_loss, 1 float) and writes d/d rend_alpha [H,W], d/d rend_dist [H,W],
+ * d/d rend_normal [3,H,W], d/d surf_normal [3,H,W] (any output may be NULL). */
+int pgs_regularizers_forward(int width, int height, const float* rend_alpha, const float* gt_mask,
+                             const float* rend_dist, const float* rend_normal, const float* surf_normal, double* sums,
+                             void* stream);
+int pgs_regularizers_backward(int width, int height, const float* rend_alpha, const float* gt_mask,
+                              const float* rend_normal, const float* surf_normal, const float* g_loss,
+                              float lambda_mask_entropy, float lambda_normal, float lambda_dist, float* g_rend_alpha,
+                              float* g_rend_dist, float* g_rend_normal, float* g_surf_normal, void* stream);
+
 /* ---- optimiser step / densification statistics ---------------------------------------------
  * SURVEY.md section 8(f) rank 3 (partial).  pgs_adam_step: torch.optim.Adam's update (no amsgrad / weight decay;
  * scene/gaussian_model.py:266 uses eps = 1e-15) for up to 16 tensors in ONE launch.  The tables are HOST arrays of

@@ -39,3 +39,19 @@ def l1_loss(network_output, gt):  # :6-7
 
 def photometric_loss(image, gt, lambda_dssim):  # train.py:230-231
     return (1.0 - lambda_dssim) * l1_loss(image, gt) + lambda_dssim * (1.0 - ssim(image, gt))
+
+
+def geometric_regularizers(rend_alpha, gt_mask, rend_dist, rend_normal, surf_normal, lambda_mask_entropy,
+                           lambda_normal, lambda_dist):  # train.py:234-251 (the terms after the photometric loss)
+    """-> (lambda_me * loss_mask_entropy + normal_loss + dist_loss, (loss_mask_entropy, normal_error mean, dist mean)).
+    ``gt_mask`` may be None (term skipped)."""
+    total = 0.0
+    me = None
+    if gt_mask is not None:
+        opacity = rend_alpha.clamp(1e-6, 1 - 1e-6).squeeze(0)
+        me = -(gt_mask * torch.log(opacity) + (1 - gt_mask) * torch.log(1 - opacity)).mean()
+        total = total + lambda_mask_entropy * me
+    normal_error = (1 - (rend_normal * surf_normal).sum(dim=0))[None]
+    normal_loss = lambda_normal * (normal_error).mean()
+    dist_loss = lambda_dist * (rend_dist).mean()
+    return total + dist_loss + normal_loss, (me, normal_error.mean(), rend_dist.mean())

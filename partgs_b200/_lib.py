@@ -78,6 +78,9 @@ SIGNATURES = {
     "pgs_photometric_forward": (C.c_int, [C.c_int, C.c_int, C.c_int, _f32p, _f32p, _vp, _f32p, _vp]),
     "pgs_photometric_backward": (C.c_int, [C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, C.c_float, _f32p,
                                            _vp]),
+    "pgs_regularizers_forward": (C.c_int, [C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _vp, _vp]),
+    "pgs_regularizers_backward": (C.c_int, [C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float,
+                                            C.c_float, _f32p, _f32p, _f32p, _f32p, _vp]),
     "pgs_adam_step": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_double,
                                 C.c_double, _vp]),
     "pgs_densify_stats": (C.c_int, [C.c_int, _vp, _f32p, _f32p, _f32p, _f32p, _vp]),

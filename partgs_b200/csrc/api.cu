@@ -788,6 +788,33 @@ int pgs_photometric_backward(int channels, int height, int width, const float* i
   return check_cuda("photometric_backward");
 }
 
+// ---- per-pixel regularisers (mask entropy, normal consistency, distortion) ---------------------------------
+int pgs_regularizers_forward(int width, int height, const float* rend_alpha, const float* gt_mask,
+                             const float* rend_dist, const float* rend_normal, const float* surf_normal, double* sums,
+                             void* stream) {
+  if (width < 0 || height < 0 || (long long)width * height > 0x7fffffffLL || !sums)
+    return set_error(PGS_ERR_INVALID_ARG, "regularizers_forward: bad arguments");
+  if ((gt_mask && !rend_alpha) || ((rend_normal == nullptr) != (surf_normal == nullptr)))
+    return set_error(PGS_ERR_INVALID_ARG, "regularizers_forward: mask needs rend_alpha; normals come in pairs");
+  launch_regularizers_fwd(width * height, rend_alpha, gt_mask, rend_dist, rend_normal, surf_normal, sums,
+                          (cudaStream_t)stream);
+  return check_cuda("regularizers_forward");
+}
+int pgs_regularizers_backward(int width, int height, const float* rend_alpha, const float* gt_mask,
+                              const float* rend_normal, const float* surf_normal, const float* g_loss,
+                              float lambda_mask_entropy, float lambda_normal, float lambda_dist, float* g_rend_alpha,
+                              float* g_rend_dist, float* g_rend_normal, float* g_surf_normal, void* stream) {
+  if (width < 0 || height < 0 || (long long)width * height > 0x7fffffffLL || !g_loss)
+    return set_error(PGS_ERR_INVALID_ARG, "regularizers_backward: bad arguments");
+  if ((gt_mask && g_rend_alpha && !rend_alpha) || ((g_rend_normal == nullptr) != (g_surf_normal == nullptr)) ||
+      (g_rend_normal && (!rend_normal || !surf_normal)))
+    return set_error(PGS_ERR_INVALID_ARG, "regularizers_backward: inconsistent pointers");
+  launch_regularizers_bwd(width * height, rend_alpha, gt_mask, rend_normal, surf_normal, g_loss, lambda_mask_entropy,
+                          lambda_normal, lambda_dist, g_rend_alpha, g_rend_dist, g_rend_normal, g_surf_normal,
+                          (cudaStream_t)stream);
+  return check_cuda("regularizers_backward");
+}
+
 // ---- optimiser step / densification statistics -----------------------------------------------------------
 int pgs_adam_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
                   float* const* exp_avg_sq, const size_t* numel, const float* step_size, double beta1, double beta2,

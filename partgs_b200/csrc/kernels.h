@@ -201,6 +201,15 @@ void launch_photometric_fwd(int C, int H, int W, const float* img, const float* 
 void launch_photometric_bwd(int C, int H, int W, const float* img, const float* gt, const float* dmaps,
                             const float* g_loss, float lambda, float* g_img, cudaStream_t s);
 
+// ---- per-pixel regularisers: mask entropy, normal consistency, distortion (regularizers.cu) ---------
+// sums: 3 doubles (zeroed inside); any of mask / rend_normal+surf_normal / dist may be NULL (term skipped)
+void launch_regularizers_fwd(int npix, const float* alpha, const float* mask, const float* dist,
+                             const float* rend_normal, const float* surf_normal, double* sums, cudaStream_t s);
+void launch_regularizers_bwd(int npix, const float* alpha, const float* mask, const float* rend_normal,
+                             const float* surf_normal, const float* g_loss, float lambda_entropy, float lambda_normal,
+                             float lambda_dist, float* g_alpha, float* g_dist, float* g_rend_normal,
+                             float* g_surf_normal, cudaStream_t s);
+
 // ---- optimiser step / densification statistics (optim.cu) -----------------------------------------
 #define PGS_ADAM_MAX_TENSORS 16
 struct AdamTable {

@@ -174,3 +174,44 @@ def test_emulated_sq2surfel_matches_reference_golden(emu, path):
         close(g[k], z["d_" + k], 1e-4, "d_" + k)
     close(d_alpha, z["d_alpha"], 1e-4, "d_alpha")
     close(d_scale, z["d_scale_raw"], 1e-4, "d_scale_raw")
+
+
+@pytest.mark.parametrize("with_mask", [True, False])
+def test_emulated_regularizers_match_the_oracle(emu, with_mask):
+    """Mask entropy + normal consistency + distortion (train.py:234-251), values and all four gradients."""
+    from oracle import loss_oracle
+    H, W = 37, 53
+    gen = torch.Generator().manual_seed(11)
+    alpha = torch.rand(1, H, W, generator=gen)
+    alpha[0, 0, :6] = torch.tensor([0.0, 1.0, 1e-7, 1 - 1e-8, 1e-6, 0.5])   # the clamp and its zero-gradient zone
+    alpha.requires_grad_(True)
+    mask = (torch.rand(H, W, generator=gen) > 0.4).float() if with_mask else None
+    dist = torch.rand(1, H, W, generator=gen).requires_grad_(True)
+    rn = torch.randn(3, H, W, generator=gen).requires_grad_(True)
+    sn = torch.randn(3, H, W, generator=gen).requires_grad_(True)
+    lam = (0.1, 0.05, 1000.0)
+    ref, parts = loss_oracle.geometric_regularizers(alpha, mask, dist, rn, sn, *lam)
+    (ref * 1.7).backward()
+    sums = np.full(3, np.nan, np.float64)
+    a_, d_, rn_, sn_ = f32(alpha), f32(dist), f32(rn), f32(sn)
+    m_ = None if mask is None else f32(mask)
+    assert emu.pgs_regularizers_forward(W, H, _p(a_), _p(m_), _p(d_), _p(rn_), _p(sn_), _p(sums), None) >= 0
+    n = float(H * W)
+    loss = (lam[0] * sums[0] / n if with_mask else 0.0) + lam[1] * sums[1] / n + lam[2] * sums[2] / n
+    assert abs(loss - float(ref.detach())) <= 2e-6 * abs(float(ref.detach()))
+    if with_mask:
+        assert abs(sums[0] / n - float(parts[0].detach())) <= 2e-6 * abs(float(parts[0].detach()))
+    g_loss = np.array([1.7], np.float32)
+    ga, gd, grn, gsn = (np.full(s, np.nan, np.float32) for s in ((1, H, W), (1, H, W), (3, H, W), (3, H, W)))
+    rc = emu.pgs_regularizers_backward(W, H, _p(a_), _p(m_), _p(rn_), _p(sn_), _p(g_loss), lam[0], lam[1], lam[2],
+                                       _p(ga), _p(gd), _p(grn), _p(gsn), None)
+    assert rc >= 0, emu.pgs_last_error()
+    for got, want, name in ((gd, dist.grad, "dist"), (grn, rn.grad, "rend_normal"), (gsn, sn.grad, "surf_normal")):
+        want = want.numpy()
+        assert float(np.abs(got - want).max()) <= 2e-6 * float(np.abs(want).max()), name
+    if with_mask:
+        want = alpha.grad.numpy()
+        assert float(np.abs(ga - want).max()) <= 2e-6 * float(np.abs(want).max())
+        assert ga[0, 0, 0] == 0 and ga[0, 0, 1] == 0 and ga[0, 0, 2] == 0 and ga[0, 0, 3] == 0 and ga[0, 0, 5] != 0
+    else:
+        assert not ga.any() and alpha.grad is None

@@ -103,11 +103,29 @@ def row_reconstruction(reps):
                 speedup=round(rw / ow, 2))
 
 
+def row_regularizers(reps):
+    from oracle import loss_oracle
+    from partgs_b200.losses import geometric_regularizers
+    H, W = 1200, 1600
+    allmap = torch.rand(7, H, W, device="cuda"); mask = (torch.rand(H, W, device="cuda") > 0.4).float()
+    rn0 = torch.randn(3, H, W, device="cuda"); sn0 = torch.randn(3, H, W, device="cuda")
+
+    def run(fused):
+        am = allmap.clone().requires_grad_(True); rn = rn0.clone().requires_grad_(True); sn = sn0.clone().requires_grad_(True)
+        pkg = {"rend_alpha": am[1:2], "rend_dist": am[6:7], "rend_normal": rn, "surf_normal": sn}
+        loss = geometric_regularizers(pkg, mask, 0.1, 0.05, 1000.0) if fused else \
+            loss_oracle.geometric_regularizers(pkg["rend_alpha"], mask, pkg["rend_dist"], rn, sn, 0.1, 0.05, 1000.0)[0]
+        loss.backward()
+    run(True); run(False)
+    o, ow = timed(lambda: run(True), reps); r, rw = timed(lambda: run(False), reps)
+    return dict(row="regularizers_fwd_bwd_1600x1200 (incl. 3 clones)", ours_ms=o, reference_ms=r, speedup=round(r / o, 2))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--P", type=int, default=1_000_000); ap.add_argument("--reps", type=int, default=5)
     a = ap.parse_args()
-    for fn, args in ((row_densify, (a.P, a.reps)), (row_adam, (a.P, a.reps)), (row_extract, (a.reps,)),
+    for fn, args in ((row_densify, (a.P, a.reps)), (row_adam, (a.P, a.reps)), (row_extract, (a.reps,)), (row_regularizers, (a.reps,)),
                      (row_reconstruction, (3,))):
         try:
             print(json.dumps(fn(*args)), flush=True)
