@@ -29,11 +29,12 @@ _MODEL_ATTR = {"xyz": "_xyz", "f_dc": "_features_dc", "f_rest": "_features_rest"
 
 
 def _check(t: torch.Tensor, name: str, rows: int) -> torch.Tensor:
-    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32):
+    if not (isinstance(t, torch.Tensor) and t.dtype == torch.float32):
         raise RuntimeError(f"densify: {name} must be a CUDA float32 tensor (no fallback)")
+    t = _lib.require_cuda_float(t.detach(), f"densify: {name}")  # raises for CPU tensors
     if t.shape[0] != rows:
         raise RuntimeError(f"densify: {name} has {t.shape[0]} rows, expected {rows}")
-    return t.detach().contiguous()
+    return t
 
 
 def densify_and_prune(params: Dict[str, torch.Tensor], moments: Dict[str, Optional[Tuple[torch.Tensor, torch.Tensor]]],

@@ -63,7 +63,7 @@ def test_rewrap_without_state_and_error_paths():
 def test_cpu_tensors_are_rejected_not_silently_processed(lib):
     params = {k: torch.zeros((4,) + s) for k, s in
               {"xyz": (3,), "f_dc": (1, 3), "f_rest": (3, 3), "opacity": (1,), "scaling": (2,), "rotation": (4,)}.items()}
-    with pytest.raises(RuntimeError, match="CUDA float32"):
+    with pytest.raises(RuntimeError, match="CUDA"):
         densify.densify_and_prune(params, {k: None for k in params}, None, torch.zeros(4, 1), torch.zeros(4, 1),
                                   0.0002, 0.005, 1.0, 20, 0.01)
 

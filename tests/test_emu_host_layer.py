@@ -1,0 +1,176 @@
+"""The product's Python host layer on CPU tensors over the emulated library (tests/emu_host.py): the ctypes argument
+order, autograd plumbing and buffer handling of the public entry points are exercised without a GPU —
+GaussianRasterizer (both forks) through autograd against the C oracle / the emulated-reference golden vectors,
+render() / render_part(), the fused losses, densification, the extraction epilogue."""
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from emu_host import emulated_host  # noqa: F401  (fixture)
+from oracle import cpu_oracle, extract_oracle, loss_oracle
+from partgs_b200 import synth
+from test_emu_raster import rel
+
+GOLD = Path(__file__).parent / "golden"
+
+
+def _small_scene(P=300, W=48, H=32, seed=1, S=0):
+    scene = synth.make_point_scene(P, seed=seed, S=S, device="cpu")
+    scene["scales"] = scene["scales"] * 3.0
+    cam = synth.make_cameras(1, W, H, seed=seed + 10, device="cpu")[0]
+    return scene, cam
+
+
+def test_rasterizer_autograd_path_matches_the_c_oracle(emulated_host):
+    from partgs_b200.diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    scene, cam = _small_scene()
+    W, H = cam.image_width, cam.image_height
+    g = synth.upstream_grads(W, H, 5, device="cpu")
+    leaf = {k: scene[k].clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+    means2D = torch.zeros_like(leaf["means3D"], requires_grad=True)
+    settings = GaussianRasterizationSettings(
+        image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=torch.zeros(3), scale_modifier=1.0,
+        viewmatrix=cam.viewmatrix, projmatrix=cam.projmatrix, sh_degree=3, campos=cam.campos, prefiltered=False,
+        debug=True)
+    rast = GaussianRasterizer(settings)
+    color, radii, allmap = rast(means3D=leaf["means3D"], means2D=means2D, opacities=leaf["opacities"], shs=leaf["shs"],
+                                scales=leaf["scales"], rotations=leaf["rotations"])
+    torch.autograd.backward([color, allmap], [g["color"], g["allmap"]])
+    f = cpu_oracle.forward_scene(scene, cam, keep_state=True)
+    gr = cpu_oracle.backward(f, g["color"], g["allmap"])
+    assert np.array_equal(radii.numpy(), f["radii"])
+    assert rel(color.detach().numpy(), f["color"]) <= 2e-5 and rel(allmap.detach().numpy(), f["allmap"]) <= 2e-5
+    for k, ok in (("means3D", "means3D"), ("scales", "scales"), ("rotations", "rotations"), ("opacities", "opacity"),
+                  ("shs", "sh")):
+        assert rel(leaf[k].grad.numpy(), gr[ok]) <= 2e-4, k
+    assert rel(means2D.grad.numpy()[:, :2], gr["means2D"][:, :2]) <= 2e-4
+    vis = rast.markVisible(scene["means3D"])
+    assert vis.dtype == torch.bool and int(vis.sum()) >= int((radii > 0).sum())
+    with pytest.raises(Exception, match="one of either SHs"):
+        rast(means3D=leaf["means3D"], means2D=means2D, opacities=leaf["opacities"], shs=None, colors_precomp=None,
+             scales=leaf["scales"], rotations=leaf["rotations"])
+
+
+def test_part_rasterizer_autograd_path_matches_reference_golden(emulated_host):
+    from partgs_b200.diff_surfel_rasterization_part import GaussianRasterizationSettings, GaussianRasterizer
+    z = dict(np.load(GOLD / "ref_emu_part_p300_s5_48x32.npz"))
+    t = lambda k: torch.from_numpy(z[k])
+    leaf = {k: t(k).clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs",
+                                                            "semantics")}
+    means2D = torch.zeros_like(leaf["means3D"], requires_grad=True)
+    tx, ty = (float(v) for v in z["tanfov"])
+    settings = GaussianRasterizationSettings(
+        image_height=int(z["H"]), image_width=int(z["W"]), tanfovx=tx, tanfovy=ty, bg=t("bg"), scale_modifier=1.0,
+        viewmatrix=t("viewmatrix"), projmatrix=t("projmatrix"), sh_degree=int(z["degree"]), campos=t("campos"),
+        prefiltered=False, debug=True)
+    color, semantic, radii, allmap = GaussianRasterizer(settings)(
+        means3D=leaf["means3D"], means2D=means2D, opacities=leaf["opacities"], semantics=leaf["semantics"],
+        shs=leaf["shs"], scales=leaf["scales"], rotations=leaf["rotations"])
+    torch.autograd.backward([color, semantic, allmap], [t("g_color"), t("g_semantic"), t("g_allmap")])
+    assert np.array_equal(radii.numpy(), z["radii"])
+    assert rel(color.detach().numpy(), z["color"]) <= 2e-5 and rel(semantic.detach().numpy(), z["semantic"]) <= 2e-5
+    for k, ok in (("means3D", "means3D"), ("scales", "scales"), ("rotations", "rotations"), ("opacities", "opacity"),
+                  ("shs", "sh"), ("semantics", "semantics")):
+        assert rel(leaf[k].grad.numpy(), z["d_" + ok]) <= 2e-4, k
+
+
+def _pc(scene):
+    return SimpleNamespace(get_xyz=scene["means3D"], get_opacity=scene["opacities"], get_scaling=scene["scales"],
+                           get_rotation=scene["rotations"], get_features=scene["shs"],
+                           get_semantic=scene.get("semantics"), active_sh_degree=3)
+
+
+def test_render_mirrors_and_fused_losses(emulated_host):
+    from partgs_b200.losses import geometric_regularizers, photometric_loss
+    from partgs_b200.renderer import render, render_part
+    scene, cam = _small_scene(S=4)
+    pipe = SimpleNamespace(depth_ratio=0.5, compute_cov3D_python=False, convert_SHs_python=False)
+    scene["means3D"].requires_grad_(True)
+    r = render(cam, _pc(scene), pipe, torch.zeros(3))
+    assert set(r) == {"render", "viewspace_points", "visibility_filter", "radii", "rend_alpha", "rend_normal",
+                      "rend_dist", "surf_depth", "surf_normal"}
+    H, W = r["render"].shape[1:]
+    gt = torch.rand(3, H, W, generator=torch.Generator().manual_seed(2))
+    mask = (torch.rand(H, W, generator=torch.Generator().manual_seed(3)) > 0.5).float()
+    loss = photometric_loss(r["render"], gt, 0.2) + geometric_regularizers(r, mask, 0.1, 0.05, 100.0)
+    want = loss_oracle.photometric_loss(r["render"].detach(), gt, 0.2) + loss_oracle.geometric_regularizers(
+        r["rend_alpha"].detach(), mask, r["rend_dist"].detach(), r["rend_normal"].detach(), r["surf_normal"].detach(),
+        0.1, 0.05, 100.0)[0]
+    assert abs(float(loss.detach()) - float(want)) <= 1e-5 * abs(float(want))
+    loss.backward()
+    assert scene["means3D"].grad is not None and bool(torch.isfinite(scene["means3D"].grad).all())
+    assert float(scene["means3D"].grad.abs().max()) > 0 and r["viewspace_points"].grad is not None
+    rp = render_part(cam, _pc(scene), pipe, torch.zeros(3))
+    assert set(rp) == set(r) | {"render_semantic"} and rp["render_semantic"].shape == (4, H, W)
+    assert bool(torch.isfinite(rp["surf_normal"]).all()) and rp["surf_depth"].shape == (1, H, W)
+
+
+@pytest.mark.parametrize("path", sorted(GOLD.glob("densify_*.npz")), ids=lambda p: p.stem)
+def test_densify_python_layer_reproduces_reference(emulated_host, path):
+    from partgs_b200 import densify
+    z = np.load(path)
+    t = {k: torch.from_numpy(z[k]) for k in z.files if z[k].ndim > 0}
+    mss = None if float(z["max_screen_size"]) < 0 else float(z["max_screen_size"])
+    names = densify.PARAM_NAMES
+    p, m, s, info = densify.densify_and_prune(
+        {k: t["in_" + k] for k in names}, {k: (t["in_m_" + k], t["in_v_" + k]) for k in names}, t["in_semantic"],
+        t["in_accum"], t["in_denom"], float(z["max_grad"]), float(z["min_opacity"]), float(z["extent"]), mss,
+        float(z["percent_dense"]), N=2, z=t["z"])
+    c = info["n_kept"] + info["n_clones"]
+    assert info["n_out"] == t["out_xyz"].shape[0]
+    for k in names:
+        if k in ("xyz", "scaling"):
+            assert torch.equal(p[k][:c], t["out_" + k][:c]), k
+            assert float((p[k][c:] - t["out_" + k][c:]).abs().max()) <= 2e-5 * float(t["out_" + k].abs().max()), k
+        else:
+            assert torch.equal(p[k], t["out_" + k]), k
+        assert torch.equal(m[k][0], t["out_m_" + k]) and torch.equal(m[k][1], t["out_v_" + k]), k
+    assert torch.equal(s, t["out_semantic"])
+
+
+def test_densify_model_level_drop_in(emulated_host):
+    from partgs_b200 import densify
+    z = np.load(GOLD / "densify_p400_s4.npz")
+    t = {k: torch.from_numpy(z[k]) for k in z.files if z[k].ndim > 0}
+    model = SimpleNamespace(percent_dense=float(z["percent_dense"]), _semantic=t["in_semantic"],
+                            xyz_gradient_accum=t["in_accum"], denom=t["in_denom"], max_radii2D=t["in_max_radii2D"])
+    groups = []
+    for k, attr in densify._MODEL_ATTR.items():
+        prm = torch.nn.Parameter(t["in_" + k].clone())
+        setattr(model, attr, prm)
+        groups.append({"params": [prm], "lr": 1e-3, "name": k})
+    model.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+    for g in model.optimizer.param_groups:
+        model.optimizer.state[g["params"][0]] = {"step": torch.tensor(3.0), "exp_avg": t["in_m_" + g["name"]].clone(),
+                                                 "exp_avg_sq": t["in_v_" + g["name"]].clone()}
+    # the draws: re-seed like tools/make_golden_densify.py did (seed + 1 = 12), CPU generator here
+    torch.manual_seed(12)
+    info = densify.densify_and_prune_model(model, float(z["max_grad"]), float(z["min_opacity"]), float(z["extent"]),
+                                           float(z["max_screen_size"]))
+    n = info["n_out"]
+    assert n == t["out_xyz"].shape[0]
+    for g in model.optimizer.param_groups:
+        k, prm = g["name"], g["params"][0]
+        assert prm is getattr(model, densify._MODEL_ATTR[k])
+        assert float((prm.detach() - t["out_" + k]).abs().max()) <= 2e-5 * float(t["out_" + k].abs().max()), k
+        st = model.optimizer.state[prm]
+        assert torch.equal(st["exp_avg"], t["out_m_" + k]) and float(st["step"]) == 3.0
+    assert torch.equal(model._semantic, t["out_semantic"])
+    assert model.xyz_gradient_accum.shape == (n, 1) and model.max_radii2D.shape == (n,) and not model.denom.any()
+
+
+def test_extract_maps_python_layer(emulated_host):
+    from partgs_b200.extract import extract_maps
+    z = np.load(GOLD / "extract_maps.npz")
+    part, pal = torch.from_numpy(z["b_part"]), torch.from_numpy(z["b_palette"])
+    nrm = torch.randn(3, *part.shape[1:], generator=torch.Generator().manual_seed(4))
+    rgb, unit = extract_maps(part, nrm, pal)
+    assert torch.equal(rgb, torch.from_numpy(z["b_rgb"]))
+    assert float((unit - extract_oracle.unit_normals(nrm)).abs().max()) <= 1e-6
+    rgb2, none = extract_maps(part, None, torch.cat([pal, torch.ones(len(pal), 1)], 1))
+    assert none is None and torch.equal(rgb2, rgb)
+    with pytest.raises(RuntimeError, match="palette"):
+        extract_maps(part, None, pal[:3])
