@@ -192,7 +192,9 @@ inline double min(double a, float b) { return fmin(a, (double)b); }
 #define cudaMemsetAsync(p, v, n, s) (memset((p), (v), (n)), cudaSuccess)
 template <class T> inline cudaError_t cudaFuncSetAttribute(T*, cudaFuncAttribute, int) { return cudaSuccess; }
 
-// Run `body` for every thread of the grid; blocks one after the other in x-fastest order.
+// Run `body` for every thread of the grid; blocks one after the other in x-fastest order.  (A kernel thread that
+// returns early simply waits at the end-of-block barrier; kernels that call __syncthreads after some threads have
+// returned are not supported.)
 inline void emu_run(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
   const unsigned nthreads = block.x * block.y * block.z;
   if (nthreads % 32 != 0 || nthreads == 0) throw std::runtime_error("emu: block size must be a multiple of 32");
@@ -202,23 +204,26 @@ inline void emu_run(dim3 grid, dim3 block, size_t smem, const std::function<void
   for (auto& w : warps) w.bar.reset(32);
   std::vector<unsigned char> dyn(smem + 64);
   emu::g_dyn_smem = (unsigned char*)(((size_t)dyn.data() + 63) & ~(size_t)63);
-  for (unsigned bz = 0; bz < grid.z; bz++)
-    for (unsigned by = 0; by < grid.y; by++)
-      for (unsigned bx = 0; bx < grid.x; bx++) {
-        emu::g_block_bar.reset((int)nthreads);
-        std::vector<std::thread> ts;
-        ts.reserve(nthreads);
-        for (unsigned t = 0; t < nthreads; t++) {
-          ts.emplace_back([&, t, bx, by, bz] {
-            threadIdx = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+  // one OS thread per CUDA thread of a block, reused for every block of the launch; a block barrier separates
+  // consecutive blocks (their `__shared__` statics are the same storage)
+  emu::g_block_bar.reset((int)nthreads);
+  std::vector<std::thread> ts;
+  ts.reserve(nthreads);
+  for (unsigned t = 0; t < nthreads; t++) {
+    ts.emplace_back([&, t] {
+      threadIdx = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+      emu::t_warp = &warps[t / 32];
+      emu::t_lane = t % 32;
+      for (unsigned bz = 0; bz < grid.z; bz++)
+        for (unsigned by = 0; by < grid.y; by++)
+          for (unsigned bx = 0; bx < grid.x; bx++) {
             blockIdx = {bx, by, bz};
-            emu::t_warp = &warps[t / 32];
-            emu::t_lane = t % 32;
             body();
-          });
-        }
-        for (auto& th : ts) th.join();
-      }
+            emu::g_block_bar.wait();
+          }
+    });
+  }
+  for (auto& th : ts) th.join();
   emu::g_dyn_smem = nullptr;
 }
 #define EMU_LAUNCH(kernel, grid, block, smem, ...) \

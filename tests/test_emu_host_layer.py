@@ -86,7 +86,7 @@ def _pc(scene):
 def test_render_mirrors_and_fused_losses(emulated_host):
     from partgs_b200.losses import geometric_regularizers, photometric_loss
     from partgs_b200.renderer import render, render_part
-    scene, cam = _small_scene(S=4)
+    scene, cam = _small_scene(P=150, W=32, H=16, S=4)
     pipe = SimpleNamespace(depth_ratio=0.5, compute_cov3D_python=False, convert_SHs_python=False)
     scene["means3D"].requires_grad_(True)
     r = render(cam, _pc(scene), pipe, torch.zeros(3))
