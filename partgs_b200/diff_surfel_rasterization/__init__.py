@@ -113,7 +113,9 @@ def _native_backward(bg, means3D, radii, colors, scales, rotations, scale_modifi
     dev = means3D.device
     P = means3D.size(0)
     H, W = dL_dout_color.size(1), dL_dout_color.size(2)
-    M = sh.size(1) if sh.numel() != 0 else 0
+    # an empty model (P == 0) still carries sh [0,M,3]: the gradient must have that shape (the reference derives M
+    # from sh.size(0) != 0 and then fails autograd's shape check)
+    M = sh.size(1) if sh.dim() == 3 else 0
     f32 = dict(dtype=torch.float32, device=dev)
     # every row is written by the kernels -> torch.empty, no 304 B/surfel zero fill.
     # The five parameter gradients (232 B/surfel) are carved out of ONE flat buffer ("gradient

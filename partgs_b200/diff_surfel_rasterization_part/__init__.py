@@ -88,7 +88,9 @@ def _native_backward(bg, means3D, radii, colors, semantics, scales, rotations, s
     dev = means3D.device
     P = means3D.size(0)
     H, W = dL_dout_color.size(1), dL_dout_color.size(2)
-    M = sh.size(1) if sh.numel() != 0 else 0
+    # an empty model (P == 0) still carries sh [0,M,3]: the gradient must have that shape (the reference derives M
+    # from sh.size(0) != 0 and then fails autograd's shape check)
+    M = sh.size(1) if sh.dim() == 3 else 0
     S = semantics.size(1)
     f32 = dict(dtype=torch.float32, device=dev)
     dL_dmeans3D = torch.empty((P, 3), **f32)

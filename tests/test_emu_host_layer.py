@@ -174,3 +174,21 @@ def test_extract_maps_python_layer(emulated_host):
     assert none is None and torch.equal(rgb2, rgb)
     with pytest.raises(RuntimeError, match="palette"):
         extract_maps(part, None, pal[:3])
+
+
+def test_empty_model_short_circuits_like_the_reference(emulated_host):
+    """P == 0: zero images, no state, gradients of the right (empty) shapes (rasterize_points.cu:85-99,197)."""
+    from partgs_b200.diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    cam = synth.make_cameras(1, 20, 12, seed=3, device="cpu")[0]
+    settings = GaussianRasterizationSettings(
+        image_height=12, image_width=20, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=torch.ones(3), scale_modifier=1.0,
+        viewmatrix=cam.viewmatrix, projmatrix=cam.projmatrix, sh_degree=3, campos=cam.campos, prefiltered=False,
+        debug=False)
+    e = lambda *s: torch.zeros(*s, requires_grad=True)
+    m3, m2, op, sh, sc, rot = e(0, 3), e(0, 3), e(0, 1), e(0, 16, 3), e(0, 2), e(0, 4)
+    color, radii, allmap = GaussianRasterizer(settings)(means3D=m3, means2D=m2, opacities=op, shs=sh, scales=sc,
+                                                        rotations=rot)
+    assert color.shape == (3, 12, 20) and allmap.shape == (7, 12, 20) and radii.shape == (0,)
+    assert not color.any() and not allmap.any()
+    (color.sum() + allmap.sum()).backward()
+    assert m3.grad.shape == (0, 3) and sh.grad.shape == (0, 16, 3)
