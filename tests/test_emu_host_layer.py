@@ -192,3 +192,31 @@ def test_empty_model_short_circuits_like_the_reference(emulated_host):
     assert not color.any() and not allmap.any()
     (color.sum() + allmap.sum()).backward()
     assert m3.grad.shape == (0, 3) and sh.grad.shape == (0, 16, 3)
+
+
+def test_precomputed_transform_path_matches_the_emulated_reference(emulated_host):
+    """`cov3D_precomp` ([P,9] ray-splat transforms instead of scales / rotations): forward and backward against the
+    UNMODIFIED reference source run on the emulator (tests/golden/ref_emu_base_precompT_*.npz)."""
+    from partgs_b200.diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    z = dict(np.load(GOLD / "ref_emu_base_precompT_p300_48x32.npz"))
+    t = lambda k: torch.from_numpy(z[k])
+    leaf = {k: t(k).clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "transMat_precomp")}
+    means2D = torch.zeros_like(leaf["means3D"], requires_grad=True)
+    tx, ty = (float(v) for v in z["tanfov"])
+    settings = GaussianRasterizationSettings(
+        image_height=int(z["H"]), image_width=int(z["W"]), tanfovx=tx, tanfovy=ty, bg=t("bg"), scale_modifier=1.0,
+        viewmatrix=t("viewmatrix"), projmatrix=t("projmatrix"), sh_degree=int(z["degree"]), campos=t("campos"),
+        prefiltered=False, debug=True)
+    color, radii, allmap = GaussianRasterizer(settings)(
+        means3D=leaf["means3D"], means2D=means2D, opacities=leaf["opacities"], shs=leaf["shs"],
+        cov3D_precomp=leaf["transMat_precomp"])
+    torch.autograd.backward([color, allmap], [t("g_color"), t("g_allmap")])
+    assert np.array_equal(radii.numpy(), z["radii"])
+    assert rel(color.detach().numpy(), z["color"]) <= 2e-5
+    for ch in range(7):
+        assert rel(allmap.detach().numpy()[ch], z["allmap"][ch]) <= (3e-3 if ch == 6 else 5e-5), ch
+    assert rel(leaf["transMat_precomp"].grad.numpy(), z["d_transMat"]) <= 2e-4
+    assert rel(leaf["opacities"].grad.numpy(), z["d_opacity"]) <= 2e-4
+    assert rel(leaf["shs"].grad.numpy(), z["d_sh"]) <= 2e-4
+    assert rel(leaf["means3D"].grad.numpy(), z["d_means3D"]) <= 2e-4
+    assert rel(means2D.grad.numpy()[:, :2], z["d_means2D"][:, :2]) <= 2e-4
