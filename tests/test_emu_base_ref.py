@@ -39,7 +39,7 @@ def test_c_oracle_matches_the_emulated_reference(path):
     tx, ty = (float(v) for v in z["tanfov"])
     f = cpu_oracle.forward(z["means3D"], z["scales"], z["rotations"], z["opacities"], z["shs"], z["viewmatrix"],
                            z["projmatrix"], z["campos"], int(z["W"]), int(z["H"]), tx, ty, bg=z["bg"],
-                           sh_degree=int(z["degree"]), keep_state=True)
+                           sh_degree=int(z["degree"]), scale_modifier=float(z["scale_modifier"]), keep_state=True)
     g = cpu_oracle.backward(f, z["g_color"], z["g_allmap"])
     _check(z, f["color"], f["allmap"], f["radii"], f["num_rendered"], g, "C oracle")
 
@@ -64,5 +64,6 @@ def test_emulated_product_matches_the_emulated_reference(emu, path):
     tx, ty = (float(v) for v in z["tanfov"])
     cam = SimpleNamespace(viewmatrix=t("viewmatrix"), projmatrix=t("projmatrix"), campos=t("campos"),
                           image_width=int(z["W"]), image_height=int(z["H"]), tanfovx=tx, tanfovy=ty)
-    ours = run_emulated(emu, scene, cam, t("g_color"), t("g_allmap"), degree=int(z["degree"]), bg=z["bg"])
+    ours = run_emulated(emu, scene, cam, t("g_color"), t("g_allmap"), degree=int(z["degree"]), bg=z["bg"],
+                        scale_modifier=float(z["scale_modifier"]))
     _check(z, ours["color"], ours["allmap"], ours["radii"], ours["R"], ours["grads"], "product")

@@ -36,6 +36,7 @@ def test_emulated_part_fork_matches_emulated_reference(emu, path):
     P, M, S = z["means3D"].shape[0], z["shs"].shape[1], z["semantics"].shape[1]
     W, H, D = int(z["W"]), int(z["H"]), int(z["degree"])
     tx, ty = (float(v) for v in z["tanfov"])
+    sm = float(z["scale_modifier"])
     c = lambda k: np.ascontiguousarray(z[k], dtype=np.float32)
     m3, sc, rot, op, sh, sem, vm, pm, cp, bg = (c(k) for k in ("means3D", "scales", "rotations", "opacities", "shs",
                                                                 "semantics", "viewmatrix", "projmatrix", "campos", "bg"))
@@ -43,7 +44,7 @@ def test_emulated_part_fork_matches_emulated_reference(emu, path):
     allmap = np.full((8, H, W), np.nan, np.float32); radii = np.full(P, -7, np.int32)
     al = HostAlloc()
     R = emu.pgs_dsrp_forward(al.cb, 1, al.cb, 2, al.cb, 3, P, D, M, _p(bg), W, H, S, _p(m3), _p(sh), None, _p(sem),
-                             _p(op), _p(sc), 1.0, _p(rot), None, _p(vm), _p(pm), _p(cp), tx, ty, 0, _p(color),
+                             _p(op), _p(sc), sm, _p(rot), None, _p(vm), _p(pm), _p(cp), tx, ty, 0, _p(color),
                              _p(semantic), _p(allmap), _p(radii), 1, None)
     assert R >= 0, emu.pgs_last_error()
     assert R == int(z["R"])
@@ -60,7 +61,7 @@ def test_emulated_part_fork_matches_emulated_reference(emu, path):
              sh=np.full((P, M, 3), np.nan, np.float32), scales=np.full((P, 2), np.nan, np.float32),
              rotations=np.full((P, 4), np.nan, np.float32))
     scratch = np.zeros(emu.pgs_dsr_backward_scratch_bytes(P) + 256, np.uint8)
-    rc = emu.pgs_dsrp_backward(P, D, M, R, _p(bg), W, H, S, _p(m3), _p(sh), None, _p(sem), _p(sc), 1.0, _p(rot), None,
+    rc = emu.pgs_dsrp_backward(P, D, M, R, _p(bg), W, H, S, _p(m3), _p(sh), None, _p(sem), _p(sc), sm, _p(rot), None,
                                _p(vm), _p(pm), _p(cp), tx, ty, _p(radii), al.ptr(1), al.ptr(2), al.nbytes(2), al.ptr(3),
                                _p(c("g_color")), _p(c("g_semantic")), _p(c("g_allmap")), _p(g["means2D"]),
                                (scratch.ctypes.data + 255) // 256 * 256, _p(g["opacity"]), _p(g["colors"]),

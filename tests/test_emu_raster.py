@@ -53,7 +53,7 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def run_emulated(emu, scene, cam, g_color, g_allmap, degree=3, colors_precomp=None, bg=None):
+def run_emulated(emu, scene, cam, g_color, g_allmap, degree=3, colors_precomp=None, bg=None, scale_modifier=1.0):
     f32 = lambda t: np.ascontiguousarray(t.detach().cpu().numpy(), dtype=np.float32)
     m3, sc, rot, op, sh = (f32(scene[k]) for k in ("means3D", "scales", "rotations", "opacities", "shs"))
     vm, pm, cp = f32(cam.viewmatrix), f32(cam.projmatrix), f32(cam.campos)
@@ -67,7 +67,7 @@ def run_emulated(emu, scene, cam, g_color, g_allmap, degree=3, colors_precomp=No
     radii = np.full(P, -7, np.int32)
     al = HostAlloc()
     R = emu.pgs_dsr_forward(al.cb, 1, al.cb, 2, al.cb, 3, P, degree, M, _p(bg), W, H, _p(m3), _p(sh_arg), _p(cpre), _p(op), _p(sc),
-                            1.0, _p(rot), None, _p(vm), _p(pm), _p(cp), cam.tanfovx, cam.tanfovy, 0, _p(color),
+                            scale_modifier, _p(rot), None, _p(vm), _p(pm), _p(cp), cam.tanfovx, cam.tanfovy, 0, _p(color),
                             _p(allmap), _p(radii), 1, None)
     assert R >= 0, emu.pgs_last_error()
     lay = _lib.DsrLayout()
@@ -83,7 +83,7 @@ def run_emulated(emu, scene, cam, g_color, g_allmap, degree=3, colors_precomp=No
              scales=np.full((P, 2), np.nan, np.float32), rotations=np.full((P, 4), np.nan, np.float32))
     scratch = np.zeros(emu.pgs_dsr_backward_scratch_bytes(P) + 256, np.uint8)
     gc, ga = f32(g_color), f32(g_allmap)
-    rc = emu.pgs_dsr_backward(P, degree, M, R, _p(bg), W, H, _p(m3), _p(sh_arg), _p(cpre), _p(sc), 1.0, _p(rot), None, _p(vm),
+    rc = emu.pgs_dsr_backward(P, degree, M, R, _p(bg), W, H, _p(m3), _p(sh_arg), _p(cpre), _p(sc), scale_modifier, _p(rot), None, _p(vm),
                               _p(pm), _p(cp), cam.tanfovx, cam.tanfovy, _p(radii), al.ptr(1), al.ptr(2), al.nbytes(2),
                               al.ptr(3), _p(gc), _p(ga), _p(g["means2D"]), (scratch.ctypes.data + 255) // 256 * 256,
                               _p(g["opacity"]), _p(g["colors"]), _p(g["means3D"]), _p(g["transMat"]), _p(g["sh"]),

@@ -30,7 +30,7 @@ def f32(t):
     return np.ascontiguousarray(t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else t, dtype=np.float32)
 
 
-def make(lib, name, P, S, W, H, seed, degree=3, scale_mul=3.0):
+def make(lib, name, P, S, W, H, seed, degree=3, scale_mul=3.0, scale_modifier=1.0):
     scene = synth.make_point_scene(P, seed=seed, S=S, device="cpu")
     cam = synth.make_cameras(1, W, H, seed=seed + 10, device="cpu")[0]
     g = synth.upstream_grads(W, H, seed + 20, n_aux=8, S=S, device="cpu")
@@ -43,7 +43,7 @@ def make(lib, name, P, S, W, H, seed, degree=3, scale_mul=3.0):
     allmap = np.zeros((8, H, W), np.float32); radii = np.zeros(P, np.int32)
     lib.ref_part_forward.restype = C.c_int
     R = lib.ref_part_forward(P, degree, M, _p(bg), W, H, S, _p(m3), _p(sh), None, _p(op), _p(sem), _p(sc),
-                             C.c_float(1.0), _p(rot), _p(vm), _p(pm), _p(cp), C.c_float(cam.tanfovx),
+                             C.c_float(scale_modifier), _p(rot), _p(vm), _p(pm), _p(cp), C.c_float(cam.tanfovx),
                              C.c_float(cam.tanfovy), _p(color), _p(semantic), _p(allmap), _p(radii))
     gc, ga, gs = f32(g["color"]), f32(g["allmap"]), f32(g["semantic"])
     d = dict(means2D=np.zeros((P, 3), np.float32), normal=np.zeros((P, 3), np.float32),
@@ -51,13 +51,13 @@ def make(lib, name, P, S, W, H, seed, degree=3, scale_mul=3.0):
              semantics=np.zeros((P, S), np.float32), means3D=np.zeros((P, 3), np.float32),
              transMat=np.zeros((P, 9), np.float32), sh=np.zeros((P, M, 3), np.float32),
              scales=np.zeros((P, 2), np.float32), rotations=np.zeros((P, 4), np.float32))
-    lib.ref_part_backward(P, degree, M, R, _p(bg), W, H, S, _p(m3), _p(sh), None, _p(sem), _p(sc), C.c_float(1.0),
+    lib.ref_part_backward(P, degree, M, R, _p(bg), W, H, S, _p(m3), _p(sh), None, _p(sem), _p(sc), C.c_float(scale_modifier),
                           _p(rot), _p(vm), _p(pm), _p(cp), C.c_float(cam.tanfovx), C.c_float(cam.tanfovy), _p(radii),
                           _p(gc), _p(gs), _p(ga), _p(d["means2D"]), _p(d["normal"]), _p(d["opacity"]), _p(d["colors"]),
                           _p(d["semantics"]), _p(d["means3D"]), _p(d["transMat"]), _p(d["sh"]), _p(d["scales"]),
                           _p(d["rotations"]))
     out = dict(means3D=m3, scales=sc, rotations=rot, opacities=op, shs=sh, semantics=sem, viewmatrix=vm, projmatrix=pm,
-               campos=cp, bg=bg, tanfov=np.array([cam.tanfovx, cam.tanfovy], np.float64), W=W, H=H, degree=degree,
+               campos=cp, bg=bg, scale_modifier=np.float64(scale_modifier), tanfov=np.array([cam.tanfovx, cam.tanfovy], np.float64), W=W, H=H, degree=degree,
                g_color=gc, g_allmap=ga, g_semantic=gs, R=R, color=color, semantic=semantic, allmap=allmap, radii=radii)
     out.update({"d_" + k: v for k, v in d.items() if k != "normal"})
     path = ROOT / "tests" / "golden" / f"ref_emu_part_{name}.npz"
@@ -66,7 +66,7 @@ def make(lib, name, P, S, W, H, seed, degree=3, scale_mul=3.0):
           all(np.isfinite(v).all() for v in d.values()))
 
 
-def make_base(lib, name, P, W, H, seed, degree=3, scale_mul=3.0, precomp=False):
+def make_base(lib, name, P, W, H, seed, degree=3, scale_mul=3.0, precomp=False, scale_modifier=1.0):
     scene = synth.make_point_scene(P, seed=seed, device="cpu")
     cam = synth.make_cameras(1, W, H, seed=seed + 10, device="cpu")[0]
     g = synth.upstream_grads(W, H, seed + 20, device="cpu")
@@ -85,7 +85,7 @@ def make_base(lib, name, P, W, H, seed, degree=3, scale_mul=3.0, precomp=False):
         T = np.ascontiguousarray(cpu_oracle.forward(m3, sc, rot, op, sh, vm, pm, cp, W, H, cam.tanfovx, cam.tanfovy,
                                                     bg=bg, sh_degree=degree)["transMat"], dtype=np.float32)
     sc_in, rot_in = (None, None) if precomp else (sc, rot)
-    R = lib.ref_base_forward(P, degree, M, _p(bg), W, H, _p(m3), _p(sh), None, _p(op), _p(sc_in), C.c_float(1.0),
+    R = lib.ref_base_forward(P, degree, M, _p(bg), W, H, _p(m3), _p(sh), None, _p(op), _p(sc_in), C.c_float(scale_modifier),
                              _p(rot_in), _p(T), _p(vm), _p(pm), _p(cp), C.c_float(cam.tanfovx), C.c_float(cam.tanfovy), _p(color),
                              _p(allmap), _p(radii))
     gc, ga = f32(g["color"]), f32(g["allmap"])
@@ -94,12 +94,12 @@ def make_base(lib, name, P, W, H, seed, degree=3, scale_mul=3.0, precomp=False):
              means3D=np.zeros((P, 3), np.float32), transMat=np.zeros((P, 9), np.float32),
              sh=np.zeros((P, M, 3), np.float32), scales=np.zeros((P, 2), np.float32),
              rotations=np.zeros((P, 4), np.float32))
-    lib.ref_base_backward(P, degree, M, R, _p(bg), W, H, _p(m3), _p(sh), None, _p(sc_in), C.c_float(1.0), _p(rot_in),
+    lib.ref_base_backward(P, degree, M, R, _p(bg), W, H, _p(m3), _p(sh), None, _p(sc_in), C.c_float(scale_modifier), _p(rot_in),
                           _p(T), _p(vm), _p(pm), _p(cp), C.c_float(cam.tanfovx), C.c_float(cam.tanfovy), _p(radii), _p(gc), _p(ga),
                           _p(d["means2D"]), _p(d["normal"]), _p(d["opacity"]), _p(d["colors"]), _p(d["means3D"]),
                           _p(d["transMat"]), _p(d["sh"]), _p(d["scales"]), _p(d["rotations"]))
     out = dict(means3D=m3, scales=sc, rotations=rot, opacities=op, shs=sh, viewmatrix=vm, projmatrix=pm, campos=cp,
-               bg=bg, tanfov=np.array([cam.tanfovx, cam.tanfovy], np.float64), W=W, H=H, degree=degree, g_color=gc,
+               bg=bg, scale_modifier=np.float64(scale_modifier), tanfov=np.array([cam.tanfovx, cam.tanfovy], np.float64), W=W, H=H, degree=degree, g_color=gc,
                g_allmap=ga, R=R, color=color, allmap=allmap, radii=radii)
     out.update({"d_" + k: v for k, v in d.items() if k != "normal"})
     if precomp:
@@ -115,6 +115,8 @@ if __name__ == "__main__":
     make_base(base, "p300_48x32", P=300, W=48, H=32, seed=61)
     make_base(base, "p400_40x24_deg2", P=400, W=40, H=24, seed=62, degree=2)
     make_base(base, "precompT_p300_48x32", P=300, W=48, H=32, seed=63, precomp=True)
+    make_base(base, "scalemod_p300_48x32", P=300, W=48, H=32, seed=64, scale_modifier=0.7, scale_mul=4.0)
     lib = C.CDLL(str(emu_build.build_reference("part")))
     make(lib, "p300_s5_48x32", P=300, S=5, W=48, H=32, seed=51)
     make(lib, "p400_s16_40x24_deg1", P=400, S=16, W=40, H=24, seed=52, degree=1)
+    make(lib, "scalemod_p300_s3_48x32", P=300, S=3, W=48, H=32, seed=53, scale_modifier=0.7)
