@@ -14,12 +14,17 @@
  *   preprocess bwd  cuda_rasterizer/backward.cu:443-630 (+ :20-139 SH backward,
  *                   auxiliary.h:128-138 dnormvdv, :238-282 quat_to_rotmat_vjp)
  *
- * Parity pin: checked against golden vectors produced by the reference CUDA itself
- * (oracle/_ref, built from the unmodified sources) — tests/golden/, generated by
- * tools/make_golden.py on a B200.  The GPU contracts a*b+c into FMAs; this file is
- * compiled with -ffp-contract=off, so results agree with the reference to rounding
- * (images ~1e-6, a handful of radii may differ by one on borderline surfels); the
- * bit-exact claims of the product are tested against oracle/_ref, not against this.
+ * Parity pin:
+ *   (1) on the CPU, against golden vectors computed by the reference's OWN CUDA source (the unmodified
+ *       cuda_rasterizer/{forward,backward,rasterizer_impl}.cu, executed by the lock-step emulator of
+ *       tests/cuda_emu; tools/make_golden_ref_emu.py -> tests/golden/ref_emu_base_*.npz): radii and the
+ *       instance count exactly, images <= 2e-5, gradients <= 2e-4, incl. scale_modifier != 1, SH degree 2 and
+ *       a non-zero background (tests/test_emu_base_ref.py);
+ *   (2) on the GPU, against the reference CUDA built for sm_100a (oracle/_ref) in the same process
+ *       (tests/test_gpu_base_raster.py).
+ * The GPU contracts a*b+c into FMAs; this file is compiled with -ffp-contract=off, so results agree with
+ * the reference build to rounding (images ~1e-6, a handful of radii may differ by one on borderline surfels);
+ * the bit-exact claims of the product are tested against oracle/_ref, not against this.
  */
 #include <math.h>
 #include <stdint.h>
