@@ -220,3 +220,68 @@ def test_precomputed_transform_path_matches_the_emulated_reference(emulated_host
     assert rel(leaf["shs"].grad.numpy(), z["d_sh"]) <= 2e-4
     assert rel(leaf["means3D"].grad.numpy(), z["d_means3D"]) <= 2e-4
     assert rel(means2D.grad.numpy()[:, :2], z["d_means2D"][:, :2]) <= 2e-4
+
+
+class _FakeStream:
+    def __init__(self, *a, **k):
+        pass
+
+    def wait_stream(self, other):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+class _FakeEvent:
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, stream=None):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+def test_extraction_loop_equals_view_by_view_rendering(emulated_host, monkeypatch):
+    """GaussianExtractor.reconstruction over render_part on the emulator (CUDA streams / events / pinned memory
+    replaced by no-ops: the loop's bookkeeping, shapes and view order are what is checked here)."""
+    from partgs_b200.extract import GaussianExtractor, fancy_palette
+    from partgs_b200.renderer import render_part
+    monkeypatch.setattr(torch.cuda, "Stream", _FakeStream)
+    monkeypatch.setattr(torch.cuda, "Event", _FakeEvent)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: _FakeStream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: s)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None)
+    scene = synth.make_point_scene(60, seed=4, S=3, device="cpu")
+    scene["scales"] = scene["scales"] * 4.0
+    cams = synth.make_cameras(2, 16, 16, seed=9, device="cpu")
+    pipe = SimpleNamespace(depth_ratio=1.0, compute_cov3D_python=False, convert_SHs_python=False)
+    pc = _pc(scene)
+    outs = {}
+    ex = GaussianExtractor(pc, render_part, pipe, bg_color=[1, 1, 1], device="cpu")
+    monkeypatch.setattr(ex, "_collect", lambda stacks, mine, V: outs.__setitem__(0, (stacks, mine)))
+    monkeypatch.setattr(ex, "estimate_bounding_sphere", lambda: None)
+    ex.reconstruction(cams)
+    assert outs[0][1] == [0, 1]
+    # camera sharding of the same loop (the gather itself is gloo-tested in test_extract.py)
+    assert GaussianExtractor(pc, render_part, pipe, rank=1, world=2, device="cpu").my_views(5) == [1, 3]
+    pal = fancy_palette(4)
+    bg = torch.ones(3)
+    with torch.no_grad():
+        for rank, (stacks, mine) in outs.items():
+            assert set(stacks) == {"rgbmaps", "partrgbs", "depthmaps", "alphamaps", "normals", "depth_normals"}
+            for slot, vi in enumerate(mine):
+                r = render_part(cams[vi], pc, pipe, bg)
+                assert torch.equal(stacks["rgbmaps"][slot], r["render"])
+                assert torch.equal(stacks["depthmaps"][slot], r["surf_depth"])
+                assert torch.equal(stacks["alphamaps"][slot], r["rend_alpha"])
+                assert torch.equal(stacks["depth_normals"][slot], r["surf_normal"])
+                assert float((stacks["normals"][slot] - extract_oracle.unit_normals(r["rend_normal"])).abs().max()) <= 1e-6
+                want = extract_oracle.partmap_to_rgbmap(r["render_semantic"], pal)
+                assert float((stacks["partrgbs"][slot] != want).float().mean()) <= 1e-3
