@@ -29,17 +29,22 @@
 #define __launch_bounds__(...)
 
 namespace emu {
+// Sense-reversing barrier: spin briefly, then yield (hundreds of OS threads share a few cores, so a waiting thread
+// must give its core away quickly; a mutex + condition variable cost ~10x more per rendezvous here).
 struct Barrier {
-  std::mutex m;
-  std::condition_variable cv;
-  int n = 0, waiting = 0;
-  unsigned long gen = 0;
-  void reset(int count) { n = count; waiting = 0; }
+  std::atomic<int> waiting{0};
+  std::atomic<unsigned> gen{0};
+  int n = 0;
+  void reset(int count) { n = count; waiting.store(0); }
   void wait() {
-    std::unique_lock<std::mutex> lk(m);
-    const unsigned long g = gen;
-    if (++waiting == n) { waiting = 0; gen++; cv.notify_all(); }
-    else cv.wait(lk, [&] { return gen != g; });
+    const unsigned g = gen.load(std::memory_order_acquire);
+    if (waiting.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
+      waiting.store(0, std::memory_order_relaxed);
+      gen.fetch_add(1, std::memory_order_release);
+      return;
+    }
+    for (int spin = 0; gen.load(std::memory_order_acquire) == g; spin++)
+      if (spin > 64) std::this_thread::yield();
   }
 };
 struct WarpState {
