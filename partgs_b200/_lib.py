@@ -204,10 +204,17 @@ def _alloc_cb(nbytes, user):
 ALLOC_CB = ALLOC_FN(_alloc_cb)
 
 
+def on_device(t) -> bool:
+    """The one place that decides whether the library may be handed a tensor's address: CUDA tensors only (there is
+    no CPU fallback).  tests/emu_host.py patches this — and nothing else in the product — to run the Python layer over
+    the CPU-emulated library."""
+    return isinstance(t, torch.Tensor) and t.is_cuda
+
+
 def require_cuda_float(t: torch.Tensor, name: str) -> torch.Tensor:
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name} must be a torch.Tensor")
-    if not t.is_cuda:
+    if not on_device(t):
         raise RuntimeError(f"{name} must be a CUDA tensor")
     if t.dtype != torch.float32:
         t = t.float()

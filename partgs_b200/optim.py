@@ -39,7 +39,7 @@ class FusedAdam(torch.optim.Optimizer):
             for p in group["params"]:
                 if p.grad is None:
                     continue
-                if not (p.is_cuda and p.dtype == torch.float32 and p.grad.dtype == torch.float32):
+                if not (_lib.on_device(p) and p.dtype == torch.float32 and p.grad.dtype == torch.float32):
                     raise RuntimeError("FusedAdam: CUDA float32 parameters and gradients only (no fallback)")
                 if p.grad.is_sparse:
                     raise RuntimeError("FusedAdam does not support sparse gradients")
@@ -79,11 +79,11 @@ def densification_stats(radii, viewspace_grad, xyz_gradient_accum, denom, max_ra
     scene/gaussian_model.py:515-517)."""
     lib = _lib.load()
     P = radii.numel()
-    if not (radii.is_cuda and radii.dtype == torch.int32):
+    if not (_lib.on_device(radii) and radii.dtype == torch.int32):
         raise RuntimeError("radii must be a CUDA int32 tensor")
     g = _lib.require_cuda_float(viewspace_grad, "viewspace_grad")
     for t, nm in ((xyz_gradient_accum, "xyz_gradient_accum"), (denom, "denom"), (max_radii2D, "max_radii2D")):
-        if t is not None and not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == P):
+        if t is not None and not (_lib.on_device(t) and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == P):
             raise RuntimeError(f"{nm} must be a contiguous CUDA float32 tensor with one entry per surfel")
     if g.dim() != 2 or g.size(0) != P or g.size(1) < 3 or g.stride(0) != 3:
         raise RuntimeError("viewspace_grad must be [P,3] contiguous")

@@ -15,7 +15,7 @@ from .. import _lib
 
 def distCUDA2(points: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
-    if not isinstance(points, torch.Tensor) or not points.is_cuda:
+    if not _lib.on_device(points):
         raise RuntimeError("points must be a CUDA tensor")
     if points.dim() != 2 or points.size(1) != 3:
         raise RuntimeError("points must have dimensions (num_points, 3)")

@@ -61,7 +61,7 @@ class _SqToSurfels(torch.autograd.Function):
     def forward(ctx, sq_r, sq_s, sq_t, sq_eps, sq_occ, alpha, scale_raw, eta, omega, faces, ratio, scale_min):
         lib = _lib.load()
         dev = sq_r.device
-        if not sq_r.is_cuda:
+        if not _lib.on_device(sq_r):
             raise RuntimeError("sq_to_surfels needs CUDA tensors (no CPU fallback)")
         B, Vt = eta.shape
         F = faces.shape[1]
@@ -206,7 +206,7 @@ class _RasterizeBlocks(torch.autograd.Function):
                 scale_min, raster_settings, materialize):
         lib = _lib.load()
         dev = sq_r.device
-        if not sq_r.is_cuda:
+        if not _lib.on_device(sq_r):
             raise RuntimeError("rasterize_blocks needs CUDA tensors (no CPU fallback)")
         B, Vt = eta.shape
         F = faces.shape[1]

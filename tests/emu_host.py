@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE: run the product's PYTHON host layer (partgs_b200/*.py: argument marshalling, autograd glue,
 buffer management) on CPU tensors against the emulator build of the whole library (tests/cuda_emu).  The product code
-is not changed: the three places where it touches the CUDA runtime through torch — the "must be a CUDA tensor" guard,
-the current-stream lookup and the device context manager — are patched for the duration of a test."""
+is not changed: the three places where it touches the CUDA runtime through torch — the "is this a CUDA tensor" predicate
+(`_lib.on_device`), the current-stream lookup and the device context manager — are patched for the duration of a test."""
 import contextlib
 import ctypes as C
 import sys
@@ -14,14 +14,6 @@ sys.path.insert(0, str(Path(__file__).parent / "cuda_emu"))
 import build as emu_build  # noqa: E402
 
 from partgs_b200 import _lib  # noqa: E402
-
-
-def _accept_cpu(t, name):
-    if not isinstance(t, torch.Tensor):
-        raise TypeError(f"{name} must be a torch.Tensor")
-    if t.dtype != torch.float32:
-        t = t.float()
-    return t.contiguous()
 
 
 class _NullDevice(contextlib.nullcontext):
@@ -39,7 +31,7 @@ def emulated_host(monkeypatch):
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
     monkeypatch.setattr(_lib, "_lib", lib)
-    monkeypatch.setattr(_lib, "require_cuda_float", _accept_cpu)
+    monkeypatch.setattr(_lib, "on_device", lambda t: isinstance(t, torch.Tensor))
     monkeypatch.setattr(_lib, "current_stream", lambda device: None)
     monkeypatch.setattr(torch.cuda, "device", _NullDevice)
     return lib
