@@ -285,3 +285,90 @@ def test_extraction_loop_equals_view_by_view_rendering(emulated_host, monkeypatc
                 assert float((stacks["normals"][slot] - extract_oracle.unit_normals(r["rend_normal"])).abs().max()) <= 1e-6
                 want = extract_oracle.partmap_to_rgbmap(r["render_semantic"], pal)
                 assert float((stacks["partrgbs"][slot] != want).float().mean()) <= 1e-3
+
+
+def test_optimizer_knn_and_block_model_python_layers(emulated_host):
+    from partgs_b200.optim import FusedAdam, densification_stats
+    from partgs_b200.simple_knn._C import distCUDA2
+    from partgs_b200.superquadric import BlockSurfelModel
+    gen = torch.Generator().manual_seed(0)
+    # FusedAdam == torch.optim.Adam over named groups with different learning rates
+    init = [torch.randn(s, generator=gen) for s in ((200, 3), (200, 1, 3), (200, 2))]
+    pa = [t.clone().requires_grad_(True) for t in init]
+    pb = [t.clone().requires_grad_(True) for t in init]
+    lrs = (1e-3, 2.5e-3, 5e-3)
+    ref = torch.optim.Adam([{"params": [p], "lr": lr} for p, lr in zip(pa, lrs)], lr=0.0, eps=1e-15, foreach=False)
+    ours = FusedAdam([{"params": [p], "lr": lr} for p, lr in zip(pb, lrs)], lr=0.0, eps=1e-15)
+    for _ in range(3):
+        for a, b in zip(pa, pb):
+            g = torch.randn(a.shape, generator=gen)
+            a.grad, b.grad = g.clone(), g.clone()
+        ref.step(); ours.step()
+    for a, b in zip(pa, pb):
+        assert float((a - b).abs().max()) <= 2e-6 * float(a.abs().max())
+        assert int(ours.state[b]["step"]) == 3
+    # densification statistics
+    radii = torch.randint(-1, 9, (200,), generator=gen).int()
+    vg = torch.randn(200, 3, generator=gen)
+    acc, den, mx = torch.zeros(200, 1), torch.zeros(200, 1), torch.zeros(200)
+    densification_stats(radii, vg, acc, den, mx)
+    vis = radii > 0
+    assert torch.equal(den.squeeze(1), vis.float()) and torch.equal(mx[vis], radii[vis].float())
+    assert torch.allclose(acc[vis, 0], vg[vis, :2].norm(dim=1), rtol=1e-6)
+    # distCUDA2
+    pts = torch.randn(300, 3, generator=gen)
+    d = ((pts[:, None].double() - pts[None].double()) ** 2).sum(-1)
+    d.fill_diagonal_(float("inf"))
+    want = d.sort(dim=1).values[:, :3].mean(1)
+    assert torch.allclose(distCUDA2(pts).double(), want, rtol=2e-5)
+    # block model: the accessors the renderer reads, gradients down to the 13 block parameters
+    m = BlockSurfelModel(2, 2, level=1, device="cpu", generator=gen)
+    assert m.get_xyz.shape == (2 * 80 * 2, 3) and m.get_opacity.shape == (320, 1)
+    (m.get_xyz.sum() + m.get_scaling.sum() + m.get_rotation[:, 0].sum()).backward()
+    assert all(getattr(m, k).grad is not None and bool(torch.isfinite(getattr(m, k).grad).all())
+               for k in ("sq_r", "sq_s", "sq_t", "sq_eps"))
+
+
+def test_fused_block_rasteriser_equals_unfused_composition(emulated_host):
+    """north_star (1): surfels generated inside preprocess (pgs_dsr_forward_blocks / _backward_blocks) against
+    sq_to_surfels -> accessors -> GaussianRasterizer, values and gradients down to the block parameters."""
+    import parity_utils as pu
+    from partgs_b200.diff_surfel_rasterization import GaussianRasterizer
+    from partgs_b200.superquadric import BlockSurfelModel, rasterize_blocks, sq_to_surfels
+    gen = torch.Generator().manual_seed(11)
+    model = BlockSurfelModel(2, 2, level=1, device="cpu", generator=gen)
+    P = 2 * model.per_gs_num
+    shs0 = torch.zeros(P, 16, 3)
+    shs0[:, 0] = synth.RGB2SH(torch.rand(P, 3, generator=gen))
+    shs0[:, 1:] = 0.05 * torch.randn(P, 15, 3, generator=gen)
+    W, H = 40, 24
+    cam = synth.make_cameras(1, W, H, 5, device="cpu")[0]
+    g = synth.upstream_grads(W, H, 6, device="cpu")
+    settings = pu.settings_from_cam(cam, torch.tensor([0.1, 0.2, 0.3]))
+    names = ("sq_r", "sq_s", "sq_t", "sq_eps", "sq_occ")
+    pa = {n: getattr(model, n).detach().clone().requires_grad_(True) for n in names}
+    shs_a = shs0.clone().requires_grad_(True)
+    _, xyz, scaling, rotation, opacity = sq_to_surfels(pa["sq_r"], pa["sq_s"], pa["sq_t"], pa["sq_eps"], pa["sq_occ"],
+                                                       model.alpha, model._scale, model.sq_eta, model.sq_omega,
+                                                       model.faces)
+    m2d_a = torch.zeros_like(xyz, requires_grad=True)
+    col_a, radii_a, all_a = GaussianRasterizer(settings)(means3D=xyz, means2D=m2d_a, opacities=opacity, shs=shs_a,
+                                                         scales=torch.exp(scaling), rotations=rotation)
+    torch.autograd.backward([col_a, all_a], [g["color"], g["allmap"]])
+    pb = {n: getattr(model, n).detach().clone().requires_grad_(True) for n in names}
+    shs_b = shs0.clone().requires_grad_(True)
+    m2d_b = torch.zeros_like(xyz, requires_grad=True)
+    out = rasterize_blocks(settings, pb["sq_r"], pb["sq_s"], pb["sq_t"], pb["sq_eps"], pb["sq_occ"], model.alpha,
+                           model._scale, shs_b, model.sq_eta, model.sq_omega, model.faces, means2D=m2d_b,
+                           materialize=True)
+    col_b, radii_b, all_b, _verts, xyz_b, scaling_b, rot_b, opa_b = out
+    torch.autograd.backward([col_b, all_b], [g["color"], g["allmap"]])
+    assert int((radii_b > 0).sum()) > 20
+    assert pu.rel_err(xyz_b, xyz) <= 1e-6 and pu.rel_err(scaling_b, scaling) <= 1e-6
+    assert pu.rel_err(rot_b, rotation) <= 1e-6 and pu.rel_err(opa_b, opacity) <= 1e-6
+    assert int((radii_a != radii_b).sum()) <= 1
+    assert rel(col_b.detach().numpy(), col_a.detach().numpy()) <= 2e-5
+    assert rel(all_b.detach().numpy(), all_a.detach().numpy()) <= 1e-4
+    for n in names:
+        assert pu.rel_err(pb[n].grad, pa[n].grad) <= 1e-3, n
+    assert pu.rel_err(shs_b.grad, shs_a.grad) <= 1e-3 and pu.rel_err(m2d_b.grad, m2d_a.grad) <= 1e-3
