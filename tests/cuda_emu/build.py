@@ -138,11 +138,16 @@ def build_reference(fork: str = "part") -> Path:
     CudaRasterizer::Rasterizer::forward / backward.  Build container only; used by tools/make_golden_ref_emu.py."""
     from concurrent.futures import ThreadPoolExecutor
     _require_toolchain()
-    sub = {"part": "diff-surfel-rasterization_part", "base": "diff-surfel-rasterization"}[fork]
-    ref = Path("/root/reference/submodules") / sub / "cuda_rasterizer"
+    if fork == "knn":
+        ref = Path("/root/reference/submodules/simple-knn")
+        names = ("simple_knn.cu",)
+    else:
+        sub = {"part": "diff-surfel-rasterization_part", "base": "diff-surfel-rasterization"}[fork]
+        ref = Path("/root/reference/submodules") / sub / "cuda_rasterizer"
+        names = ("forward.cu", "backward.cu", "rasterizer_impl.cu")
     if not ref.is_dir():
         raise EmuUnavailable(f"{ref} not found (reference tree not mounted)")
-    srcs = [ref / n for n in ("forward.cu", "backward.cu", "rasterizer_impl.cu")]
+    srcs = [ref / n for n in names]
     wrap = HERE / f"ref_wrap_{fork}.cpp"
     h = hashlib.sha1()
     for f in srcs + sorted(ref.glob("*.h")) + [wrap, HERE / "emu.h", HERE / "emu_runtime.cpp"] + \

@@ -18,6 +18,16 @@ struct DeviceScan {
     return cudaSuccess;
   }
 };
+struct DeviceReduce {
+  template <typename In, typename Out, typename Op, typename T>
+  static cudaError_t Reduce(void* temp, size_t& temp_bytes, In in, Out out, int n, Op op, T init) {
+    if (temp == nullptr) { temp_bytes = 16; return cudaSuccess; }
+    T acc = init;
+    for (int i = 0; i < n; i++) acc = op(acc, in[i]);
+    *out = acc;
+    return cudaSuccess;
+  }
+};
 struct DeviceRadixSort {
   template <typename K, typename V>
   static cudaError_t SortPairs(void* temp, size_t& temp_bytes, const K* keys_in, K* keys_out, const V* vals_in,

@@ -215,3 +215,19 @@ def test_emulated_regularizers_match_the_oracle(emu, with_mask):
         assert ga[0, 0, 0] == 0 and ga[0, 0, 1] == 0 and ga[0, 0, 2] == 0 and ga[0, 0, 3] == 0 and ga[0, 0, 5] != 0
     else:
         assert not ga.any() and alpha.grad is None
+
+
+def test_emulated_dist2_matches_the_emulated_reference(emu):
+    """distCUDA2 against the reference's own simple_knn.cu run on the emulator (tests/golden/ref_emu_knn.npz):
+    uniform, clustered + outliers, coincident points, and the fewer-than-four-points cases."""
+    z = np.load(Path(__file__).parent / "golden" / "ref_emu_knn.npz")
+    for name in sorted(k[:-7] for k in z.files if k.endswith("_points")):
+        pts = np.ascontiguousarray(z[name + "_points"])
+        want = z[name + "_dist2"]
+        P = pts.shape[0]
+        out = np.full(P, np.nan, np.float32)
+        temp = np.zeros(emu.pgs_knn_temp_bytes(P) + 256, np.uint8)
+        assert emu.pgs_knn_dist2(P, _p(pts), _p(out), (temp.ctypes.data + 255) // 256 * 256, None) >= 0, name
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isfinite(out), fin), name
+        np.testing.assert_allclose(out[fin], want[fin], rtol=2e-6, atol=1e-12, err_msg=name)

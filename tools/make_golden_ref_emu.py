@@ -110,7 +110,28 @@ def make_base(lib, name, P, W, H, seed, degree=3, scale_mul=3.0, precomp=False, 
           all(np.isfinite(v).all() for v in d.values()))
 
 
+def make_knn(lib):
+    """distCUDA2 = SimpleKNN::knn of the reference, on point sets that exercise its box pruning: uniform, tightly
+    clustered + outliers, coincident points, and fewer than four points (FLT_MAX placeholders stay in the mean)."""
+    g = np.random.default_rng(7)
+    sets = {"uniform_1500": g.normal(size=(1500, 3)),
+            "clustered_1100": np.concatenate([g.normal(size=(1000, 3)) * 0.01 + 3.0, g.normal(size=(100, 3)) * 5.0]),
+            "duplicates_40": np.repeat(g.normal(size=(10, 3)), 4, axis=0),
+            "p3": g.normal(size=(3, 3)), "p2": g.normal(size=(2, 3)), "p1": g.normal(size=(1, 3)),
+            "p1025": g.random(size=(1025, 3))}
+    out = {}
+    for name, pts in sets.items():
+        pts = np.ascontiguousarray(pts, dtype=np.float32)
+        d = np.full(pts.shape[0], np.nan, np.float32)
+        lib.ref_knn(pts.shape[0], _p(pts), _p(d))
+        out[name + "_points"], out[name + "_dist2"] = pts, d
+    path = ROOT / "tests" / "golden" / "ref_emu_knn.npz"
+    np.savez_compressed(path, **out)
+    print(path, {k: (v.shape, float(np.nanmax(v))) for k, v in out.items() if k.endswith("dist2")})
+
+
 if __name__ == "__main__":
+    make_knn(C.CDLL(str(emu_build.build_reference("knn"))))
     base = C.CDLL(str(emu_build.build_reference("base")))
     make_base(base, "p300_48x32", P=300, W=48, H=32, seed=61)
     make_base(base, "p400_40x24_deg2", P=400, W=40, H=24, seed=62, degree=2)
