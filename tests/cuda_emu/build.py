@@ -84,6 +84,16 @@ def build(cu_name: str, exports: str) -> Path:
     return so
 
 
+def _sanitize_flags():
+    """PGS_EMU_SANITIZE=address|thread builds the emulated library with that sanitizer (run pytest with the matching
+    runtime preloaded, see tools/emu_sanitize.sh): memcheck / racecheck of the kernels on the CPU."""
+    import os
+    kind = os.environ.get("PGS_EMU_SANITIZE", "")
+    if kind not in ("address", "thread"):
+        return "", []
+    return "_" + kind, [f"-fsanitize={kind}", "-fno-omit-frame-pointer", "-g"]
+
+
 def build_full() -> Path:
     """The WHOLE product library (every partgs_b200/csrc/*.cu, including the C-ABI layer api.cu) for the emulator:
     same exported `pgs_*` symbols as libpartgs_b200.so, host memory instead of device memory, synchronous streams."""
@@ -95,7 +105,8 @@ def build_full() -> Path:
     h = hashlib.sha1()
     for f in srcs + hdrs:
         h.update(f.read_bytes())
-    tag = h.hexdigest()[:16]
+    suffix, san = _sanitize_flags()
+    tag = h.hexdigest()[:16] + suffix
     OUT.mkdir(exist_ok=True)
     so = OUT / f"libpartgs_b200_emu_{tag}.so"
     if so.exists():
@@ -103,7 +114,7 @@ def build_full() -> Path:
     work = OUT / f"full_{tag}"
     work.mkdir(exist_ok=True)
     flags = ["-std=c++17", "-O1", "-fPIC", "-pthread", "-w", "-ffp-contract=off", "-DPGS_EMU", f"-I{HERE}", f"-I{CSRC}",
-             f"-I{CUDA_INC}", "-include", "emu.h"]
+             f"-I{CUDA_INC}", "-include", "emu.h", *san]
 
     def compile_one(src: Path) -> Path:
         body = rewrite_launches(src.read_text())
@@ -120,12 +131,12 @@ def build_full() -> Path:
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, srcs))
     rt = work / "emu_runtime.o"
-    res = subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-w", f"-I{CUDA_INC}", "-c", str(HERE / "emu_runtime.cpp"),
-                          "-o", str(rt)], capture_output=True, text=True)
+    res = subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-w", *san, f"-I{CUDA_INC}", "-c",
+                          str(HERE / "emu_runtime.cpp"), "-o", str(rt)], capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("emulator runtime build failed:\n" + res.stderr[-3000:])
-    res = subprocess.run(["g++", "-shared", "-pthread", "-Wl,-Bsymbolic", "-o", str(so), *map(str, objs), str(rt)], capture_output=True,
-                         text=True)
+    res = subprocess.run(["g++", "-shared", "-pthread", "-Wl,-Bsymbolic", *san, "-o", str(so), *map(str, objs), str(rt)],
+                         capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("emulator link failed:\n" + res.stderr[-3000:])
     return so
