@@ -69,14 +69,15 @@ def build(cu_name: str, exports: str) -> Path:
     assert "<<<" not in body, "unconverted kernel launch"
     tu = ('#include "emu.h"\nnamespace pgs { void count_launch(int) {} }\n' + body + "\n" + exports + "\n")
     deps = "".join(p.read_text() for p in [HERE / "emu.h", CSRC / "common.cuh", CSRC / "kernels.h"])
-    tag = hashlib.sha1((tu + deps).encode()).hexdigest()[:16]
+    suffix, san = _sanitize_flags()
+    tag = hashlib.sha1((tu + deps).encode()).hexdigest()[:16] + suffix
     OUT.mkdir(exist_ok=True)
     so = OUT / f"{Path(cu_name).stem}_{tag}.so"
     if so.exists():
         return so
     cpp = OUT / f"{Path(cu_name).stem}_{tag}.cpp"
     cpp.write_text(tu)
-    cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-Wl,-Bsymbolic", "-w", "-ffp-contract=off", f"-I{HERE}",
+    cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-Wl,-Bsymbolic", "-w", "-ffp-contract=off", *san, f"-I{HERE}",
            f"-I{CSRC}", f"-I{CUDA_INC}", str(cpp), "-o", str(so)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -6,10 +6,10 @@
 kind=${1:-address}; shift
 lib=$(gcc -print-file-name=lib$([ "$kind" = thread ] && echo tsan || echo asan).so)
 log=/tmp/emu_sanitize_${kind}.log
-tests=${@:-tests/test_emu_raster.py tests/test_emu_part.py tests/test_emu_ops.py tests/test_emu_host_layer.py tests/test_emu_training_loop.py}
+if [ $# -eq 0 ]; then set -- tests/test_emu_raster.py tests/test_emu_part.py tests/test_emu_ops.py tests/test_emu_host_layer.py tests/test_emu_training_loop.py; fi
 PGS_EMU_SANITIZE=$kind LD_PRELOAD=$lib ASAN_OPTIONS=detect_leaks=0:halt_on_error=0 \
   TSAN_OPTIONS=halt_on_error=0:report_signal_unsafe=0:history_size=2 \
-  python -m pytest $tests -q -s -p no:cacheprovider > $log 2>&1
+  python -m pytest "$@" -q -s -p no:cacheprovider > $log 2>&1
 echo "pytest rc=$?  (log: $log)"
 echo "sanitizer reports inside the emulated library:"
 grep -E "ERROR: AddressSanitizer|WARNING: ThreadSanitizer" $log | sort | uniq -c | head
