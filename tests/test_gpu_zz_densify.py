@@ -15,7 +15,7 @@ import torch
 from oracle import densify_oracle
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(strict=False, reason="densify kernels not yet run on a B200 (round-1 GPU budget spent)")]
+              pytest.mark.xfail(strict=False, reason="densify kernels: green on the CPU emulator (tests/test_emu_zz_mirror.py), first run on a B200 pending")]
 DEV = "cuda"
 NAMES = densify_oracle.PARAM_NAMES
 GOLDEN = sorted((Path(__file__).parent / "golden").glob("densify_*.npz"))

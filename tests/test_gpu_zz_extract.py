@@ -15,7 +15,7 @@ import torch
 from oracle import extract_oracle
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(strict=False, reason="extraction kernels not yet run on a B200 (round-1 GPU budget spent)")]
+              pytest.mark.xfail(strict=False, reason="extraction kernels: green on the CPU emulator (tests/test_emu_zz_mirror.py), first run on a B200 pending")]
 DEV = "cuda"
 Z = np.load(Path(__file__).parent / "golden" / "extract_maps.npz")
 

@@ -9,7 +9,7 @@ import torch
 from oracle import loss_oracle
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(strict=False, reason="regulariser kernels not yet run on a B200 (round-1 GPU budget spent)")]
+              pytest.mark.xfail(strict=False, reason="regulariser kernels: green on the CPU emulator (tests/test_emu_zz_mirror.py), first run on a B200 pending")]
 DEV = "cuda"
 
 
