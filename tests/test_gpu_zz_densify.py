@@ -1,10 +1,12 @@
 """GPU parity of the planned-compaction densification (csrc/densify.cu) against the torch restatement of the
 reference (oracle/densify_oracle.py, itself pinned bit-exactly by golden vectors of the unmodified reference classes).
 
-STATUS: these kernels were written after this round's GPU budget was spent — they compile for sm_100a and the
-algorithm is checked on CPU (tests/test_densify_plan_model.py), but this file has not yet run on a B200.  Until it
-has, its tests are non-strict xfail (a pass shows up as XPASS, a failure cannot hide the verified suites) and the
-file sorts after every other GPU test.  Remove the marker once green on hardware.
+STATUS: these kernels were written after this round's GPU budget was spent.  Their source runs on the CPU lock-step
+emulator against the reference golden vectors (tests/test_emu_densify.py), the Python layer and this very file run on
+it too (tests/test_emu_host_layer.py, tests/test_emu_zz_mirror.py), memcheck / racecheck are clean there — but the
+file has not yet run on a B200.  Until it has, its tests are non-strict xfail (a pass shows up as XPASS, a failure
+cannot hide the verified suites) and the file sorts after every other GPU test.  Remove the marker once green on
+hardware.
 """
 from pathlib import Path
 
