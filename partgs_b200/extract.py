@@ -184,9 +184,18 @@ class GaussianExtractor(object):
                 setattr(self, k, v)
             return
         import torch.distributed as dist
-        names = [k for k in MAP_NAMES if k in stacks]
+        # a rank without views (more ranks than cameras) has no stacks of its own: agree on the maps and their shapes
+        # first, so that every rank takes part in every gather
+        meta = [None] * self.world
+        dist.all_gather_object(meta, {k: tuple(v.shape[1:]) for k, v in stacks.items()}, group=self.group)
+        shapes = {}
+        for m in meta:
+            shapes.update(m)
+        names = [k for k in MAP_NAMES if k in shapes]
         for k in names:
-            local = stacks[k]
+            local = stacks.get(k)
+            if local is None:
+                local = torch.empty((0,) + shapes[k], dtype=torch.float32)
             per_rank = [len(shard_views(V, r, self.world)) for r in range(self.world)]
             pad = max(per_rank)
             buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype)

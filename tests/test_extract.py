@@ -72,10 +72,10 @@ def _worker(rank, world, port, V, out):
         per_view = [_view_maps(v) for v in mine]
         stacks = {k: torch.stack([m[k] for m in per_view]) for k in per_view[0]}
     else:
-        stacks = {k: torch.empty((0,) + tuple(v.shape)) for k, v in _view_maps(0).items()}
+        stacks = {}   # what reconstruction() has on a rank without views
     ex._collect(stacks, mine, V)
     if rank == 0:
-        out["maps"] = {k: getattr(ex, k) for k in stacks}
+        out["maps"] = {k: getattr(ex, k) for k in _view_maps(0)}
     dist.barrier()
     dist.destroy_process_group()
 
