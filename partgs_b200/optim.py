@@ -91,3 +91,113 @@ def densification_stats(radii, viewspace_grad, xyz_gradient_accum, denom, max_ra
         rc = lib.pgs_densify_stats(P, radii.data_ptr(), g.data_ptr(), _lib.ptr(max_radii2D),
                                    xyz_gradient_accum.data_ptr(), denom.data_ptr(), _lib.current_stream(radii.device))
     _lib.check(rc, "pgs_densify_stats")
+
+
+class ShardedFusedAdam:
+    """Data-parallel Adam with the optimiser state sharded over the ranks (SURVEY.md §8(e) "alternative to evaluate",
+    §8(f) rank 3): instead of all-reducing the 232 B/surfel gradient bucket and running the same Adam step on every
+    rank, the gradients are **reduce-scattered**, every rank updates only its 1/W slice of the parameters (and keeps
+    only that slice of ``exp_avg / exp_avg_sq``: 1/W of the 464 B/surfel optimiser state), and the updated slices are
+    **all-gathered**.  Same bytes on the wire as an all-reduce, 1/W of the optimiser work and state per rank.
+
+    All parameters live in ONE flat float32 buffer (``self.flat``); the tensors handed in are re-pointed at views of
+    it (``p.data``), and ``p.grad`` at views of a second flat buffer that autograd accumulates into in place — so
+    the collectives move one contiguous range each and no gather / scatter copies exist.  The update itself is the
+    library's one-launch Adam (``pgs_adam_step``): one table entry per (parameter ∩ my slice), each with its group's
+    learning rate.  ``param_groups`` keeps the ``{"name", "lr"}`` entries the reference's schedulers write to
+    (scene/gaussian_model.py:268-275).  Arithmetic = torch.optim.Adam(eps=1e-15) on the rank-summed gradient.
+    """
+
+    def __init__(self, named_params, betas=(0.9, 0.999), eps=1e-15, group=None, average: bool = False):
+        import torch.distributed as dist
+        self._dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.betas, self.eps, self.average = betas, eps, average
+        self.param_groups = []
+        params = []
+        for g in named_params:
+            if len(g["params"]) != 1:
+                raise RuntimeError("ShardedFusedAdam: one tensor per group (as in training_setup)")
+            p = g["params"][0]
+            if not (_lib.on_device(p) and p.dtype == torch.float32):
+                raise RuntimeError("ShardedFusedAdam: CUDA float32 parameters only (no fallback)")
+            params.append(p)
+            self.param_groups.append({"name": g.get("name"), "lr": float(g.get("lr", 0.0)), "params": [p]})
+        dev = params[0].device
+        align = 64 * self.world
+        self.offsets, total = [], 0
+        for p in params:
+            self.offsets.append(total)
+            total += (p.numel() + 63) // 64 * 64
+        self.numel = (total + align - 1) // align * align
+        self.slice = self.numel // self.world
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(params, self.offsets):
+                self.flat[o:o + p.numel()].copy_(p.detach().reshape(-1))
+                p.data = self.flat[o:o + p.numel()].view(p.shape)
+                p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+        lo = self.rank * self.slice
+        self.exp_avg = torch.zeros(self.slice, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(self.slice, dtype=torch.float32, device=dev)
+        self.grad_slice = torch.zeros(self.slice, dtype=torch.float32, device=dev)
+        self.step_count = 0
+        self._lo = lo
+
+    def zero_grad(self, set_to_none: bool = False):
+        """Gradients are views of the flat buffer that autograd accumulates into in place: they are zeroed and
+        re-attached, never dropped (``set_to_none`` is accepted for signature compatibility and ignored)."""
+        self.flat_grad.zero_()
+        for g, o in zip(self.param_groups, self.offsets):
+            p = g["params"][0]
+            p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+
+    @torch.no_grad()
+    def step(self):
+        lib = _lib.load()
+        dist, W = self._dist, self.world
+        lo, hi = self._lo, self._lo + self.slice
+        # 1. my slice of the rank-summed gradient
+        if W > 1:
+            backend = dist.get_backend(self.group)
+            if backend == "nccl":
+                dist.reduce_scatter_tensor(self.grad_slice, self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            else:  # gloo (CPU tests) has no reduce-scatter: all-reduce, then take the slice
+                dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+                self.grad_slice.copy_(self.flat_grad[lo:hi])
+            if self.average:
+                self.grad_slice.div_(W)
+        else:
+            self.grad_slice.copy_(self.flat_grad[lo:hi])
+        # 2. one-launch Adam over (parameter ∩ my slice), each piece with its group's learning rate
+        self.step_count += 1
+        beta1, beta2 = self.betas
+        bc1 = 1 - beta1 ** self.step_count
+        bc2_sqrt = (1 - beta2 ** self.step_count) ** 0.5
+        pieces = []
+        for g, o in zip(self.param_groups, self.offsets):
+            a, b = max(o, lo), min(o + g["params"][0].numel(), hi)
+            if a < b:
+                pieces.append((a, b - a, g["lr"] / bc1))
+        dev = self.flat.device
+        base_p, base_g = self.flat.data_ptr(), self.grad_slice.data_ptr()
+        base_m, base_v = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+        for s0 in range(0, len(pieces), _MAX):
+            chunk = pieces[s0:s0 + _MAX]
+            n = len(chunk)
+            pa = (C.c_void_p * n)(*[base_p + 4 * a for a, _, _ in chunk])
+            ga = (C.c_void_p * n)(*[base_g + 4 * (a - lo) for a, _, _ in chunk])
+            ma = (C.c_void_p * n)(*[base_m + 4 * (a - lo) for a, _, _ in chunk])
+            va = (C.c_void_p * n)(*[base_v + 4 * (a - lo) for a, _, _ in chunk])
+            na = (C.c_size_t * n)(*[cnt for _, cnt, _ in chunk])
+            sa = (C.c_float * n)(*[ss for _, _, ss in chunk])
+            with torch.cuda.device(dev):
+                rc = lib.pgs_adam_step(n, pa, ga, ma, va, na, sa, float(beta1), float(beta2), float(self.eps),
+                                       float(bc2_sqrt), _lib.current_stream(dev))
+            _lib.check(rc, "pgs_adam_step")
+        # 3. everybody gets every updated slice
+        if W > 1:
+            dist.all_gather_into_tensor(self.flat, self.flat[lo:hi].clone(), group=self.group)
