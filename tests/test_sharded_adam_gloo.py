@@ -38,7 +38,9 @@ def _grad(k, rank, step):
     return torch.randn(SHAPES[k], generator=g) * (0.1 if step != 1 else 10.0)
 
 
-def _patch_emulated_library():
+def _patch_emulated_library(monkeypatch=None):
+    """In a spawned rank: plain assignment (the process ends with the test).  In the pytest process: through
+    `monkeypatch`, so that nothing leaks into other tests."""
     import contextlib
     import build as emu_build
     from partgs_b200 import _lib
@@ -46,14 +48,15 @@ def _patch_emulated_library():
     for name, (res, args) in _lib.SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    _lib._lib = lib
-    _lib.on_device = lambda t: isinstance(t, torch.Tensor)
-    _lib.current_stream = lambda device: None
 
     class _Null(contextlib.nullcontext):
         def __init__(self, *a, **k):
             super().__init__()
-    torch.cuda.device = _Null
+    put = (lambda o, n, v: setattr(o, n, v)) if monkeypatch is None else monkeypatch.setattr
+    put(_lib, "_lib", lib)
+    put(_lib, "on_device", lambda t: isinstance(t, torch.Tensor))
+    put(_lib, "current_stream", lambda device: None)
+    put(torch.cuda, "device", _Null)
 
 
 def _worker(rank, world, port, out):
@@ -106,3 +109,66 @@ def test_sharded_adam_equals_adam_on_the_summed_gradients():
     assert torch.equal(out[0][3]["rotation"], _init()["rotation"])      # lr 0: untouched on every rank
     for k in SHAPES:
         assert torch.equal(out[0][3][k], out[1][3][k])                 # replicas stay bit-identical
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the camera-sharded step of SURVEY 8(e) with the REAL rasteriser (emulated) on two gloo ranks
+# ---------------------------------------------------------------------------------------------------------------
+def _render_loss(params, cam, upstream):
+    from partgs_b200.diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    settings = GaussianRasterizationSettings(
+        image_height=cam.image_height, image_width=cam.image_width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+        bg=torch.zeros(3), scale_modifier=1.0, viewmatrix=cam.viewmatrix, projmatrix=cam.projmatrix, sh_degree=3,
+        campos=cam.campos, prefiltered=False, debug=False)
+    means2D = torch.zeros_like(params["means3D"], requires_grad=True)
+    color, _radii, allmap = GaussianRasterizer(settings)(
+        means3D=params["means3D"], means2D=means2D, opacities=params["opacities"], shs=params["shs"],
+        scales=params["scales"], rotations=params["rotations"])
+    return (color * upstream["color"]).sum() + (allmap * upstream["allmap"]).sum()
+
+
+def _scene_and_views(n_views):
+    from partgs_b200 import synth
+    scene = synth.make_point_scene(120, seed=3, device="cpu")
+    scene["scales"] = scene["scales"] * 3.0
+    cams = synth.make_cameras(n_views, 32, 16, seed=4, device="cpu")
+    ups = [synth.upstream_grads(32, 16, 50 + v, device="cpu") for v in range(n_views)]
+    return scene, cams, ups
+
+
+def _raster_worker(rank, world, port, n_views, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _patch_emulated_library()
+    from partgs_b200.dist import GradAllReducer, sharded_step
+    scene, cams, ups = _scene_and_views(n_views)
+    params = {k: scene[k].clone().requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    total, mine = sharded_step(lambda v: _render_loss(params, cams[v], ups[v]), params, n_views, GradAllReducer())
+    out[rank] = (mine, {k: p.grad.clone() for k, p in params.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_camera_sharded_step_with_the_real_rasteriser(monkeypatch):
+    """Views shard by camera, parameters are replicated, the five parameter gradients are summed over the ranks:
+    equal to one process back-propagating all views — with the product's own kernels (emulated)."""
+    import build as emu_build
+    try:
+        emu_build.build_full()
+    except emu_build.EmuUnavailable as ex:
+        pytest.skip(str(ex))
+    world, n_views = 2, 3
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_raster_worker, args=(world, _free_port(), n_views, out), nprocs=world, join=True)
+    _patch_emulated_library(monkeypatch)
+    scene, cams, ups = _scene_and_views(n_views)
+    params = {k: scene[k].clone().requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    for v in range(n_views):
+        _render_loss(params, cams[v], ups[v]).backward()
+    assert out[0][0] == [0, 2] and out[1][0] == [1]
+    for rank in range(world):
+        for k, p in params.items():
+            got = out[rank][1][k]
+            assert float((got - p.grad).abs().max()) <= 2e-5 * (float(p.grad.abs().max()) + 1e-12), (rank, k)
