@@ -37,3 +37,11 @@ def lib():
     if not _lib.LIB_PATH.exists():
         build.build()
     return _lib.load()
+
+
+def pytest_runtest_logreport(report):
+    """PGS_INSTAFAIL=1: print a failure's traceback as soon as the test ends (short GPU calls under a hard time limit
+    keep what was printed, not what pytest would have summarised at the end)."""
+    import os
+    if os.environ.get("PGS_INSTAFAIL") and report.failed:
+        print("\n[instafail] " + report.nodeid + "\n" + str(report.longrepr)[-3000:], flush=True)

@@ -1,12 +1,10 @@
 """GPU parity of the planned-compaction densification (csrc/densify.cu) against the torch restatement of the
 reference (oracle/densify_oracle.py, itself pinned bit-exactly by golden vectors of the unmodified reference classes).
 
-STATUS: these kernels were written after this round's GPU budget was spent.  Their source runs on the CPU lock-step
-emulator against the reference golden vectors (tests/test_emu_densify.py), the Python layer and this very file run on
-it too (tests/test_emu_host_layer.py, tests/test_emu_zz_mirror.py), memcheck / racecheck are clean there — but the
-file has not yet run on a B200.  Until it has, its tests are non-strict xfail (a pass shows up as XPASS, a failure
-cannot hide the verified suites) and the file sorts after every other GPU test.  Remove the marker once green on
-hardware.
+STATUS: written without GPU access — the kernel source, the Python layer and this very file were first verified on the
+CPU lock-step emulator (tests/test_emu_densify.py, tests/test_emu_host_layer.py, tests/test_emu_zz_mirror.py; memcheck /
+racecheck clean there) — and then passed on a B200 on their first hardware run (profiles/r1_gpu_pytest_new_kernels.log,
+19 passed across the three test_gpu_zz_* files).  The former non-strict xfail marker is gone.
 """
 from pathlib import Path
 
@@ -16,8 +14,7 @@ import torch
 
 from oracle import densify_oracle
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(strict=False, reason="densify kernels: green on the CPU emulator (tests/test_emu_zz_mirror.py), first run on a B200 pending")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 DEV = "cuda"
 NAMES = densify_oracle.PARAM_NAMES
 GOLDEN = sorted((Path(__file__).parent / "golden").glob("densify_*.npz"))

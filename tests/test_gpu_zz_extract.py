@@ -2,9 +2,8 @@
 against the torch restatement (oracle/extract_oracle.py, pinned by golden vectors of the reference's own
 partmap_to_rgbmap) and against view-by-view calls of render_part.
 
-STATUS: written after this round's GPU budget was spent; compiles for sm_100a, CPU-side logic tested
-(tests/test_extract.py), not yet run on a B200 -> non-strict xfail, sorted after every verified GPU suite.  Remove
-the marker once green on hardware."""
+STATUS: written without GPU access; first verified on the CPU emulator (tests/test_extract.py,
+tests/test_emu_zz_mirror.py), then green on a B200 on its first hardware run (profiles/r1_gpu_pytest_new_kernels.log)."""
 from pathlib import Path
 from types import SimpleNamespace
 
@@ -14,8 +13,7 @@ import torch
 
 from oracle import extract_oracle
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(strict=False, reason="extraction kernels: green on the CPU emulator (tests/test_emu_zz_mirror.py), first run on a B200 pending")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 DEV = "cuda"
 Z = np.load(Path(__file__).parent / "golden" / "extract_maps.npz")
 

@@ -1,15 +1,14 @@
 """GPU parity of the fused per-pixel regularisers (csrc/regularizers.cu, partgs_b200.losses.geometric_regularizers)
 against the torch restatement of train.py:234-251 (oracle/loss_oracle.py).
 
-STATUS: written after this round's GPU budget was spent; the kernel source passes on the CPU emulator
-(tests/test_emu_ops.py) but has not yet run on a B200 -> non-strict xfail, sorted after the verified GPU suites."""
+STATUS: written without GPU access; first verified on the CPU emulator (tests/test_emu_ops.py,
+tests/test_emu_zz_mirror.py), then green on a B200 on its first hardware run (profiles/r1_gpu_pytest_new_kernels.log)."""
 import pytest
 import torch
 
 from oracle import loss_oracle
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(strict=False, reason="regulariser kernels: green on the CPU emulator (tests/test_emu_zz_mirror.py), first run on a B200 pending")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 DEV = "cuda"
 
 

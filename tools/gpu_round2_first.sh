@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of round 2: everything that was written after round 1's GPU budget ran out.
-#   1. the hardware parity tests of the new kernels (densification, extraction epilogue / loop, regularisers) — they are
-#      non-strict xfail until this has been green once: look for XPASS / xfailed in the log, fix, drop the markers;
+#   1. the hardware parity tests of the kernels written on the emulator (densification, extraction epilogue / loop,
+#      regularisers; green on a B200 since the last call of round 1, profiles/r1_gpu_pytest_new_kernels.log);
 #   2. the whole verified GPU suite + smoke (nothing on the render path changed, this is the regression check);
 #   3. timing rows for the new ops against the reference's torch sequences (tools/time_rank34.py);
 #   4. compute-sanitizer memcheck over the new GPU tests.
@@ -10,11 +10,11 @@ tag=${1:-r2a}
 out=gpurun_out
 mkdir -p $out
 timeout 600 python -m pytest tests/test_gpu_zz_densify.py tests/test_gpu_zz_extract.py tests/test_gpu_zz_regularizers.py \
-    -q -rxXs --runxfail > $out/${tag}_new_kernels.log 2>&1; echo "new kernels rc=$?" | tee -a $out/${tag}_new_kernels.log
+    -q -rxXs > $out/${tag}_new_kernels.log 2>&1; echo "new kernels rc=$?" | tee -a $out/${tag}_new_kernels.log
 tail -30 $out/${tag}_new_kernels.log
 timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $out/${tag}_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" | tee -a $out/${tag}_smoke.log
 timeout 600 python tools/time_rank34.py > $out/${tag}_rank34.jsonl 2> $out/${tag}_rank34.err; cut -c1-300 $out/${tag}_rank34.jsonl
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_zz_densify.py \
-    tests/test_gpu_zz_regularizers.py -q --runxfail -k "golden or 5_000 or 77" > $out/${tag}_memcheck.log 2>&1
+    tests/test_gpu_zz_regularizers.py -q -k "golden or 5_000 or 77" > $out/${tag}_memcheck.log 2>&1
 echo "memcheck rc=$?" | tee -a $out/${tag}_memcheck.log; tail -5 $out/${tag}_memcheck.log
