@@ -37,44 +37,58 @@ def _load(name, path):
     return mod
 
 
+_NAMESPACES = ("diff_surfel_rasterization", "diff_surfel_rasterization_part", "scene", "utils", "renderer",
+               "ref_gaussian_renderer", "ref_gaussian_renderer_2d")
+_ABSENT_THIRD_PARTY = ("open3d", "seaborn", "matplotlib", "matplotlib.pyplot", "matplotlib.colors", "mediapy",
+                       "pytorch3d", "pytorch3d.renderer", "plyfile", "trimesh")
+
+
 @pytest.fixture()
 def reference_callers(emulated_host, monkeypatch):
-    """The two reference renderer modules, imported from where they lie, with `diff_surfel_rasterization[_part]`
-    resolving to the drop-in shims.  `scene.gaussian_model` (only a type annotation there; it drags in plyfile,
-    simple_knn, ...) is a stub; `utils.sh_utils` / `utils.point_utils` are the reference's own files."""
+    """The reference's renderer modules and its GaussianExtractor, imported from where they lie, with
+    `diff_surfel_rasterization[_part]` resolving to the drop-in shims.  `utils` is the reference's own package
+    (sh_utils, point_utils, mesh_utils, ...); `scene.gaussian_model` (only a type annotation in the renderers; it
+    drags in plyfile, simple_knn, ...) is a stub; third-party packages absent from this image (open3d, seaborn,
+    matplotlib, mediapy, pytorch3d — none is executed on this path) are placeholders."""
+    from unittest.mock import MagicMock
     monkeypatch.syspath_prepend(str(ROOT / "partgs_b200" / "dropin"))
-    for name in [m for m in sys.modules if m.split(".")[0] in ("diff_surfel_rasterization",
-                                                               "diff_surfel_rasterization_part", "scene", "utils")]:
+    for name in [m for m in sys.modules if m.split(".")[0] in _NAMESPACES]:
         monkeypatch.delitem(sys.modules, name)
+    before = set(sys.modules)
+    for name in _ABSENT_THIRD_PARTY:
+        try:
+            __import__(name)
+        except Exception:
+            monkeypatch.setitem(sys.modules, name, MagicMock())
     scene = types.ModuleType("scene")
     gm = types.ModuleType("scene.gaussian_model")
     gm.GaussianModel = type("GaussianModel", (), {})
     scene.gaussian_model = gm
     utils = types.ModuleType("utils")
-    utils.__path__ = []
+    utils.__path__ = [str(REF / "utils")]
     monkeypatch.setitem(sys.modules, "scene", scene)
     monkeypatch.setitem(sys.modules, "scene.gaussian_model", gm)
     monkeypatch.setitem(sys.modules, "utils", utils)
-    for sub in ("sh_utils", "point_utils"):
-        m = _load("utils." + sub, REF / "utils" / (sub + ".py"))
-        monkeypatch.setitem(sys.modules, "utils." + sub, m)
-        setattr(utils, sub, m)
-    # the reference hard-codes device="cuda" in three places (render():20, point_utils.py:10,14)
+    # the reference hard-codes device="cuda" (render():20, point_utils.py:10,14, mesh_utils.py:70,143)
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
-    _arange, _zeros_like = torch.arange, torch.zeros_like
-    monkeypatch.setattr(torch, "arange", lambda *a, **k: _arange(*a, **{kk: v for kk, v in k.items() if kk != "device"}))
-    monkeypatch.setattr(torch, "zeros_like",
-                        lambda *a, **k: _zeros_like(*a, **{kk: v for kk, v in k.items() if kk != "device"}))
+    monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
+
+    def _on_cpu(fn):
+        return lambda *a, **k: fn(*a, **{kk: v for kk, v in k.items() if not (kk == "device" and str(v) == "cuda")})
+
+    for fname in ("arange", "zeros_like", "tensor"):
+        monkeypatch.setattr(torch, fname, _on_cpu(getattr(torch, fname)))
     base = _load("ref_gaussian_renderer", REF / "renderer" / "gaussian_renderer" / "__init__.py")
     part = _load("ref_gaussian_renderer_2d", REF / "renderer" / "gaussian_renderer_2d" / "__init__.py")
+    import utils.mesh_utils as mesh_utils  # the reference's, through the `utils` package above
+    assert Path(mesh_utils.__file__).resolve() == (REF / "utils" / "mesh_utils.py").resolve()
     # the names the reference imported are this repo's classes
     from partgs_b200 import diff_surfel_rasterization as ours_base, diff_surfel_rasterization_part as ours_part
     assert base.GaussianRasterizer is ours_base.GaussianRasterizer
     assert part.GaussianRasterizer is ours_part.GaussianRasterizer
-    yield SimpleNamespace(render=base.render, render_part=part.render_part)
-    for name in [m for m in sys.modules if m.split(".")[0] in ("diff_surfel_rasterization",
-                                                               "diff_surfel_rasterization_part")]:
-        monkeypatch.delitem(sys.modules, name, raising=False)
+    yield SimpleNamespace(render=base.render, render_part=part.render_part, mesh_utils=mesh_utils)
+    for name in [m for m in sys.modules if m not in before and m.split(".")[0] in _NAMESPACES]:
+        sys.modules.pop(name, None)
 
 
 PARAMS = ("means3D", "opacities", "scales", "rotations", "shs")
@@ -171,3 +185,41 @@ def test_reference_render_with_override_color_and_scaling_modifier(reference_cal
     m = mirror(cam, pc, pipe, torch.zeros(3), scaling_modifier=0.7, override_color=col)
     assert torch.equal(r["radii"], m["radii"]) and torch.equal(r["render"], m["render"])
     assert _close(m["surf_normal"], r["surf_normal"], 2e-4)
+
+
+def test_reference_extraction_loop_runs_on_the_drop_in_and_equals_ours(reference_callers, monkeypatch):
+    """render.py's loop: the reference's GaussianExtractor.reconstruction (utils/mesh_utils.py:102-129, unmodified)
+    driving the reference's render_part on the drop-in rasteriser, against this repo's pipelined extractor (one fused
+    epilogue kernel per view, pinned host stacks).  The palette is an input on both sides (seaborn is absent)."""
+    from partgs_b200.extract import GaussianExtractor
+    from partgs_b200.renderer import render_part as mirror
+    from test_emu_host_layer import _FakeEvent, _FakeStream   # CUDA streams / events / pinning are no-ops on the emulator
+    monkeypatch.setattr(torch.cuda, "Stream", _FakeStream)
+    monkeypatch.setattr(torch.cuda, "Event", _FakeEvent)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: _FakeStream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: s)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None)
+    scene, _ = _model(P=200, W=40, H=24, S=5, seed=11)
+    cams = synth.make_cameras(3, 40, 24, seed=21, device="cpu")
+    pipe = SimpleNamespace(depth_ratio=1.0, compute_cov3D_python=False, convert_SHs_python=False, debug=False)
+    palette = torch.rand(6, 3, generator=torch.Generator().manual_seed(4))
+    pc, _, _ = _pc(scene, False)
+    mu = reference_callers.mesh_utils
+    mu.get_fancy_color = lambda n: palette[:n]
+    ref = mu.GaussianExtractor(pc, reference_callers.render_part, pipe, bg_color=[0, 0, 0])
+    ref.reconstruction(cams)
+    ours = GaussianExtractor(pc, mirror, pipe, bg_color=[0, 0, 0], palette=palette, device="cpu")
+    ours.reconstruction(cams)
+    assert ref.rgbmaps.shape == (3, 3, 24, 40) and float(ref.alphamaps.max()) > 0.5
+    for name, tol in (("rgbmaps", 0.0), ("alphamaps", 0.0), ("partrgbs", 0.0), ("depthmaps", 1e-5),
+                      ("depth_normals", 2e-4)):
+        a, b = getattr(ours, name), getattr(ref, name)
+        assert a.shape == b.shape, name
+        assert float((a - b).abs().max()) <= tol * float(b.abs().max()), name
+    # the reference keeps `normals` as a list of per-view maps (it never stacks them, mesh_utils.py:121-127)
+    rn = torch.stack(ref.normals) if isinstance(ref.normals, list) else ref.normals
+    on = torch.stack(list(ours.normals)) if isinstance(ours.normals, (list, tuple)) else ours.normals
+    assert float((on - rn).abs().max()) <= 1e-5
+    assert abs(float(ours.radius) - float(ref.radius)) <= 1e-6 * float(ref.radius)
+    assert float((ours.center.cpu() - ref.center).abs().max()) <= 1e-5
