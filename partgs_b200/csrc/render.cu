@@ -30,10 +30,10 @@
 //     to be bit-identical to forward, i.e. IEEE divisions and precise expf) from the backward
 //     pass: its per-fragment values are recomputed with MUFU.RCP / MUFU.EX2 (gradients are
 //     gated at 1e-4 relative, measured ~1e-6);
-//   * backward: the 16+3(+S) per-fragment gradient components are reduced over the 32 pixels
-//     with a transposed butterfly (16 shuffles for 16 values instead of 80); 16 lanes then
-//     hold one finished component each and issue one coalesced red.global.add.f32 into the
-//     surfel's 80-byte gradient record.
+//   * backward: the 18 (+S) per-fragment gradient components are summed over the 32 pixels
+//     through the warp's shared memory (column-wise stores, four rotated 128-bit loads and one
+//     shuffle per lane pair; two colour sums take a register butterfly); 18 lanes then hold one
+//     finished component each and issue one red.global.add.f32 into the surfel's 80-byte record.
 // The forward per-fragment arithmetic is pinned in frag_math.cuh; accumulations below use the
 // reference's rounding sequence (explicit fma/mul), so images are bit-identical.
 #include "common.cuh"
