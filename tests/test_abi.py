@@ -75,3 +75,40 @@ def test_rasterizer_argument_validation():
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         r(means3D=x, means2D=x, opacities=torch.zeros(4, 1), shs=torch.zeros(4, 16, 3), scales=torch.zeros(4, 2),
           rotations=torch.zeros(4, 4))
+
+
+def _fp_opcode_mix(symbol_fragment):
+    """FP arithmetic opcodes of one kernel of the built library (cuobjdump -sass), as a Counter."""
+    import collections
+    import shutil
+    import subprocess
+    from partgs_b200 import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    if not hasattr(_fp_opcode_mix, "sass"):     # one dump of the library for all callers
+        _fp_opcode_mix.sass = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATH)], capture_output=True,
+                                             text=True).stdout
+    out = _fp_opcode_mix.sass
+    mix, inside = collections.Counter(), False
+    for line in out.splitlines():
+        if "Function :" in line:
+            inside = symbol_fragment in line
+            continue
+        if inside:
+            m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\w+\s+)?(FADD|FFMA|FMUL|DADD|DFMA|DMUL|MUFU\.\w+|FCHK)\b", line)
+            if m:
+                mix[m.group(1)] += 1
+    return mix
+
+
+@pytest.mark.parametrize("sq", ["Lb0", "Lb1"])
+def test_cooperative_sh_preprocess_keeps_the_fp_instruction_mix(lib, sq):
+    """The bit-exactness of `rgb` / the ray-splat transform against the reference build rests on nvcc contracting the
+    same multiply-adds (52 FADD / 205 FFMA / 117 FMUL in the point-level kernel, as in the reference's).
+    The experimental cooperative-SH variant (PGS_SH_COOP=1) only changes how coefficients reach the thread: its FP
+    opcode mix must equal the default kernel's."""
+    default = _fp_opcode_mix(f"preprocess_fwd_kernelI{sq}E")
+    coop = _fp_opcode_mix(f"preprocess_fwd_coop_kernelI{sq}E")
+    assert default["FFMA"] > 100 and coop == default, (default, coop)
+    if sq == "Lb0":
+        assert (default["FADD"], default["FFMA"], default["FMUL"]) == (52, 205, 117)

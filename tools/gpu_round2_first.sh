@@ -18,3 +18,17 @@ timeout 600 python tools/time_rank34.py > $out/${tag}_rank34.jsonl 2> $out/${tag
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_zz_densify.py \
     tests/test_gpu_zz_regularizers.py -q -k "golden or 5_000 or 77" > $out/${tag}_memcheck.log 2>&1
 echo "memcheck rc=$?" | tee -a $out/${tag}_memcheck.log; tail -5 $out/${tag}_memcheck.log
+# 5. the prepared cooperative-SH forward preprocess (PGS_SH_COOP=1): bit-exact parity against the reference build, then timing
+PGS_SH_COOP=1 timeout 600 python -m pytest tests/test_gpu_base_raster.py tests/test_gpu_blocks_fused.py -q > $out/${tag}_shcoop_pytest.log 2>&1
+echo "sh-coop pytest rc=$?" | tee -a $out/${tag}_shcoop_pytest.log; tail -3 $out/${tag}_shcoop_pytest.log
+timeout 300 python bench.py --no-cpu > $out/${tag}_bench_default.json 2> $out/${tag}_bench_default.err
+PGS_SH_COOP=1 timeout 300 python bench.py --no-cpu > $out/${tag}_bench_shcoop.json 2> $out/${tag}_bench_shcoop.err
+TAG=$tag python - <<'PY'
+import json, os
+for name in ("default", "shcoop"):
+    try:
+        d = json.load(open(f"gpurun_out/{os.environ['TAG']}_bench_{name}.json"))
+        print(name, d["value"], "frames/s; preprocess_fwd", d["stage_ms_per_step"]["preprocess_fwd"], "ms")
+    except Exception as ex:
+        print(name, "unreadable:", ex)
+PY
