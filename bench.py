@@ -163,6 +163,30 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def next_rows(rows="sh_coop,regularizers,adam,densify,extract", reps=3, timeout_s=120):
+    """tools/time_rank34.py in a child process with a hard time limit; its JSON lines as a list (errors included as rows:
+    this is informative output and must never fail, or delay for long, the bench line)."""
+    out = []
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / "tools" / "time_rank34.py"), "--reps", str(reps), "--rows", rows],
+                           capture_output=True, text=True, timeout=timeout_s, cwd=str(ROOT))
+        for line in r.stdout.splitlines():
+            if line.startswith("{"):
+                try:
+                    row = json.loads(line)
+                except Exception:
+                    continue
+                row.pop("trace", None)
+                if "error" in row:
+                    row["error"] = str(row["error"])[:160]
+                out.append(row)
+        if not out:
+            out.append({"error": (r.stderr or "no output")[-160:]})
+    except Exception as ex:   # incl. TimeoutExpired
+        out.append({"error": repr(ex)[:160]})
+    return out
+
+
 def algorithmic_bytes(P, V, R, npix, ntile, M=16, S=0, passes=6):
     """compulsory-traffic model of one frame."""
     a_f = 64 * P + (12 * M + 91) * V + (104 + 24 * passes + 4 * S) * R + (60 + 4 * S) * npix + 8 * ntile
@@ -596,6 +620,13 @@ def run(args):
                 "ours_gpu_ms": round(best_ms(sq_gpu, True), 3)}
         except Exception as ex:  # the baseline is informative; never fail the bench line over it
             out["cpu_baseline"]["superquadric_to_surfel"] = {"error": str(ex)[:200]}
+    # ---- next rows and the prepared preprocess variant, timed beside the headline -----------
+    # Run as a SEPARATE process with a hard time limit (tools/time_rank34.py): whatever happens there cannot touch the
+    # numbers above.  Each row is ours vs the reference's torch sequence on this GPU; `sh_coop_probe_C3` reports whether
+    # the opt-in cooperative-SH preprocess is bit-identical on this GPU and what the stage costs in both variants.
+    if world == 1 and args.impl != "reference" and not args.no_cpu and not args.no_extras:
+        torch.cuda.empty_cache()
+        out["next_rows"] = next_rows()
     if args.impl == "reference":
         out["cpu_baseline"] = {"value": out["value"], "unit": UNIT, "cores": 0, "kind": "reference",
                                "sample": "unmodified reference CUDA rasteriser (oracle/_ref) on the same GPU, same steps"}
@@ -614,6 +645,8 @@ def main():
                     help="N>1: which views share a lock-step (cost-sorted groups, or plain round-robin)")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="gradient all-reduce at N>1: copy-engine peer-memory collective (default) or NCCL")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the timing of the SURVEY 8(f) rows / prepared variants in a subprocess after the bench")
     ap.add_argument("--no-allreduce", action="store_true",
                     help="diagnostic: skip the gradient all-reduce at N>1 (shows what the collective costs)")
     args = ap.parse_args()

@@ -61,3 +61,16 @@ def test_bucket_provider_hook_round_trip():
         dsr.set_grad_bucket_provider(None)
     views = dsr._carve_bucket("cpu", [(2, 3)])
     assert views[0].shape == (2, 3)
+
+
+def test_bench_next_rows_never_raises_and_reports_errors_as_rows():
+    """bench.py's `next_rows` leg (tools/time_rank34.py in a child process): without a GPU every row fails inside the
+    child — the parent still gets one compact row per request and no exception; a timeout is reported the same way."""
+    import bench
+    rows = bench.next_rows(rows="adam,extract", reps=1, timeout_s=120)
+    assert len(rows) == 2 and all("row" in r and "trace" not in r for r in rows)
+    if not torch.cuda.is_available():
+        assert [r["row"] for r in rows] == ["row_adam", "row_extract"]
+        assert all("error" in r and len(r["error"]) <= 160 for r in rows)
+    rows = bench.next_rows(rows="adam", reps=1, timeout_s=0.01)
+    assert len(rows) == 1 and "TimeoutExpired" in rows[0]["error"]
