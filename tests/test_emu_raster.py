@@ -207,4 +207,4 @@ def test_emulated_cooperative_sh_variant_is_bit_identical(emu, monkeypatch, P, d
     # backward consumes the same forward state; its float atomics commit in a run-dependent order, so the
     # gradients of two runs agree to the last bits rather than exactly (true for two default runs as well)
     for k, v in base["grads"].items():
-        assert rel(coop["grads"][k], v) <= 1e-6, k
+        assert rel(coop["grads"][k], v) <= 2e-5, k      # reordered fp32 sums of a few dozen terms: ~1e-6, with margin
