@@ -151,9 +151,11 @@ def row_sh_coop(reps):
             for c in cams:
                 frame(c)
         torch.cuda.synchronize()
-        ms, n = _lib.timing_read(reset=True)["preprocess_fwd"]
+        stages = _lib.timing_read(reset=True)
         _lib.timing_enable(False)
+        ms, n = stages["preprocess_fwd"]
         out[mode + "_preprocess_fwd_ms"] = round(ms / max(n, 1), 4)
+        out[mode + "_forward_stages_ms"] = {k: round(v[0] / v[1], 4) for k, v in stages.items() if v[1]}
     os.environ.pop("PGS_SH_COOP", None)
     bits = lambda t: t.view(torch.int32) if t.dtype == torch.float32 else t      # bitwise: NaNs must match too
     same = all(a[0] == b[0] and all(torch.equal(bits(x), bits(y)) for x, y in zip(a[1:], b[1:]))
