@@ -114,6 +114,15 @@ template <int OFF> __device__ __forceinline__ uint2 lds_u2(saddr_t a) {
   asm volatile("ld.shared.v2.b32 {%0, %1}, [%2+%3];" : "=r"(r.x), "=r"(r.y) : "r"(a), "n"(OFF) : "memory");
   return r;
 }
+template <int OFF> __device__ __forceinline__ uint32_t lds_u32(saddr_t a) {
+  uint32_t r;
+  asm volatile("ld.shared.b32 %0, [%1+%2];" : "=r"(r) : "r"(a), "n"(OFF) : "memory");
+  return r;
+}
+template <typename T> __device__ __forceinline__ T* opaque_ptr(T* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
 template <int OFF> __device__ __forceinline__ void sts_p2(saddr_t a, P2 v) {
   asm volatile("st.shared.v2.f32 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "f"(lo(v)), "f"(hi(v)) : "memory");
 }
@@ -128,6 +137,8 @@ template <int OFF> inline Q2 lds_q2(saddr_t a) { return *reinterpret_cast<const 
 template <int OFF> inline uint4 lds_u4(saddr_t a) { return *reinterpret_cast<const uint4*>(a + OFF); }
 template <int OFF> inline float4 lds_f4(saddr_t a) { return *reinterpret_cast<const float4*>(a + OFF); }
 template <int OFF> inline uint2 lds_u2(saddr_t a) { return *reinterpret_cast<const uint2*>(a + OFF); }
+template <int OFF> inline uint32_t lds_u32(saddr_t a) { return *reinterpret_cast<const uint32_t*>(a + OFF); }
+template <typename T> inline T* opaque_ptr(T* p) { return p; }
 template <int OFF> inline void sts_p2(saddr_t a, P2 v) { *reinterpret_cast<P2*>(a + OFF) = v; }
 template <int OFF> inline void sts_f32(saddr_t a, float v) { *reinterpret_cast<float*>(a + OFF) = v; }
 #endif

@@ -25,13 +25,4 @@ inline int warps_per_cta(int ntiles) {
   if (ntiles >= 750) return 2;
   return 1;
 }
-// The backward kernel keeps ~10.5 KB of shared memory per warp (raw ring, pair buffer, reduction columns): half
-// tiles (4 warps, 42 KB) fit five CTAs = 20 warps on an SM where whole tiles would fit two CTAs = 16 warps.
-inline int bwd_warps_per_cta(int ntiles) {
-  static const int forced = render_env_int("PGS_BWD_WARPS_PER_CTA", 0);
-  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
-  const int nw = warps_per_cta(ntiles);
-  return nw > 4 ? 4 : nw;
-}
-
 }  // namespace pgs
