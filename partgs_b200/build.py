@@ -25,6 +25,7 @@ NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
+    *os.environ.get("PGS_NVCC_EXTRA", "").split(),   # experiments only (e.g. -DPGS_BWD_MIN_CTAS=5)
 ]
 
 

@@ -25,11 +25,13 @@ __device__ __forceinline__ P2 pk(float a, float b) {
 __device__ __forceinline__ float lo(P2 p) {
   float a, b;
   asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v));
+  (void)b;
   return a;
 }
 __device__ __forceinline__ float hi(P2 p) {
   float a, b;
   asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v));
+  (void)a;
   return b;
 }
 __device__ __forceinline__ P2 fma2(P2 a, P2 b, P2 c) {

@@ -36,6 +36,26 @@ def mismatch_frac(a: torch.Tensor, b: torch.Tensor, rtol: float) -> float:
     return ((a - b).abs() > tol).double().mean().item()
 
 
+def grad_violations(a: torch.Tensor, b: torch.Tensor, rtol: float = GRAD_RTOL, afloor: float = 1e-6) -> float:
+    """Element-wise gate: fraction of elements with |a-b| > rtol * |b| + afloor * max|b|  (b is the reference).
+    The absolute floor covers entries that are sums of cancelling float atomics — there two runs of the reference
+    itself differ by more than rtol * |entry|."""
+    a = a.double()
+    b = b.double()
+    if a.numel() == 0:
+        return 0.0
+    tol = rtol * b.abs() + afloor * b.abs().max()
+    return ((a - b).abs() > tol).double().mean().item()
+
+
+def assert_equal_images(name: str, ours: torch.Tensor, ref: torch.Tensor):
+    """Bit-identical images (base fork: the per-fragment rounding sequence is pinned in frag_math.cuh)."""
+    if not torch.equal(ours, ref):
+        neq = ours != ref
+        d = (ours.double() - ref.double()).abs()
+        raise AssertionError(f"{name}: {int(neq.sum())} of {neq.numel()} elements differ, max |diff| {float(d.max()):.3e}")
+
+
 def robust_close(a, b, atol_frac=1e-4, max_frac=2e-3):
     """Comparison against the CPU restatement, which rounds differently from the GPU (no FMA
     contraction): a few fragments sit on the other side of the alpha >= 1/255 or T < 1e-4
