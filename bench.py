@@ -163,7 +163,7 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def next_rows(rows="sh_coop,regularizers,adam,densify,extract", reps=3, timeout_s=120):
+def next_rows(rows="regularizers,adam,densify,extract", reps=3, timeout_s=120):
     """tools/time_rank34.py in a child process with a hard time limit; its JSON lines as a list (errors included as rows:
     this is informative output and must never fail, or delay for long, the bench line)."""
     out = []

@@ -225,108 +225,20 @@ __device__ __forceinline__ void cull_record(const m3& T, float2 xy, float opa, f
 
 // SQ = block-level mode: the surfel is generated here from the superquadric parameters
 // (sq_device.cuh: sq_generate) instead of being read from means3D / scales / rotations / opacities.
-template <bool SQ>
-__global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessFwdArgs a) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.P) return;
-
-  // Invisible unless proven otherwise (reference forward.cu:184-185).
-  a.radii[idx] = 0;
-  a.tiles_touched[idx] = 0;
-
-  const int W = a.W, H = a.H;
-  const float* orig_points = a.means3D;
-
-  SqSurfel sf;
-  if (SQ) {
-    sf = sq_generate(a.sq, a.sq_vertices, idx);
-    if (a.sq_out_xyz) { a.sq_out_xyz[3 * idx] = sf.mean.x; a.sq_out_xyz[3 * idx + 1] = sf.mean.y; a.sq_out_xyz[3 * idx + 2] = sf.mean.z; }
-    if (a.sq_out_scaling) { a.sq_out_scaling[2 * idx] = sf.log_scale.x; a.sq_out_scaling[2 * idx + 1] = sf.log_scale.y; }
-    if (a.sq_out_rotation) reinterpret_cast<float4*>(a.sq_out_rotation)[idx] = sf.quat;
-    if (a.sq_out_opacity) a.sq_out_opacity[idx] = sf.opacity;
-  }
-
-  // near cull (auxiliary.h:185-210): only p_view.z <= 0.2 rejects.
-  float3 p_orig = SQ ? sf.mean : make_float3(orig_points[3 * idx], orig_points[3 * idx + 1], orig_points[3 * idx + 2]);
-  float3 p_view = xform_point4x3(p_orig, a.viewmatrix);
-  if (p_view.z <= 0.2f) return;
-
-  m3 T;
-  float3 normal;
-  if (SQ || a.transMat_precomp == nullptr) {
-    const v2 scale_in = SQ ? v2(sf.scale.x, sf.scale.y) : ((const v2*)a.scales)[idx];
-    const v4 rot_in = SQ ? v4(sf.quat.x, sf.quat.y, sf.quat.z, sf.quat.w) : ((const v4*)a.rotations)[idx];
-    compute_transmat(p_orig, scale_in, a.scale_modifier, rot_in, a.projmatrix, a.viewmatrix, W, H, T, normal);
-  } else {
-    const v3* T_ptr = (const v3*)a.transMat_precomp;
-    T = make_m3(T_ptr[idx * 3 + 0], T_ptr[idx * 3 + 1], T_ptr[idx * 3 + 2]);
-    normal = make_float3(0.0, 0.0, 1.0);
-  }
-
-  // dual-visible: flip the normal toward the camera (forward.cu:209-214)
-  float cosv = -(p_view.x * normal.x + p_view.y * normal.y + p_view.z * normal.z);
-  if (cosv == 0) return;
-  float multiplier = cosv > 0 ? 1 : -1;
-  normal = make_float3(multiplier * normal.x, multiplier * normal.y, multiplier * normal.z);
-
-  float cutoff = 3.0f;
-  float2 point_image;
-  float radius;
-  {
-    float2 extent;
-    bool ok = compute_aabb(T, cutoff, point_image, extent);
-    if (!ok) return;
-    radius = ceil(max(max(extent.x, extent.y), cutoff * PGS_FILTER_SIZE));
-  }
-
-  dim3 grid(a.grid_x, a.grid_y, 1);
-  uint2 rect_min, rect_max;
-  tile_rect(point_image, radius, rect_min, rect_max, grid);
-  if ((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y) == 0) return;
-
-  float r, g, b;
-  unsigned clamped = 0;
-  if (a.colors_precomp == nullptr) {
-    v3 c = color_from_sh<SQ>(idx, a.D, a.M, (const v3*)orig_points, *(const v3*)a.cam_pos, a.shs, clamped,
-                             v3(p_orig.x, p_orig.y, p_orig.z));
-    r = c.x; g = c.y; b = c.z;
-  } else {
-    r = a.colors_precomp[idx * 3 + 0];
-    g = a.colors_precomp[idx * 3 + 1];
-    b = a.colors_precomp[idx * 3 + 2];
-  }
-
-  const float opa = SQ ? sf.opacity : a.opacities[idx];
-  float4* rec = a.rec + (size_t)idx * REC_QUADS;
-  rec[0] = make_float4(T[0].x, T[0].y, T[0].z, point_image.x);
-  rec[1] = make_float4(T[1].x, T[1].y, T[1].z, point_image.y);
-  rec[2] = make_float4(T[2].x, T[2].y, T[2].z, opa);
-  rec[3] = make_float4(normal.x, normal.y, normal.z, p_view.z);
-  rec[4] = make_float4(r, g, b, __uint_as_float(clamped));
-  cull_record(T, point_image, opa, a.bbox + (size_t)idx * CULL_QUADS);
-
-  a.radii[idx] = (int)radius;
-  a.tiles_touched[idx] = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
-}
-
-// -----------------------------------------------------------------------------
-// EXPERIMENTAL (opt-in: PGS_SH_COOP=1, not yet timed on a B200): the same kernel with a warp-cooperative SH load.
-// ncu of preprocess_fwd_kernel on C3 (profiles/r1_ncu_full_C3_step.txt): l1tex throughput 91.5 % of peak, DRAM 31.6 %
-// — the 48 strided 4-byte loads per thread (32 sectors per warp request) saturate L1TEX long before HBM.  Here a warp
-// first runs the geometry of its 32 surfels (no early return: culled lanes only clear `vis`), compacts the visible ones,
-// copies their coefficient rows to shared memory with fully coalesced loads (lane k reads float k of a row: 4 + 2
-// sectors per row instead of 48 x 32 per warp), four rows in flight per step, and every visible thread then evaluates
-// the SH polynomial from its shared-memory row (row stride 49 floats: conflict-free).  The arithmetic — expression
-// trees of the geometry and of color_from_sh — is the original's, so results must stay bit-identical; the FP opcode
-// sequence of both instantiations is compared in tests/test_abi.py.  The body duplicates preprocess_fwd_kernel on
-// purpose: the measured, bit-exact default is left untouched until this variant has been timed and parity-checked on
-// hardware (round 2), after which one of the two goes.
-// -----------------------------------------------------------------------------
+//
+// The SH coefficients (192 B per surfel, the bulk of this kernel's traffic) are loaded warp-cooperatively: read per
+// thread they are 48 strided 4-byte loads (32 sectors per warp request), which kept L1TEX 91 % busy at 32 % of DRAM
+// peak (profiles/r1_ncu_full_C3_step.txt).  A warp therefore first runs the geometry of its 32 surfels (no early
+// return: culled lanes only clear `vis`), compacts the visible ones, copies their coefficient rows to shared memory
+// with fully coalesced loads (lane k reads float k of a row: 4 + 2 sectors per row), four rows in flight per step, and
+// every visible thread then evaluates the SH polynomial from its shared-memory row (row stride 49 floats:
+// conflict-free).  The arithmetic — the expression trees of the geometry and of color_from_sh — is unchanged, so the
+// outputs stay bit-identical to the reference build (checked stage by stage in tests/test_gpu_base_raster.py).
 constexpr int SH_ROW = 49;  // floats per staged row (48 coefficients + 1 pad)
 constexpr size_t SH_COOP_SMEM = (size_t)8 * 32 * SH_ROW * sizeof(float) + 8 * 32 * sizeof(uint32_t);
 
 template <bool SQ>
-__global__ void __launch_bounds__(256) preprocess_fwd_coop_kernel(PreprocessFwdArgs a) {
+__global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessFwdArgs a) {
   extern __shared__ __align__(16) unsigned char coop_smem[];
   float* s_rows = reinterpret_cast<float*>(coop_smem);
   uint32_t* s_ids = reinterpret_cast<uint32_t*>(coop_smem + (size_t)8 * 32 * SH_ROW * sizeof(float));
@@ -381,41 +293,48 @@ __global__ void __launch_bounds__(256) preprocess_fwd_coop_kernel(PreprocessFwdA
     vis = true;
   } while (0);
 
-  // ---- warp-cooperative copy of the visible surfels' SH rows to shared memory ----
-  const unsigned vmask = __ballot_sync(0xffffffffu, vis);
-  const int nv = __popc(vmask), slot = __popc(vmask & ((1u << lane) - 1u));
-  float* rows = s_rows + (size_t)wrp * 32 * SH_ROW;
-  uint32_t* ids = s_ids + wrp * 32;
-  if (vis) ids[slot] = (uint32_t)idx;
-  __syncwarp();
-  const int n = 3 * (a.D + 1) * (a.D + 1);  // floats the active degree reads (<= 48)
-  const size_t row_floats = (size_t)a.M * 3;
-  for (int s0 = 0; s0 < nv; s0 += 4) {
-    float v0[4], v1[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      v0[u] = v1[u] = 0.f;
-      if (s0 + u < nv) {
-        const float* src = a.shs + (size_t)ids[s0 + u] * row_floats;
-        if ((int)lane < n) v0[u] = __ldg(src + lane);
-        if ((int)lane + 32 < n) v1[u] = __ldg(src + 32 + lane);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      if (s0 + u < nv) {
-        rows[(s0 + u) * SH_ROW + lane] = v0[u];
-        if (lane + 32 < (unsigned)SH_ROW) rows[(s0 + u) * SH_ROW + 32 + lane] = v1[u];
-      }
-    }
-  }
-  __syncwarp();
-  if (!vis) return;
-
+  float r, g, b;
   unsigned clamped = 0;
-  v3 c = color_from_sh<SQ, true>(idx, a.D, a.M, (const v3*)orig_points, *(const v3*)a.cam_pos, rows + slot * SH_ROW,
-                                 clamped, v3(p_orig.x, p_orig.y, p_orig.z));
-  const float r = c.x, g = c.y, b = c.z;
+  if (a.colors_precomp == nullptr) {
+    // ---- warp-cooperative copy of the visible surfels' SH rows to shared memory ----
+    const unsigned vmask = __ballot_sync(0xffffffffu, vis);
+    const int nv = __popc(vmask), slot = __popc(vmask & ((1u << lane) - 1u));
+    float* rows = s_rows + (size_t)wrp * 32 * SH_ROW;
+    uint32_t* ids = s_ids + wrp * 32;
+    if (vis) ids[slot] = (uint32_t)idx;
+    __syncwarp();
+    const int n = 3 * (a.D + 1) * (a.D + 1);  // floats the active degree reads (<= 48: degrees 0..3, as in the reference)
+    const size_t row_floats = (size_t)a.M * 3;
+    for (int s0 = 0; s0 < nv; s0 += 4) {
+      float v0[4], v1[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        v0[u] = v1[u] = 0.f;
+        if (s0 + u < nv) {
+          const float* src = a.shs + (size_t)ids[s0 + u] * row_floats;
+          if ((int)lane < n) v0[u] = __ldg(src + lane);
+          if ((int)lane + 32 < n) v1[u] = __ldg(src + 32 + lane);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (s0 + u < nv) {
+          rows[(s0 + u) * SH_ROW + lane] = v0[u];
+          if (lane + 32 < (unsigned)SH_ROW) rows[(s0 + u) * SH_ROW + 32 + lane] = v1[u];
+        }
+      }
+    }
+    __syncwarp();
+    if (!vis) return;
+    v3 c = color_from_sh<SQ, true>(idx, a.D, a.M, (const v3*)orig_points, *(const v3*)a.cam_pos, rows + slot * SH_ROW,
+                                   clamped, v3(p_orig.x, p_orig.y, p_orig.z));
+    r = c.x; g = c.y; b = c.z;
+  } else {
+    if (!vis) return;
+    r = a.colors_precomp[idx * 3 + 0];
+    g = a.colors_precomp[idx * 3 + 1];
+    b = a.colors_precomp[idx * 3 + 2];
+  }
 
   const float opa = SQ ? sf.opacity : a.opacities[idx];
   float4* rec = a.rec + (size_t)idx * REC_QUADS;
@@ -553,34 +472,18 @@ __global__ void __launch_bounds__(256) check_frustum_kernel(int P, const float* 
   present[idx] = (pv.z <= 0.2f) ? 0 : 1;
 }
 
-static bool sh_coop_requested() {
-  const char* e = getenv("PGS_SH_COOP");  // experimental variant, see preprocess_fwd_coop_kernel
-  return e != nullptr && e[0] != '\0' && e[0] != '0';
-}
-
-template <bool SQ> static void launch_coop(const PreprocessFwdArgs& a, cudaStream_t s) {
-  static bool attr_set[64] = {};
-  if (first_use_on_device(attr_set))
-    cudaFuncSetAttribute(preprocess_fwd_coop_kernel<SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH_COOP_SMEM);
-  preprocess_fwd_coop_kernel<SQ><<<(a.P + 255) / 256, 256, SH_COOP_SMEM, s>>>(a);
-  count_launch();
-}
-
 void launch_preprocess_fwd(const PreprocessFwdArgs& a, cudaStream_t s) {
-  if (a.P > 0 && a.colors_precomp == nullptr && a.shs != nullptr && a.M * 3 <= 48 && sh_coop_requested()) {
-    if (a.use_sq) launch_coop<true>(a, s);
-    else launch_coop<false>(a, s);
-    return;
-  }
-  if (a.P > 0 && a.use_sq) {
-    preprocess_fwd_kernel<true><<<(a.P + 255) / 256, 256, 0, s>>>(a);
-    count_launch();
-    return;
-  }
   if (a.P <= 0) return;
-  preprocess_fwd_kernel<false><<<(a.P + 255) / 256, 256, 0, s>>>(a);
+  static bool attr_set[2][64] = {};
+  if (first_use_on_device(attr_set[a.use_sq ? 1 : 0])) {
+    if (a.use_sq) cudaFuncSetAttribute(preprocess_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH_COOP_SMEM);
+    else cudaFuncSetAttribute(preprocess_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH_COOP_SMEM);
+  }
+  if (a.use_sq) preprocess_fwd_kernel<true><<<(a.P + 255) / 256, 256, SH_COOP_SMEM, s>>>(a);
+  else preprocess_fwd_kernel<false><<<(a.P + 255) / 256, 256, SH_COOP_SMEM, s>>>(a);
   count_launch();
 }
+
 void launch_check_frustum(int P, const float* means3D, const float* viewmatrix, unsigned char* present,
                           cudaStream_t s) {
   if (P <= 0) return;

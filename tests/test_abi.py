@@ -101,14 +101,11 @@ def _fp_opcode_mix(symbol_fragment):
     return mix
 
 
-@pytest.mark.parametrize("sq", ["Lb0", "Lb1"])
-def test_cooperative_sh_preprocess_keeps_the_fp_instruction_mix(lib, sq):
+def test_preprocess_forward_keeps_the_fp_instruction_mix(lib):
     """The bit-exactness of `rgb` / the ray-splat transform against the reference build rests on nvcc contracting the
     same multiply-adds (52 FADD / 205 FFMA / 117 FMUL in the point-level kernel, as in the reference's).
-    The experimental cooperative-SH variant (PGS_SH_COOP=1) only changes how coefficients reach the thread: its FP
-    opcode mix must equal the default kernel's."""
-    default = _fp_opcode_mix(f"preprocess_fwd_kernelI{sq}E")
-    coop = _fp_opcode_mix(f"preprocess_fwd_coop_kernelI{sq}E")
-    assert default["FFMA"] > 100 and coop == default, (default, coop)
-    if sq == "Lb0":
-        assert (default["FADD"], default["FFMA"], default["FMUL"]) == (52, 205, 117)
+    The warp-cooperative SH load only changes how coefficients reach the thread, not this mix; a change of these
+    numbers means the expression trees were touched (the GPU stage tests are the real gate, this is the early warning
+    that works without a GPU)."""
+    mix = _fp_opcode_mix("preprocess_fwd_kernelILb0E")
+    assert (mix["FADD"], mix["FFMA"], mix["FMUL"]) == (52, 205, 117), mix

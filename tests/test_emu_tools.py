@@ -51,17 +51,6 @@ def tool(emulated_host, monkeypatch):
     return mod
 
 
-def test_sh_coop_probe_row(tool, monkeypatch):
-    from partgs_b200 import synth
-    monkeypatch.setitem(synth.CONFIGS, "C3", dict(synth.CONFIGS["C3"], P=400, W=48, H=32))
-    monkeypatch.delenv("PGS_SH_COOP", raising=False)
-    row = tool.row_sh_coop(1)
-    assert row["row"] == "sh_coop_probe_C3" and row["bit_identical_outputs"] is True and row["num_rendered"] > 0
-    assert row["default_preprocess_fwd_ms"] >= 0 and row["coop_preprocess_fwd_ms"] >= 0 and "speedup" in row
-    import os
-    assert "PGS_SH_COOP" not in os.environ
-
-
 def test_rank34_rows_at_toy_sizes(tool, monkeypatch):
     r = tool.row_densify(3000, 1)
     assert r["row"] == "densify_and_prune" and r["n_out"] > 0 and r["ours_ms"] >= 0 and r["reference_ms"] >= 0

@@ -120,59 +120,14 @@ def row_regularizers(reps, H=1200, W=1600):
     return dict(row=f"regularizers_fwd_bwd_{W}x{H} (incl. 3 clones)", ours_ms=o, reference_ms=r, speedup=round(r / o, 2))
 
 
-def row_sh_coop(reps):
-    """The prepared cooperative-SH forward preprocess (PGS_SH_COOP=1, csrc/preprocess_fwd.cu) beside the default kernel on
-    C3: are the frame's outputs bit-identical on this GPU, and what does the stage cost (library stage timers)?"""
-    import os
-    from partgs_b200 import _lib, synth
-    from partgs_b200.diff_surfel_rasterization import _C
-    cfg = synth.CONFIGS["C3"]
-    seed = synth.SEED_BASE + synth.CONFIG_INDEX["C3"]
-    scene = synth.make_point_scene(cfg["P"], seed, S=0, device="cuda")
-    cams = synth.make_cameras(4, cfg["W"], cfg["H"], seed, device="cuda")
-    bg = torch.zeros(3, device="cuda"); e = torch.empty(0, device="cuda")
-
-    def frame(cam):
-        return _C.rasterize_gaussians(bg, scene["means3D"], e, scene["opacities"], scene["scales"], scene["rotations"], 1.0,
-                                      e, cam.viewmatrix, cam.projmatrix, cam.tanfovx, cam.tanfovy, cfg["H"], cfg["W"],
-                                      scene["shs"], 3, cam.campos, False, False)[:4]
-    out, res = {}, {}
-    for mode in ("default", "coop"):
-        if mode == "coop":
-            os.environ["PGS_SH_COOP"] = "1"
-        else:
-            os.environ.pop("PGS_SH_COOP", None)
-        res[mode] = [tuple(t.clone() if isinstance(t, torch.Tensor) else t for t in frame(c)) for c in cams]
-        for c in cams:
-            frame(c)
-        torch.cuda.synchronize()
-        _lib.timing_enable(True); _lib.timing_read(reset=True)
-        for _ in range(reps):
-            for c in cams:
-                frame(c)
-        torch.cuda.synchronize()
-        stages = _lib.timing_read(reset=True)
-        _lib.timing_enable(False)
-        ms, n = stages["preprocess_fwd"]
-        out[mode + "_preprocess_fwd_ms"] = round(ms / max(n, 1), 4)
-        out[mode + "_forward_stages_ms"] = {k: round(v[0] / v[1], 4) for k, v in stages.items() if v[1]}
-    os.environ.pop("PGS_SH_COOP", None)
-    bits = lambda t: t.view(torch.int32) if t.dtype == torch.float32 else t      # bitwise: NaNs must match too
-    same = all(a[0] == b[0] and all(torch.equal(bits(x), bits(y)) for x, y in zip(a[1:], b[1:]))
-               for a, b in zip(res["default"], res["coop"]))
-    return dict(row="sh_coop_probe_C3", bit_identical_outputs=bool(same), num_rendered=int(res["default"][0][0]), **out,
-                speedup=round(out["default_preprocess_fwd_ms"] / max(out["coop_preprocess_fwd_ms"], 1e-9), 3))
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--P", type=int, default=1_000_000); ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--rows", default="densify,adam,extract,regularizers,reconstruction,sh_coop",
-                    help="comma-separated subset of: densify, adam, extract, regularizers, reconstruction, sh_coop")
+    ap.add_argument("--rows", default="densify,adam,extract,regularizers,reconstruction",
+                    help="comma-separated subset of: densify, adam, extract, regularizers, reconstruction")
     a = ap.parse_args()
     table = dict(densify=(row_densify, (a.P, a.reps)), adam=(row_adam, (a.P, a.reps)), extract=(row_extract, (a.reps,)),
-                 regularizers=(row_regularizers, (a.reps,)), reconstruction=(row_reconstruction, (3,)),
-                 sh_coop=(row_sh_coop, (a.reps,)))
+                 regularizers=(row_regularizers, (a.reps,)), reconstruction=(row_reconstruction, (3,)))
     for name in [r for r in a.rows.split(",") if r]:
         fn, args = table[name]
         try:
