@@ -302,6 +302,12 @@ int pgs_sort_pairs_u64(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uin
  * pgs_dsr_forward; keys/values must hold num_rendered entries. */
 int pgs_dsr_duplicate_with_keys(int P, const char* geom_buffer, int width, int height, const int* radii,
                                 uint64_t* keys, uint32_t* values, void* stream);
+/* BinningState::point_list_keys (rasterizer_impl.cu:187-194): the (tile << 32 | depth bits) keys of the sorted
+ * instance list of the frame pgs_dsr_forward last rendered into these buffers.  The production path sorts the
+ * surfels by depth and the instances by tile id only and never materialises the 64-bit keys; this entry rebuilds
+ * them (keys [num_rendered]) for stage-wise parity checks against the reference's sorted keys. */
+int pgs_dsr_sorted_keys(int P, int width, int height, const char* geom_buffer, const char* binning_buffer,
+                        size_t binning_bytes, int num_rendered, uint64_t* keys, void* stream);
 /* identifyTileRanges, rasterizer_impl.cu:116-138 (ranges [ntiles] uint2, zeroed here). */
 int pgs_identify_tile_ranges(int L, const uint64_t* sorted_keys, uint32_t* ranges, int ntiles, void* stream);
 /* getHigherMsb, rasterizer_impl.cu:35-50 */

@@ -99,8 +99,15 @@ struct GeomState {
   float4* bbox;
   int* radii;
   uint32_t* tiles_touched;
-  uint32_t* point_offsets;
+  uint32_t* point_offsets;  // stage-wise entry points only (pgs_dsr_duplicate_with_keys)
   char* scan_temp;
+  // production binning path (binning.cu, "instance emission in depth order")
+  uint2* rect;              // tile rectangle of every surfel
+  uint32_t* dkey_a, *dkey_b;  // depth bits, ping-pong of the depth sort
+  uint32_t* dval_a, *dval_b;  // surfel indices, ditto; the depth order ends up in dval_a
+  uint32_t* total;          // number of instances of the frame (device copy)
+  char* dsort_temp;
+  char* emit_state;
   static GeomState from(char*& p, size_t P) {
     GeomState g;
     carve(p, g.rec, P * REC_QUADS);
@@ -109,6 +116,14 @@ struct GeomState {
     carve(p, g.tiles_touched, P);
     carve(p, g.point_offsets, P);
     carve(p, g.scan_temp, scan_temp_bytes((int)P));
+    carve(p, g.rect, P);
+    carve(p, g.dkey_a, P);
+    carve(p, g.dkey_b, P);
+    carve(p, g.dval_a, P);
+    carve(p, g.dval_b, P);
+    carve(p, g.total, 64);
+    carve(p, g.dsort_temp, radix_sort32_temp_bytes((int)P, 32));
+    carve(p, g.emit_state, emit_state_bytes((int)P));
     return g;
   }
 };
@@ -127,8 +142,8 @@ struct ImageState {
   }
 };
 struct BinningState {
-  uint64_t* keys_a;
-  uint64_t* keys_b;
+  uint64_t* keys_a;  // production path: two u32[R] halves = ping-pong of the tile-id sort
+  uint64_t* keys_b;  // the reference's sorted 64-bit keys, rebuilt on request (pgs_dsr_sorted_keys)
   uint32_t* vals_a;
   uint32_t* vals_b;
   uint32_t* frag_mask;  // [8 warps][mask_stride]: forward's per-warp blend masks (render.cu)
@@ -149,9 +164,10 @@ struct BinningState {
     carve(p, b.vals_b, R);
     carve(p, b.keys_a, R);
     carve(p, b.keys_b, R);
-    carve(p, b.sort_temp, radix_sort_temp_bytes((int)R, end_bit));
+    carve(p, b.sort_temp, radix_sort_temp_bytes((int)R, end_bit));  // >= the two-pass tile sort's need
     return b;
   }
+  uint32_t* tile_keys(int which) const { return reinterpret_cast<uint32_t*>(keys_a) + (which ? mask_stride : 0); }
   static size_t bytes(size_t capacity, int end_bit) {
     char* p = nullptr;
     from(p, capacity, end_bit);
@@ -237,8 +253,7 @@ int pgs_dsr_get_layout(int P, int width, int height, size_t binning_bytes, pgs_d
     char* p = nullptr;
     BinningState b = BinningState::from(p, cap, end_bit);
     out->binning_bytes = (size_t)p + 256;
-    const bool in_b = ((end_bit + 7) / 8) & 1;
-    out->binning_keys_sorted = in_b ? (size_t)b.keys_b : (size_t)b.keys_a;
+    out->binning_keys_sorted = (size_t)b.keys_b;  // filled by pgs_dsr_sorted_keys
     out->binning_point_list = (size_t)b.vals_a;
     out->binning_frag_mask = (size_t)b.frag_mask;
     out->binning_mask_stride = b.mask_stride;
@@ -290,6 +305,7 @@ static int forward_impl(const SqForward* sqf, bool part, int S, const float* sem
 
   const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
   const size_t ntiles = (size_t)gx * gy;
+  if (gx > 0xffff || gy > 0xffff) return set_error(PGS_ERR_UNSUPPORTED, "image too large (more than 65535 tiles per axis)");
 
   size_t geom_bytes = required([&](char*& p) { GeomState::from(p, P); });
   char* gptr = geometry_buffer(geom_bytes, geometry_user);
@@ -309,6 +325,7 @@ static int forward_impl(const SqForward* sqf, bool part, int S, const float* sem
   pa.colors_precomp = colors_precomp; pa.viewmatrix = viewmatrix; pa.projmatrix = projmatrix; pa.cam_pos = cam_pos;
   pa.W = width; pa.H = height; pa.grid_x = gx; pa.grid_y = gy;
   pa.radii = radii; pa.rec = geom.rec; pa.bbox = geom.bbox; pa.tiles_touched = geom.tiles_touched;
+  pa.depth_key = geom.dkey_a; pa.rect = geom.rect;
   pa.focal_y = height / (2.0f * tan_fovy);
   pa.focal_x = width / (2.0f * tan_fovx);
   pa.use_sq = sqf != nullptr;
@@ -326,24 +343,28 @@ static int forward_impl(const SqForward* sqf, bool part, int S, const float* sem
   if (int e = check_cuda("preprocess_fwd")) return e;
   if (debug) if (int e = check_sync(s, "preprocess_fwd")) return e;
 
-  { StageTimer t(PGS_STAGE_SCAN, s); launch_inclusive_scan_u32(geom.tiles_touched, geom.point_offsets, P, geom.scan_temp, s); }
-  if (int e = check_cuda("scan")) return e;
+  // Depth order of the surfels (stable sort of the depth bits; culled surfels carry 0xffffffff and end up last).
+  // Reference: the low 32 key bits of its one big sort, rasterizer_impl.cu:301-309.
+  {
+    StageTimer t(PGS_STAGE_SCAN, s);
+    const int where = launch_radix_sort_index32(geom.dkey_a, geom.dval_a, geom.dkey_b, geom.dval_b, P, 32,
+                                                geom.dsort_temp, s);
+    if (where) return set_error(PGS_ERR_CUDA, "depth sort ended in the wrong buffer");  // 4 passes: never
+  }
+  if (int e = check_cuda("depth_sort")) return e;
 
-  // Number of surfel x tile instances R (reference: blocking cudaMemcpy, rasterizer_impl.cu:282).  The
-  // count travels to pinned host memory asynchronously; meanwhile binning + render are launched
-  // SPECULATIVELY for a capacity remembered from earlier frames, reading the count on the device.  Only
-  // then does the host wait for the count: the GPU already has the rest of the frame queued, so the
-  // round trip costs no device idle time, and the exact count is still returned to the caller.  If the
-  // count exceeds the capacity the speculative kernels did nothing and everything is launched again
-  // with a larger arena (first frames of a scene only).
+  // Number of surfel x tile instances R (reference: blocking cudaMemcpy, rasterizer_impl.cu:282).  Binning +
+  // render are launched SPECULATIVELY for a capacity remembered from earlier frames, the kernels reading the
+  // count on the device (the emission kernel computes it); the count travels to pinned host memory
+  // asynchronously and only then does the host wait for it: the GPU already has the rest of the frame queued, so
+  // the round trip costs no device idle time, and the exact count is still returned to the caller.  If the count
+  // exceeds the capacity the speculative kernels did nothing and everything is launched again with a larger
+  // arena (first frames of a scene only).
   int dev = 0;
   cudaGetDevice(&dev);
   CountFetch& cf = count_fetch();
   if (!cf.init()) return set_error(PGS_ERR_CUDA, "pinned count buffer: %s", cudaGetErrorString(cudaGetLastError()));
-  const uint32_t* n_dev = geom.point_offsets + P - 1;
-  cudaError_t ce = cudaMemcpyAsync(cf.host, n_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
-  if (ce != cudaSuccess) return set_error(PGS_ERR_CUDA, "memcpy num_rendered: %s", cudaGetErrorString(ce));
-  cudaEventRecord(cf.ev, s);
+  const uint32_t* n_dev = geom.total;
 
   const int end_bit = 32 + (int)higher_msb(gx * gy);
   auto launch_rest = [&](size_t capacity, const uint32_t* count_dev, int count_host) -> int {
@@ -354,20 +375,33 @@ static int forward_impl(const SqForward* sqf, bool part, int S, const float* sem
     const int n = count_dev ? (int)capacity : count_host;  // launch size
 
     cudaMemsetAsync(img.ranges, 0, ntiles * sizeof(uint2), s);
+    // Emit the (tile, surfel) instances in depth order, then stable-sort them by tile id: the reference's
+    // (tile | depth) order (duplicateWithKeys + SortPairs, rasterizer_impl.cu:70-111,301-309) with two digit
+    // passes over R instead of six.  The sort must end in (tile_keys(0), vals_a): start in b for an odd pass count.
+    const RsPlan plan = rs_plan_even(end_bit - 32);
+    const int first = plan.passes & 1;
+    uint32_t* k0 = bin.tile_keys(first), *k1 = bin.tile_keys(first ^ 1);
+    uint32_t* v0 = first ? bin.vals_b : bin.vals_a, *v1 = first ? bin.vals_a : bin.vals_b;
+    {
+      StageTimer t(PGS_STAGE_DUP_KEYS, s);
+      radix_sort_plan_prepare(n, plan, bin.sort_temp, s);
+      EmitArgs ea;
+      ea.P = P; ea.sorted_ids = geom.dval_a; ea.rect = geom.rect; ea.gx = (unsigned)gx;
+      ea.keys = k0; ea.vals = v0; ea.capacity = (uint32_t)capacity; ea.total = geom.total;
+      ea.hist = reinterpret_cast<uint32_t*>(bin.sort_temp); ea.plan = plan; ea.counter = nullptr; ea.state = nullptr;
+      launch_emit_instances(ea, geom.emit_state, s);
+    }
+    if (int e = check_cuda("emit_instances")) return e;
+    if (count_dev) {  // speculative launch: the count goes to the host while the rest of the frame is queued
+      cudaError_t ce = cudaMemcpyAsync(cf.host, geom.total, sizeof(int), cudaMemcpyDeviceToHost, s);
+      if (ce != cudaSuccess) return set_error(PGS_ERR_CUDA, "memcpy num_rendered: %s", cudaGetErrorString(ce));
+      cudaEventRecord(cf.ev, s);
+    }
     if (n > 0) {
-      { StageTimer t(PGS_STAGE_DUP_KEYS, s);
-        launch_duplicate_with_keys(P, geom.rec, geom.point_offsets, bin.keys_a, bin.vals_a, radii, gx, gy, s,
-                                   (uint32_t)capacity); }
-      if (int e = check_cuda("duplicate_with_keys")) return e;
-      int where;
       { StageTimer t(PGS_STAGE_SORT, s);
-        where = launch_radix_sort_pairs(bin.keys_a, bin.vals_a, bin.keys_b, bin.vals_b, n, end_bit, bin.sort_temp, s,
-                                        count_dev); }
+        launch_radix_sort_plan32(k0, v0, k1, v1, n, plan, bin.sort_temp, s, count_dev); }
       if (int e = check_cuda("radix_sort")) return e;
-      const uint64_t* sorted_keys = where ? bin.keys_b : bin.keys_a;
-      if (where)  // odd number of digit passes (<= 256 tiles): bring the sorted values home
-        cudaMemcpyAsync(bin.vals_a, bin.vals_b, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
-      { StageTimer t(PGS_STAGE_TILE_RANGES, s); launch_identify_tile_ranges(n, sorted_keys, img.ranges, s, count_dev); }
+      { StageTimer t(PGS_STAGE_TILE_RANGES, s); launch_identify_tile_ranges32(n, bin.tile_keys(0), img.ranges, s, count_dev); }
       if (int e = check_cuda("identify_tile_ranges")) return e;
       if (debug) if (int e = check_sync(s, "binning")) return e;
     }
@@ -396,8 +430,15 @@ static int forward_impl(const SqForward* sqf, bool part, int S, const float* sem
   if (speculate) {
     capacity = BinningState::capacity_for(capacity_hint[dev].load());
     if (int e = launch_rest(capacity, n_dev, 0)) return e;
+  } else {
+    // no capacity to speculate with (first frame, debug mode): count first, as the reference does
+    launch_inclusive_scan_u32(geom.tiles_touched, geom.point_offsets, P, geom.scan_temp, s);
+    if (int e = check_cuda("scan")) return e;
+    cudaError_t ce0 = cudaMemcpyAsync(cf.host, geom.point_offsets + P - 1, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (ce0 != cudaSuccess) return set_error(PGS_ERR_CUDA, "memcpy num_rendered: %s", cudaGetErrorString(ce0));
+    cudaEventRecord(cf.ev, s);
   }
-  ce = cudaEventSynchronize(cf.ev);
+  cudaError_t ce = cudaEventSynchronize(cf.ev);
   if (ce != cudaSuccess) return set_error(PGS_ERR_CUDA, "scan/num_rendered: %s", cudaGetErrorString(ce));
   const int num_rendered = *cf.host;
   if (num_rendered < 0) return set_error(PGS_ERR_UNSUPPORTED, "more than 2^31 surfel-tile instances");
@@ -953,8 +994,26 @@ int pgs_dsr_duplicate_with_keys(int P, const char* geom_buffer, int width, int h
   char* p = const_cast<char*>(geom_buffer);
   GeomState geom = GeomState::from(p, P);
   if (!radii) radii = geom.radii;
+  launch_inclusive_scan_u32(geom.tiles_touched, geom.point_offsets, P, geom.scan_temp, (cudaStream_t)stream);
   launch_duplicate_with_keys(P, geom.rec, geom.point_offsets, keys, values, radii, gx, gy, (cudaStream_t)stream);
   return check_cuda("duplicate_with_keys");
+}
+int pgs_dsr_sorted_keys(int P, int width, int height, const char* geom_buffer, const char* binning_buffer,
+                        size_t binning_bytes, int num_rendered, uint64_t* keys, void* stream) {
+  if (P <= 0 || width <= 0 || height <= 0 || !geom_buffer || !binning_buffer || num_rendered < 0 ||
+      (num_rendered > 0 && !keys))
+    return set_error(PGS_ERR_INVALID_ARG, "bad args");
+  const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+  const int end_bit = 32 + (int)higher_msb(gx * gy);
+  const size_t cap = BinningState::capacity_from_bytes(binning_bytes, end_bit);
+  if (cap == 0 || (size_t)num_rendered > cap)
+    return set_error(PGS_ERR_INVALID_ARG, "binning buffer size %zu matches no capacity", binning_bytes);
+  char* gp = const_cast<char*>(geom_buffer);
+  GeomState geom = GeomState::from(gp, P);
+  char* bp = const_cast<char*>(binning_buffer);
+  BinningState bin = BinningState::from(bp, cap, end_bit);
+  launch_rebuild_sorted_keys(num_rendered, bin.tile_keys(0), bin.vals_a, geom.rec, keys, (cudaStream_t)stream);
+  return check_cuda("rebuild_sorted_keys");
 }
 int pgs_identify_tile_ranges(int L, const uint64_t* sorted_keys, uint32_t* ranges, int ntiles, void* stream) {
   if (L < 0 || ntiles <= 0 || !ranges || (L > 0 && !sorted_keys)) return set_error(PGS_ERR_INVALID_ARG, "bad args");

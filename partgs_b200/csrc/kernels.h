@@ -45,6 +45,8 @@ struct PreprocessFwdArgs {
   float4* rec;    // [P][REC_QUADS]
   float4* bbox;   // [P][CULL_QUADS] cull records (box + conic)
   uint32_t* tiles_touched;
+  uint32_t* depth_key;  // [P] bits of the view depth; 0xffffffff for culled surfels (they sort to the end)
+  uint2* rect;          // [P] tile rectangle {x0 | x1 << 16, y0 | y1 << 16}; empty for culled surfels
   // block-level mode: surfel i is generated in the kernel from the superquadric parameters (means3D, scales,
   // rotations, opacities are then ignored); sq_out_* optionally materialise what was generated
   bool use_sq;
@@ -87,6 +89,43 @@ int launch_radix_sort_pairs32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys
 // reference identifyTileRanges (rasterizer_impl.cu:116-138); ranges must be zeroed first.
 void launch_identify_tile_ranges(int L, const uint64_t* keys, uint2* ranges, cudaStream_t s,
                                  const uint32_t* n_dev = nullptr);
+void launch_identify_tile_ranges32(int L, const uint32_t* tile_keys, uint2* ranges, cudaStream_t s,
+                                   const uint32_t* n_dev = nullptr);
+
+// ---- production binning path: depth-ordered emission + tile-id sort (binning.cu) ------------------------------
+#define PGS_RS_MAX_PASSES 8
+struct RsPlan {  // digit passes of a radix sort
+  int passes;
+  int shift[PGS_RS_MAX_PASSES];
+  int bits[PGS_RS_MAX_PASSES];
+};
+RsPlan rs_plan_even(int end_bit);
+// index sort: (keys_a, positions) sorted by keys_a on bits [0, end_bit); vals_a is scratch.  Returns where (0: a, 1: b)
+int launch_radix_sort_index32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, int n,
+                              int end_bit, void* temp, cudaStream_t s);
+size_t radix_sort_plan_temp_bytes(int n, const RsPlan& pl);
+void radix_sort_plan_prepare(int n, const RsPlan& pl, void* temp, cudaStream_t s);  // zero histograms + look-back
+// sort whose digit histograms were accumulated into `temp` by launch_emit_instances (after radix_sort_plan_prepare)
+int launch_radix_sort_plan32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, int n,
+                             const RsPlan& pl, void* temp, cudaStream_t s, const uint32_t* n_dev);
+struct EmitArgs {
+  int P;
+  const uint32_t* sorted_ids;  // [P] surfel indices in depth order (culled surfels last)
+  const uint2* rect;           // [P] tile rectangles written by preprocess
+  unsigned gx;
+  uint32_t* keys;              // [capacity] out: tile id of every instance
+  uint32_t* vals;              // [capacity] out: surfel index of every instance
+  uint32_t capacity;
+  uint32_t* total;             // out: number of instances of the frame
+  uint32_t* hist;              // digit histograms of the tile sort (head of its temp storage)
+  RsPlan plan;
+  uint32_t* counter;           // set by the launcher
+  unsigned long long* state;   // set by the launcher
+};
+size_t emit_state_bytes(int P);
+void launch_emit_instances(const EmitArgs& a, void* state_mem, cudaStream_t s);
+void launch_rebuild_sorted_keys(int L, const uint32_t* tile_keys, const uint32_t* point_list, const float4* rec,
+                                uint64_t* keys, cudaStream_t s);
 
 // ---- render -----------------------------------------------------------------
 // tile ids sorted longest-list-first (launch order of the render kernels)

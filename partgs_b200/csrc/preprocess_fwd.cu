@@ -257,6 +257,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessFwdArgs a
   if (idx < a.P) do {
     a.radii[idx] = 0;
     a.tiles_touched[idx] = 0;
+    a.depth_key[idx] = 0xffffffffu;
+    a.rect[idx] = make_uint2(0u, 0u);
     if (SQ) {
       sf = sq_generate(a.sq, a.sq_vertices, idx);
       if (a.sq_out_xyz) { a.sq_out_xyz[3 * idx] = sf.mean.x; a.sq_out_xyz[3 * idx + 1] = sf.mean.y; a.sq_out_xyz[3 * idx + 2] = sf.mean.z; }
@@ -347,6 +349,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessFwdArgs a
 
   a.radii[idx] = (int)radius;
   a.tiles_touched[idx] = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
+  a.depth_key[idx] = __float_as_uint(p_view.z);
+  a.rect[idx] = make_uint2(rect_min.x | (rect_max.x << 16), rect_min.y | (rect_max.y << 16));
 }
 
 // =============================================================================
@@ -409,6 +413,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_part_kernel(PreprocessFwdA
   if (idx >= a.P) return;
   a.radii[idx] = 0;
   a.tiles_touched[idx] = 0;
+  a.depth_key[idx] = 0xffffffffu;
+  a.rect[idx] = make_uint2(0u, 0u);
 
   const int W = a.W, H = a.H;
   const float* orig_points = a.means3D;
@@ -454,6 +460,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_part_kernel(PreprocessFwdA
   cull_record(T, center, opa, a.bbox + (size_t)idx * CULL_QUADS);
   a.radii[idx] = (int)radius;
   a.tiles_touched[idx] = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
+  a.depth_key[idx] = __float_as_uint(p_view.z);
+  a.rect[idx] = make_uint2(rect_min.x | (rect_max.x << 16), rect_min.y | (rect_max.y << 16));
 }
 
 void launch_preprocess_fwd_part(const PreprocessFwdArgs& a, cudaStream_t s) {

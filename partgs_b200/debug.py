@@ -7,6 +7,7 @@ reference's GeometryState / ImageState / BinningState::fromChunk expose
 from __future__ import annotations
 
 import ctypes as C
+from contextlib import nullcontext as _nullcontext
 
 import torch
 
@@ -59,7 +60,14 @@ def parse_state(geom: torch.Tensor, img: torch.Tensor, binning: torch.Tensor, P:
         ranges=_view(img, lay.image_ranges, 8 * nt, torch.int32, (nt, 2)),
     )
     if R > 0:
+        # the production path sorts by depth, then by tile id, and never materialises the reference's 64-bit keys:
+        # rebuild them (into the arena's spare key region) for the comparison with BinningState::point_list_keys
         out["point_list_keys"] = _view(binning, lay.binning_keys_sorted, 8 * R, torch.int64, (R,))
+        with torch.cuda.device(geom.device) if geom.is_cuda else _nullcontext():
+            _lib.check(_lib.load().pgs_dsr_sorted_keys(P, W, H, geom.data_ptr(), binning.data_ptr(), binning.numel(), R,
+                                                       out["point_list_keys"].data_ptr(),
+                                                       _lib.current_stream(geom.device) if geom.is_cuda else None),
+                       "pgs_dsr_sorted_keys")
         out["point_list"] = _view(binning, lay.binning_point_list, 4 * R, torch.int32, (R,))
         # [8 warps][R]: bit l of frag_mask[w][i] = pixel (lane l of warp w's 8x4 footprint) blended instance i
         ms = lay.binning_mask_stride
