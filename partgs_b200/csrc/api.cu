@@ -326,6 +326,9 @@ static int forward_impl(const SqForward* sqf, bool part, int S, const float* sem
   pa.W = width; pa.H = height; pa.grid_x = gx; pa.grid_y = gy;
   pa.radii = radii; pa.rec = geom.rec; pa.bbox = geom.bbox; pa.tiles_touched = geom.tiles_touched;
   pa.depth_key = geom.dkey_a; pa.rect = geom.rect;
+  // base fork: preprocess accumulates the digit histograms of the depth sort (head of its temp storage)
+  pa.depth_hist = part ? nullptr : reinterpret_cast<uint32_t*>(geom.dsort_temp);
+  radix_sort32_prepare(P, 32, geom.dsort_temp, s);
   pa.focal_y = height / (2.0f * tan_fovy);
   pa.focal_x = width / (2.0f * tan_fovx);
   pa.use_sq = sqf != nullptr;
@@ -348,7 +351,7 @@ static int forward_impl(const SqForward* sqf, bool part, int S, const float* sem
   {
     StageTimer t(PGS_STAGE_SCAN, s);
     const int where = launch_radix_sort_index32(geom.dkey_a, geom.dval_a, geom.dkey_b, geom.dval_b, P, 32,
-                                                geom.dsort_temp, s);
+                                                geom.dsort_temp, s, /*hist_ready=*/pa.depth_hist != nullptr);
     if (where) return set_error(PGS_ERR_CUDA, "depth sort ended in the wrong buffer");  // 4 passes: never
   }
   if (int e = check_cuda("depth_sort")) return e;
@@ -374,7 +377,6 @@ static int forward_impl(const SqForward* sqf, bool part, int S, const float* sem
     BinningState bin = BinningState::from(bptr, capacity, end_bit);
     const int n = count_dev ? (int)capacity : count_host;  // launch size
 
-    cudaMemsetAsync(img.ranges, 0, ntiles * sizeof(uint2), s);
     // Emit the (tile, surfel) instances in depth order, then stable-sort them by tile id: the reference's
     // (tile | depth) order (duplicateWithKeys + SortPairs, rasterizer_impl.cu:70-111,301-309) with two digit
     // passes over R instead of six.  The sort must end in (tile_keys(0), vals_a): start in b for an odd pass count.
@@ -389,6 +391,7 @@ static int forward_impl(const SqForward* sqf, bool part, int S, const float* sem
       ea.P = P; ea.sorted_ids = geom.dval_a; ea.rect = geom.rect; ea.gx = (unsigned)gx;
       ea.keys = k0; ea.vals = v0; ea.capacity = (uint32_t)capacity; ea.total = geom.total;
       ea.hist = reinterpret_cast<uint32_t*>(bin.sort_temp); ea.plan = plan; ea.counter = nullptr; ea.state = nullptr;
+      ea.ranges = img.ranges; ea.ntiles = (int)ntiles;
       launch_emit_instances(ea, geom.emit_state, s);
     }
     if (int e = check_cuda("emit_instances")) return e;
@@ -399,10 +402,9 @@ static int forward_impl(const SqForward* sqf, bool part, int S, const float* sem
     }
     if (n > 0) {
       { StageTimer t(PGS_STAGE_SORT, s);
-        launch_radix_sort_plan32(k0, v0, k1, v1, n, plan, bin.sort_temp, s, count_dev); }
+        // identifyTileRanges (rasterizer_impl.cu:116-138) is fused into the last pass
+        launch_radix_sort_plan32(k0, v0, k1, v1, n, plan, bin.sort_temp, s, count_dev, img.ranges); }
       if (int e = check_cuda("radix_sort")) return e;
-      { StageTimer t(PGS_STAGE_TILE_RANGES, s); launch_identify_tile_ranges32(n, bin.tile_keys(0), img.ranges, s, count_dev); }
-      if (int e = check_cuda("identify_tile_ranges")) return e;
       if (debug) if (int e = check_sync(s, "binning")) return e;
     }
     launch_tile_order(img.ranges, (int)ntiles, img.tile_order, s);

@@ -277,7 +277,8 @@ __global__ void __launch_bounds__(RS_THREADS)
                        KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n_cap, int shift, int bits,
                        const uint32_t* __restrict__ bin_base,  // [256] exclusive global digit offsets
                        uint32_t* lookback,                     // [tiles][256]
-                       uint32_t* tile_counter, const uint32_t* __restrict__ n_dev) {
+                       uint32_t* tile_counter, const uint32_t* __restrict__ n_dev,
+                       uint2* __restrict__ ranges = nullptr) {  // last pass of the tile-id sort: see below
   extern __shared__ __align__(16) unsigned char rs_smem[];
   KeyT* s_keys = reinterpret_cast<KeyT*>(rs_smem);                                   // [RS_TILE]
   uint32_t* s_vals = reinterpret_cast<uint32_t*>(rs_smem + sizeof(KeyT) * RS_TILE);  // [RS_TILE]
@@ -420,6 +421,25 @@ __global__ void __launch_bounds__(RS_THREADS)
       uint32_t g = s_goff[d] + j;
       keys_out[g] = k;
       vals_out[g] = s_vals[j];
+      if (sizeof(KeyT) == 4 && ranges != nullptr) {
+        // identifyTileRanges (rasterizer_impl.cu:116-138) fused into the final scatter of the tile-id sort: the
+        // keys are tile ids and g is the element's final position.  Inside this CTA's run of a digit the
+        // neighbours are at hand; a tile may continue in another CTA's run, so starts / ends are combined with
+        // min / max (ranges are initialised to {0xffffffff, 0} by the emission kernel; tile_order_kernel turns
+        // untouched entries into the reference's {0, 0}).
+        const uint32_t t = (uint32_t)k;
+        bool first = (j == 0), last = (j == nvalid - 1);
+        if (!first) {
+          const uint32_t kp = (uint32_t)s_keys[j - 1];
+          first = kp != t;  // a different digit implies a different tile id
+        }
+        if (!last) {
+          const uint32_t kn = (uint32_t)s_keys[j + 1];
+          last = kn != t;
+        }
+        if (first) atomicMin(&ranges[t].x, g);
+        if (last) atomicMax(&ranges[t].y, g + 1);
+      }
     }
   }
 }
@@ -429,7 +449,8 @@ __global__ void __launch_bounds__(RS_THREADS)
 // `iota_vals`: vals_a holds nothing yet; the first pass takes each element's position as its value.
 template <typename KeyT>
 static int rs_sort(KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b, int n, const RsPlan& pl, void* temp,
-                   cudaStream_t s, const uint32_t* n_dev, bool hist_ready = false, bool iota_vals = false) {
+                   cudaStream_t s, const uint32_t* n_dev, bool hist_ready = false, bool iota_vals = false,
+                   uint2* ranges = nullptr) {
   if (n <= 0) return 0;
   const int passes = pl.passes;
   const int tiles = (n + RS_TILE - 1) / RS_TILE;
@@ -459,7 +480,7 @@ static int rs_sort(KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_
     rs_onesweep_kernel<KeyT><<<tiles, RS_THREADS, smem, s>>>(kin, (p == 0 && iota_vals) ? nullptr : vin, kout, vout, n,
                                                               pl.shift[p], pl.bits[p], hist + p * RS_RADIX,
                                                               lookback + (size_t)p * tiles * RS_RADIX, counters + p,
-                                                              n_dev);
+                                                              n_dev, p == passes - 1 ? ranges : nullptr);
     count_launch();
     KeyT* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
@@ -476,16 +497,19 @@ int launch_radix_sort_pairs32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys
   return rs_sort<uint32_t>(keys_a, vals_a, keys_b, vals_b, n, rs_plan_lsd8(end_bit), temp, s, nullptr);
 }
 int launch_radix_sort_index32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, int n,
-                              int end_bit, void* temp, cudaStream_t s) {
-  return rs_sort<uint32_t>(keys_a, vals_a, keys_b, vals_b, n, rs_plan_lsd8(end_bit), temp, s, nullptr, false, true);
+                              int end_bit, void* temp, cudaStream_t s, bool hist_ready) {
+  return rs_sort<uint32_t>(keys_a, vals_a, keys_b, vals_b, n, rs_plan_lsd8(end_bit), temp, s, nullptr, hist_ready, true);
+}
+void radix_sort32_prepare(int n, int end_bit, void* temp, cudaStream_t s) {
+  if (n > 0) cudaMemsetAsync(temp, 0, rs_temp_bytes<uint32_t>(n, end_bit), s);
 }
 size_t radix_sort_plan_temp_bytes(int n, const RsPlan& pl) { return rs_temp_bytes_passes(n, pl.passes); }
 void radix_sort_plan_prepare(int n, const RsPlan& pl, void* temp, cudaStream_t s) {
   if (n > 0) cudaMemsetAsync(temp, 0, rs_temp_bytes_passes(n, pl.passes), s);
 }
 int launch_radix_sort_plan32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, int n,
-                             const RsPlan& pl, void* temp, cudaStream_t s, const uint32_t* n_dev) {
-  return rs_sort<uint32_t>(keys_a, vals_a, keys_b, vals_b, n, pl, temp, s, n_dev, /*hist_ready=*/true);
+                             const RsPlan& pl, void* temp, cudaStream_t s, const uint32_t* n_dev, uint2* ranges) {
+  return rs_sort<uint32_t>(keys_a, vals_a, keys_b, vals_b, n, pl, temp, s, n_dev, /*hist_ready=*/true, false, ranges);
 }
 
 // =============================================================================
@@ -523,6 +547,9 @@ __global__ void __launch_bounds__(EM_THREADS) emit_instances_kernel(EmitArgs a) 
   const unsigned lane = tid & 31, wid = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(a.counter, 1u);
   for (int i = tid; i < a.plan.passes * RS_RADIX; i += EM_THREADS) s_hist[i] = 0;
+  // tile ranges start as {max, 0}: the last pass of the tile-id sort combines starts / ends with min / max
+  for (int i = blockIdx.x * EM_THREADS + tid; i < a.ntiles; i += gridDim.x * EM_THREADS)
+    a.ranges[i] = make_uint2(0xffffffffu, 0u);
   __syncthreads();
   const uint32_t tile = s_tile;
   const int base = tile * EM_TILE + tid * EM_ITEMS;

@@ -46,6 +46,7 @@ struct PreprocessFwdArgs {
   float4* bbox;   // [P][CULL_QUADS] cull records (box + conic)
   uint32_t* tiles_touched;
   uint32_t* depth_key;  // [P] bits of the view depth; 0xffffffff for culled surfels (they sort to the end)
+  uint32_t* depth_hist; // [4][256] digit histograms of depth_key, accumulated here (zeroed by the caller); or nullptr
   uint2* rect;          // [P] tile rectangle {x0 | x1 << 16, y0 | y1 << 16}; empty for culled surfels
   // block-level mode: surfel i is generated in the kernel from the superquadric parameters (means3D, scales,
   // rotations, opacities are then ignored); sq_out_* optionally materialise what was generated
@@ -101,13 +102,17 @@ struct RsPlan {  // digit passes of a radix sort
 };
 RsPlan rs_plan_even(int end_bit);
 // index sort: (keys_a, positions) sorted by keys_a on bits [0, end_bit); vals_a is scratch.  Returns where (0: a, 1: b)
+// hist_ready: the four digit histograms were accumulated into `temp` by the producer of the keys (preprocess,
+// after radix_sort32_prepare zeroed it)
 int launch_radix_sort_index32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, int n,
-                              int end_bit, void* temp, cudaStream_t s);
+                              int end_bit, void* temp, cudaStream_t s, bool hist_ready = false);
+void radix_sort32_prepare(int n, int end_bit, void* temp, cudaStream_t s);
 size_t radix_sort_plan_temp_bytes(int n, const RsPlan& pl);
 void radix_sort_plan_prepare(int n, const RsPlan& pl, void* temp, cudaStream_t s);  // zero histograms + look-back
 // sort whose digit histograms were accumulated into `temp` by launch_emit_instances (after radix_sort_plan_prepare)
 int launch_radix_sort_plan32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, int n,
-                             const RsPlan& pl, void* temp, cudaStream_t s, const uint32_t* n_dev);
+                             const RsPlan& pl, void* temp, cudaStream_t s, const uint32_t* n_dev,
+                             uint2* ranges = nullptr);  // ranges: identifyTileRanges fused into the last pass
 struct EmitArgs {
   int P;
   const uint32_t* sorted_ids;  // [P] surfel indices in depth order (culled surfels last)
@@ -118,6 +123,8 @@ struct EmitArgs {
   uint32_t capacity;
   uint32_t* total;             // out: number of instances of the frame
   uint32_t* hist;              // digit histograms of the tile sort (head of its temp storage)
+  uint2* ranges;               // [ntiles] initialised here to {0xffffffff, 0}
+  int ntiles;
   RsPlan plan;
   uint32_t* counter;           // set by the launcher
   unsigned long long* state;   // set by the launcher
@@ -129,7 +136,8 @@ void launch_rebuild_sorted_keys(int L, const uint32_t* tile_keys, const uint32_t
 
 // ---- render -----------------------------------------------------------------
 // tile ids sorted longest-list-first (launch order of the render kernels)
-void launch_tile_order(const uint2* ranges, int ntiles, uint32_t* order, cudaStream_t s);
+// also rewrites tile ranges that were never touched ({0xffffffff, 0}, see EmitArgs::ranges) as {0, 0}
+void launch_tile_order(uint2* ranges, int ntiles, uint32_t* order, cudaStream_t s);
 
 struct RenderFwdArgs {
   const uint2* ranges;

@@ -295,6 +295,31 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessFwdArgs a
     vis = true;
   } while (0);
 
+  // Digit histograms of the depth keys for the depth sort that follows (binning.cu), accumulated here so that the
+  // sort needs no histogram pass of its own.  Culled surfels carry the key 0xffffffff.
+  if (a.depth_hist != nullptr) {
+    __shared__ uint32_t s_dh[4 * 256];
+    for (int i = threadIdx.x; i < 4 * 256; i += 256) s_dh[i] = 0;
+    __syncthreads();
+    const bool live = idx < a.P;
+    const uint32_t key = vis ? __float_as_uint(p_view.z) : 0xffffffffu;
+    if (live) {
+      atomicAdd(&s_dh[key & 0xffu], 1u);  // the low digits are spread out ...
+      atomicAdd(&s_dh[256 + ((key >> 8) & 0xffu)], 1u);
+    }
+#pragma unroll
+    for (int p = 2; p < 4; p++) {  // ... the high ones take a handful of values: one atomic per value and warp
+      const uint32_t d = live ? ((key >> (8 * p)) & 0xffu) : (0x100u + lane);
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      if (live && (int)lane == __ffs(peers) - 1) atomicAdd(&s_dh[p * 256 + d], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * 256; i += 256) {
+      const uint32_t c = s_dh[i];
+      if (c) atomicAdd(&a.depth_hist[i], c);
+    }
+  }
+
   float r, g, b;
   unsigned clamped = 0;
   if (a.colors_precomp == nullptr) {

@@ -99,17 +99,37 @@ __device__ __forceinline__ bool conic_hits(const float4 c1, const float4 c2, flo
 // tile order: longest list first (approximate LPT by counting sort on len/16)
 // =============================================================================
 constexpr int TO_BUCKETS = 1024;
-__global__ void __launch_bounds__(1024) tile_order_kernel(const uint2* __restrict__ ranges, int ntiles,
+__global__ void __launch_bounds__(1024) tile_order_kernel(uint2* __restrict__ ranges, int ntiles,
                                                           uint32_t* __restrict__ order) {
   __shared__ uint32_t s_cnt[TO_BUCKETS];
   __shared__ uint32_t s_warp[32];
   const int tid = threadIdx.x;
   s_cnt[tid] = 0;
   __syncthreads();
-  for (int t = tid; t < ntiles; t += blockDim.x) {
-    const uint2 r = ranges[t];
-    const uint32_t b = TO_BUCKETS - 1 - min((r.y - r.x) >> 4, (uint32_t)(TO_BUCKETS - 1));  // long lists -> small bucket
-    atomicAdd(&s_cnt[b], 1u);
+  // Tiles without instances still carry the {0xffffffff, 0} the fused range detection starts from (binning.cu):
+  // they become the reference's {0, 0} here.  Eight tiles per thread and round, so that the loads overlap.
+  constexpr int U = 8;
+  auto bucket_of = [](uint2 r) -> uint32_t {  // long lists -> small bucket
+    return TO_BUCKETS - 1 - min((r.y - r.x) >> 4, (uint32_t)(TO_BUCKETS - 1));
+  };
+  for (int t0 = 0; t0 < ntiles; t0 += U * 1024) {
+    uint2 r[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int t = t0 + u * 1024 + tid;
+      r[u] = t < ntiles ? ranges[t] : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int t = t0 + u * 1024 + tid;
+      if (t < ntiles) {
+        if (r[u].x > r[u].y) {
+          r[u] = make_uint2(0u, 0u);
+          ranges[t] = r[u];
+        }
+        atomicAdd(&s_cnt[bucket_of(r[u])], 1u);
+      }
+    }
   }
   __syncthreads();
   // exclusive scan of the 1024 bucket counts
@@ -129,14 +149,22 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const uint2* __restric
   __syncthreads();
   s_cnt[tid] = off + w - c;
   __syncthreads();
-  for (int t = tid; t < ntiles; t += blockDim.x) {
-    const uint2 r = ranges[t];
-    const uint32_t b = TO_BUCKETS - 1 - min((r.y - r.x) >> 4, (uint32_t)(TO_BUCKETS - 1));
-    order[atomicAdd(&s_cnt[b], 1u)] = (uint32_t)t;
+  for (int t0 = 0; t0 < ntiles; t0 += U * 1024) {
+    uint2 r[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int t = t0 + u * 1024 + tid;
+      r[u] = t < ntiles ? ranges[t] : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int t = t0 + u * 1024 + tid;
+      if (t < ntiles) order[atomicAdd(&s_cnt[bucket_of(r[u])], 1u)] = (uint32_t)t;
+    }
   }
 }
 
-void launch_tile_order(const uint2* ranges, int ntiles, uint32_t* order, cudaStream_t s) {
+void launch_tile_order(uint2* ranges, int ntiles, uint32_t* order, cudaStream_t s) {
   if (ntiles <= 0) return;
   tile_order_kernel<<<1, 1024, 0, s>>>(ranges, ntiles, order);
   count_launch();
