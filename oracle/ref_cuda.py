@@ -130,6 +130,11 @@ def backward(fwd, scene, cam, bg, dL_dcolor, dL_dallmap, sh_degree=3, scale_modi
     return dict(zip(names, C.rasterize_gaussians_backward(*args)))
 
 
+def mark_visible(means3D, cam, module="ref_dsr_C"):
+    """_C.mark_visible of the reference (rasterize_points.cu:235-254)."""
+    return load(module).mark_visible(means3D, cam.viewmatrix, cam.projmatrix)
+
+
 # ---- `_part` fork (ref_dsrp_C) ------------------------------------------------------
 def forward_part(scene, cam, bg, sh_degree=3, scale_modifier=1.0):
     """_C.rasterize_gaussians of the fork (DSRP/rasterize_points.cu:39-146)."""

@@ -222,6 +222,19 @@ def require_cuda_float(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
+def require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    """Rasteriser inputs: float32 CUDA tensors only, like the reference's `.contiguous().data<float>()`
+    (rasterize_points.cu:104-126), which raises on any other dtype.  (A silent conversion here would hand the
+    ORIGINAL tensor to backward and a float32 gradient to a non-float32 leaf.)"""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not on_device(t):
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name}: expected scalar type Float but found {str(t.dtype).replace('torch.', '')}")
+    return t.contiguous()
+
+
 STAGES = ("preprocess_fwd", "scan", "dup_keys", "sort", "tile_ranges", "render_fwd", "render_bwd", "preprocess_bwd",
           "knn", "sq_fwd", "sq_bwd", "surface_fwd", "surface_bwd", "photo_fwd", "photo_bwd")
 

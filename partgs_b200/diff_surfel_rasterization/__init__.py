@@ -38,18 +38,18 @@ def _native_forward(bg, means3D, colors, opacity, scales, rotations, scale_modif
     lib = _lib.load()
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
-    means3D = _lib.require_cuda_float(means3D, "means3D")
+    means3D = _lib.require_cuda_f32(means3D, "means3D")
     dev = means3D.device
-    bg = _lib.require_cuda_float(bg, "background")
-    colors = _lib.require_cuda_float(colors, "colors")
-    opacity = _lib.require_cuda_float(opacity, "opacity")
-    scales = _lib.require_cuda_float(scales, "scales")
-    rotations = _lib.require_cuda_float(rotations, "rotations")
-    transMat_precomp = _lib.require_cuda_float(transMat_precomp, "transMat_precomp")
-    viewmatrix = _lib.require_cuda_float(viewmatrix, "viewmatrix")
-    projmatrix = _lib.require_cuda_float(projmatrix, "projmatrix")
-    sh = _lib.require_cuda_float(sh, "sh")
-    campos = _lib.require_cuda_float(campos, "campos")
+    bg = _lib.require_cuda_f32(bg, "background")
+    colors = _lib.require_cuda_f32(colors, "colors")
+    opacity = _lib.require_cuda_f32(opacity, "opacity")
+    scales = _lib.require_cuda_f32(scales, "scales")
+    rotations = _lib.require_cuda_f32(rotations, "rotations")
+    transMat_precomp = _lib.require_cuda_f32(transMat_precomp, "transMat_precomp")
+    viewmatrix = _lib.require_cuda_f32(viewmatrix, "viewmatrix")
+    projmatrix = _lib.require_cuda_f32(projmatrix, "projmatrix")
+    sh = _lib.require_cuda_f32(sh, "sh")
+    campos = _lib.require_cuda_f32(campos, "campos")
 
     P = means3D.size(0)
     H, W = int(image_height), int(image_width)

@@ -37,9 +37,9 @@ def _native_forward(bg, means3D, colors, opacity, semantics, scales, rotations, 
     lib = _lib.load()
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
-    means3D = _lib.require_cuda_float(means3D, "means3D")
+    means3D = _lib.require_cuda_f32(means3D, "means3D")
     dev = means3D.device
-    rq = _lib.require_cuda_float
+    rq = _lib.require_cuda_f32
     bg, colors, opacity, semantics = rq(bg, "background"), rq(colors, "colors"), rq(opacity, "opacity"), \
         rq(semantics, "semantics")
     scales, rotations, transMat_precomp = rq(scales, "scales"), rq(rotations, "rotations"), \

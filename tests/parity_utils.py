@@ -48,6 +48,22 @@ def grad_violations(a: torch.Tensor, b: torch.Tensor, rtol: float = GRAD_RTOL, a
     return ((a - b).abs() > tol).double().mean().item()
 
 
+def assert_grad_close(name: str, ours: torch.Tensor, ref: torch.Tensor, rtol: float = GRAD_RTOL, afloor: float = 1e-6):
+    """north_star gradient gate, ELEMENT-wise: every entry within rtol * |ref| + afloor * max|ref| (see grad_violations),
+    plus the norm-wise bound.  On failure reports the fraction and the worst offender."""
+    assert ours.shape == ref.shape, (name, ours.shape, ref.shape)
+    if ours.numel() == 0:
+        return
+    frac = grad_violations(ours, ref, rtol, afloor)
+    e = rel_err(ours, ref)
+    if frac > 0.0 or e > rtol:
+        a, b = ours.double().flatten(), ref.double().flatten()
+        excess = (a - b).abs() - (rtol * b.abs() + afloor * b.abs().max())
+        i = int(excess.argmax())
+        raise AssertionError(f"{name}: {frac:.3e} of {a.numel()} elements outside {rtol:g}*|ref| + {afloor:g}*max|ref|; "
+                             f"worst: ours {a[i].item():.9g} vs ref {b[i].item():.9g}; norm-wise rel err {e:.3e}")
+
+
 def assert_equal_images(name: str, ours: torch.Tensor, ref: torch.Tensor):
     """Bit-identical images (base fork: the per-fragment rounding sequence is pinned in frag_math.cuh)."""
     if not torch.equal(ours, ref):

@@ -38,6 +38,18 @@ def run_ours(scene, cam, bg, g=None):
     return out
 
 
+def _check_images(o, ref):
+    """Part map and the 8 auxiliary maps: bit-identical.  Colour: the fork's SH polynomial is contracted differently
+    by nvcc in the two builds, so the per-surfel rgb differs in the last bit -> within 1e-5 of the image range and
+    element-wise within a few ulps of the accumulated value."""
+    pu.assert_equal_images("semantic", o["semantic"], ref["semantic"])
+    for ch in range(8):
+        pu.assert_equal_images(f"allmap[{ch}]", o["allmap"][ch], ref["allmap"][ch])
+    assert pu.rel_err(o["color"], ref["color"]) <= pu.IMG_RTOL
+    d = (o["color"].double() - ref["color"].double()).abs()
+    assert float((d - (4e-7 * ref["color"].double().abs() + 4e-7)).max()) <= 0.0, float(d.max())
+
+
 @pytest.mark.parametrize("P,W,H,S", [(20_000, 400, 300, 16), (150_000, 800, 600, 16), (50_000, 333, 201, 5)])
 def test_part_forward_backward_vs_reference(P, W, H, S):
     from oracle import ref_cuda
@@ -49,14 +61,10 @@ def test_part_forward_backward_vs_reference(P, W, H, S):
         o = run_ours(scene, cam, bg, g)
         assert torch.equal(o["radii"], ref["radii"])
         assert o["allmap"].shape == (8, H, W) and o["semantic"].shape == (S, H, W)
-        assert pu.rel_err(o["color"], ref["color"]) <= pu.IMG_RTOL
-        assert pu.rel_err(o["semantic"], ref["semantic"]) <= pu.IMG_RTOL
-        for ch in range(8):
-            assert pu.rel_err(o["allmap"][ch], ref["allmap"][ch]) <= pu.IMG_RTOL, f"allmap[{ch}]"
+        _check_images(o, ref)
         gref = ref_cuda.backward_part(ref, scene, cam, bg, g["color"], g["semantic"], g["allmap"])
         for k in ("means3D", "means2D", "opacity", "scales", "rotations", "sh", "semantics"):
-            e = pu.rel_err(o["grads"][k], gref[k].view_as(o["grads"][k]))
-            assert e <= pu.GRAD_RTOL, (k, e)
+            pu.assert_grad_close(k, o["grads"][k], gref[k].view_as(o["grads"][k]))
 
 
 def test_part_c4_full_size_properties():
@@ -72,8 +80,12 @@ def test_part_c4_full_size_properties():
     if ref_cuda.available("ref_dsrp_C"):
         ref = ref_cuda.forward_part(scene, cams[0], bg)
         assert torch.equal(o["radii"], ref["radii"])
-        assert pu.rel_err(o["semantic"], ref["semantic"]) <= pu.IMG_RTOL
-        assert pu.rel_err(o["allmap"], ref["allmap"]) <= pu.IMG_RTOL
+        _check_images(o, ref)
+        # backward at the full C4 size
+        og = run_ours(scene, cams[0], bg, g)
+        gref = ref_cuda.backward_part(ref, scene, cams[0], bg, g["color"], g["semantic"], g["allmap"])
+        for k in ("means3D", "means2D", "opacity", "scales", "rotations", "sh", "semantics"):
+            pu.assert_grad_close(k, og["grads"][k], gref[k].view_as(og["grads"][k]))
 
 
 def test_part_rejects_more_than_16_channels():
