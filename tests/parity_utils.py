@@ -48,15 +48,17 @@ def grad_violations(a: torch.Tensor, b: torch.Tensor, rtol: float = GRAD_RTOL, a
     return ((a - b).abs() > tol).double().mean().item()
 
 
-def assert_grad_close(name: str, ours: torch.Tensor, ref: torch.Tensor, rtol: float = GRAD_RTOL, afloor: float = 1e-6):
+def assert_grad_close(name: str, ours: torch.Tensor, ref: torch.Tensor, rtol: float = GRAD_RTOL, afloor: float = 1e-6,
+                      max_frac: float = 0.0):
     """north_star gradient gate, ELEMENT-wise: every entry within rtol * |ref| + afloor * max|ref| (see grad_violations),
-    plus the norm-wise bound.  On failure reports the fraction and the worst offender."""
+    plus the norm-wise bound.  On failure reports the fraction and the worst offender.  `max_frac`: fraction of entries
+    allowed outside (0 unless the caller measured the reference's own run-to-run level for the case)."""
     assert ours.shape == ref.shape, (name, ours.shape, ref.shape)
     if ours.numel() == 0:
         return
     frac = grad_violations(ours, ref, rtol, afloor)
     e = rel_err(ours, ref)
-    if frac > 0.0 or e > rtol:
+    if frac > max_frac or not (e <= rtol):
         a, b = ours.double().flatten(), ref.double().flatten()
         excess = (a - b).abs() - (rtol * b.abs() + afloor * b.abs().max())
         i = int(excess.argmax())

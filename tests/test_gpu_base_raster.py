@@ -151,9 +151,13 @@ def test_full_size_c3_properties():
         assert torch.equal(st["point_list"], rb["point_list"])
         assert torch.equal(keys, rb["point_list_keys"])
         gref = ref_cuda.backward(ref, scene, cam, bg, g["color"], g["allmap"])
+        gref2 = ref_cuda.backward(ref, scene, cam, bg, g["color"], g["allmap"])
         o = pu.run_ours(scene, cam, bg, grads=g)
         for k in ("means3D", "means2D", "opacity", "scales", "rotations", "sh"):
-            pu.assert_grad_close(k, o["grads"][k], gref[k].view_as(o["grads"][k]))
+            # at this size a few of the reference's own entries move between two runs (its float atomics commit in a
+            # different order): allow that level, measured here, and no more than 5e-6 of the entries
+            noise = pu.grad_violations(gref2[k], gref[k])
+            pu.assert_grad_close(k, o["grads"][k], gref[k].view_as(o["grads"][k]), max_frac=min(5e-6, max(2e-6, 4 * noise)))
 
 
 def test_binning_primitives_edge_cases():
@@ -341,3 +345,24 @@ def test_non_float32_inputs_are_rejected_like_the_reference():
         bad = dict(kw); bad[k] = kw[k].to(dt)
         with pytest.raises(RuntimeError, match="expected scalar type Float"):
             rast(**bad)
+
+
+@pytest.mark.parametrize("channel,scale", [(6, 1e4), (0, 1e4), (1, 1e4), ("color", 1e4)])
+def test_backward_with_one_dominant_channel_vs_reference(channel, scale):
+    """train.py weighs the distortion map with lambda_dist = 1000 (DTU) against O(1) photometric terms: the gradient is
+    then dominated by d(rend_dist), whose per-fragment factor m_d^2 A - 2 m_d D + D2 is a near-cancelling sum — the
+    backward kernel evaluates it (and the ray-splat depth it depends on) with the reference build's rounding
+    sequence, so the element-wise gate holds in that regime too.  Other channels dominant: same gate."""
+    ref_cuda = _ref()
+    cfg, scene, cams, bg, g0 = _setup("C2", 60_000, views=1)
+    cam = cams[0]
+    g = {k: v.clone() for k, v in g0.items()}
+    if channel == "color":
+        g["color"] *= scale
+    else:
+        g["allmap"][channel] *= scale
+    ref = ref_cuda.forward(scene, cam, bg)
+    gref = ref_cuda.backward(ref, scene, cam, bg, g["color"], g["allmap"])
+    o = pu.run_ours(scene, cam, bg, grads=g)
+    for k in ("means3D", "means2D", "opacity", "scales", "rotations", "sh"):
+        pu.assert_grad_close(k, o["grads"][k], gref[k].view_as(o["grads"][k]))
