@@ -5,8 +5,10 @@
 
 A "step" is one view rendered forward + backward (all 3+7 output channels receive a
 fixed synthetic upstream gradient) over the workload's resident surfel set; at N>1 every
-rank renders its own cameras (views shard by camera, surfel parameters replicated) and
-the per-step parameter gradients are all-reduced over NCCL.
+rank renders its own cameras (views shard by camera, surfel parameters replicated), the
+parameter gradients of a rank accumulate over its ceil(views / N) views of a batch and ONE
+all-reduce per batch sums them over the ranks; the per-view all-reduce
+and the no-collective numbers are reported beside it (`collective_modes`).
 
 One JSON line on rank 0; see DESIGN.md §Measurement for how each field is derived.
 `--impl reference` times the UNMODIFIED reference CUDA rasteriser (oracle/_ref, built
@@ -298,51 +300,99 @@ def run(args):
     if world > 1:
         import torch.distributed as dist
 
-    pending = []
-    peer = None
-    if world > 1 and arm.name == "ours" and args.collective == "peer" and not args.no_allreduce:
-        # gradients are produced straight into peer-mapped memory and summed by copy-engine transfers over
-        # NVLink (partgs_b200.dist.PeerGradAllReducer): no NCCL kernel competes with the render kernels for SMs
-        from partgs_b200.dist import PeerGradAllReducer
+    # ---- data-parallel batch: accum views per rank and batch, one all-reduce per batch ----------
+    accum = args.accum if args.accum > 0 else (len(all_cams) + world - 1) // world
+    reducer = None
+    if world > 1 and arm.name == "ours":
+        # the backward kernel accumulates the batch in ONE bucket (232 B/surfel) that lives in peer-mapped memory and
+        # is reduced by one kernel over NVLink (partgs_b200.dist.PeerGradAllReducer), or by one NCCL all-reduce
+        from partgs_b200.dist import NcclBucketAllReducer, PeerGradAllReducer
         from partgs_b200 import diff_surfel_rasterization as dsr
-        numel = sum((n + 63) // 64 * 64 for n in (P * 3, P * 16 * 3, P, P * 2, P * 4))
-        peer = PeerGradAllReducer(numel, dev)
-        dsr.set_grad_bucket_provider(peer.bucket_provider)
+        numel = dsr.bucket_numel(P, 16)
+        reducer = PeerGradAllReducer(numel, dev) if args.collective == "peer" else NcclBucketAllReducer(numel, dev)
+        dsr.set_grad_bucket_provider(reducer.bucket_provider)
+    ref_acc, ref_pending = [], []   # reference arm: gradients accumulated with torch adds, NCCL all-reduce per batch
 
-    def allreduce_grads(grads):
-        # one asynchronous all-reduce of the 232 B/surfel gradient bucket per step, overlapped with the next
-        # step's kernels; the previous step's collective is waited on before the next one is launched
-        if peer is not None:
-            peer.wait()
-            peer.launch(grads)
+    state = {"mode": "per_batch", "in_batch": 0}
+
+    def close_batch(grads):
+        """All-reduce what the batch accumulated (asynchronously: it overlaps the next batch's kernels)."""
+        state["in_batch"] = 0
+        if world == 1 or state["mode"] == "none":
+            if reducer is not None:
+                reducer._open = False          # the next backward opens a fresh batch (nothing is reduced)
             return
-        for h in pending:
+        if reducer is not None:
+            reducer.wait()                     # the previous batch's collective (launched a whole batch ago)
+            reducer.launch(grads)
+            return
+        for h in ref_pending:
             h.wait()
-        pending.clear()
-        if world > 1 and not args.no_allreduce:
-            from partgs_b200.dist import grad_bucket
-            bucket = grad_bucket(grads)  # ours: the five gradients are views of one flat buffer
-            for t in ([bucket] if bucket is not None else grads):
-                pending.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
-
-    def drain():
-        if peer is not None:
-            peer.wait()
-        for h in pending:
-            h.wait()
-        pending.clear()
-
-    schedule = None  # balanced per-step view assignment (N > 1), built after the first pass over the views
-
-    def cam_of_step(i):
-        if schedule is not None:
-            return all_cams[schedule[i % len(schedule)][rank]]
-        return my_cams[i % len(my_cams)]
+        ref_pending.clear()
+        for t in grads:
+            ref_pending.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
 
     def one_step(i):
+        per = 1 if state["mode"] == "per_view" else accum
+        first = state["in_batch"] == 0
+        if first and reducer is not None:
+            reducer.begin_batch()
         loss, grads = arm.step(cam_of_step(i), bg, g)
-        allreduce_grads(grads)
-        return loss
+        if reducer is None and world > 1 and per > 1 and state["mode"] != "none":
+            # reference arm: what train.py would do with a data-parallel batch — accumulate in torch
+            if first:
+                for h in ref_pending:
+                    h.wait()
+                ref_pending.clear()
+                if not ref_acc:
+                    ref_acc.extend(torch.empty_like(t) for t in grads)
+                for a_, t in zip(ref_acc, grads):
+                    a_.copy_(t)
+            else:
+                torch._foreach_add_(ref_acc, list(grads))
+        state["in_batch"] += 1
+        if state["in_batch"] >= per:
+            close_batch(ref_acc if (reducer is None and per > 1 and ref_acc) else grads)
+        return loss, grads
+
+    def drain():
+        if state["in_batch"] > 0 and reducer is not None and not reducer._fresh and state["mode"] != "none" and world > 1:
+            close_batch(None)                  # a partial last batch is reduced as well
+        state["in_batch"] = 0
+        if reducer is not None:
+            reducer._open = False
+            reducer.wait()
+        for h in ref_pending:
+            h.wait()
+        ref_pending.clear()
+
+    # Which views share a lock-step: dealt from the view list sorted by a cost proxy that depends on the scene and the
+    # cameras only (surfels in front of the camera whose centre projects into the image) — the SAME schedule for both
+    # arms, so that they time the same views (`--schedule roundrobin`: plain rank::world assignment).
+    schedule = None
+    if world > 1 and args.schedule == "balanced":
+        from partgs_b200.dist import balanced_view_schedule
+        costs = []
+        for cam in all_cams:
+            ph = torch.cat([scene["means3D"], torch.ones_like(scene["means3D"][:, :1])], dim=1) @ cam.projmatrix
+            w_ = ph[:, 3:4].clamp_min(1e-6)
+            inside = (ph[:, 3] > 0.2) & ((ph[:, :2] / w_).abs() < 1.05).all(dim=1)
+            costs.append(float(inside.sum()))
+        schedule = balanced_view_schedule(costs, world)
+
+    def view_of_step(i):
+        if schedule is not None:
+            return schedule[i % len(schedule)][rank]
+        if world > 1:
+            return (rank + world * (i % len(my_cams))) % len(all_cams)
+        # N = 1: stride through the camera ring (the views sweep the azimuth in order; K < views consecutive ones
+        # would time one side of the scene only)
+        n_ = len(all_cams)
+        stride = next(s_ for s_ in (5, 7, 3, 1) if n_ % s_ != 0 or s_ == 1)
+        return (i * stride) % n_
+
+    def cam_of_step(i):
+        return all_cams[view_of_step(i)]
 
     def barrier():
         if world > 1:
@@ -363,26 +413,9 @@ def run(args):
         # during warm-up already, so that no cudaEventCreate (slow on some hosts) lands inside the timed steps
         arm._lib.timing_enable(True)
     views_per_rank = (len(all_cams) + world - 1) // world  # same count on every rank (collectives must match)
-    if world > 1 and args.schedule == "balanced":
-        # first pass: every rank renders its round-robin share once and times each view; the costs are shared and
-        # the views re-dealt so that the N views of one step cost about the same (dist.balanced_view_schedule)
-        from partgs_b200.dist import balanced_view_schedule
-        cost = torch.zeros(len(all_cams), device=dev)
-        for vi in range(rank, len(all_cams), world):
-            arm.step(all_cams[vi], bg, g)          # allocator / arena warm-up for this view
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-            arm.step(all_cams[vi], bg, g)
-            ev1.record()
-            torch.cuda.synchronize()
-            cost[vi] = ev0.elapsed_time(ev1)
-        dist.all_reduce(cost)
-        schedule = balanced_view_schedule(cost.tolist(), world)
-        for i in range(len(schedule) + n_warm):
-            one_step(i)
-    else:
-        for i in range(min(views_per_rank, 64) + n_warm):
-            one_step(i)
+    n_pass = len(schedule) if schedule is not None else min(views_per_rank, 64)
+    for i in range(n_pass + n_warm):
+        one_step(i)
     drain()
     torch.cuda.synchronize()
 
@@ -437,15 +470,58 @@ def run(args):
         return dict(t_ms=float(red[0]), busy_ms=float(red[1]), host_ms=host_ms, launches=l1 - l0, stage=stage,
                     mallocs=int(mem1.get("num_device_alloc", 0) - mem0.get("num_device_alloc", 0)))
 
-    # EXACTLY K timed steps.  If the GPU sat idle for more than 20 % of them (device time inside our kernels vs
-    # elapsed: the host of this box could not enqueue fast enough), the K steps are timed again, at most twice,
-    # and the fastest pass is reported; every attempt is listed in the JSON line.
-    attempts = [timed_pass()]
-    while arm.name == "ours" and len(attempts) < 3 and attempts[-1]["t_ms"] > 1.25 * attempts[-1]["busy_ms"]:
-        attempts.append(timed_pass())
+    # EXACTLY K timed steps, timed twice; the faster pass is reported and both are listed in the JSON line (some boxes
+    # of the pool have hosts that enqueue 10-50x slower than others and stumble in a pass).  Same rule for both arms.
+    attempts = [timed_pass(), timed_pass()]
     best = min(attempts, key=lambda a_: a_["t_ms"])
     t_ms, host_ms, stage = best["t_ms"], best["host_ms"], best["stage"]
     n_launch, n_malloc = best["launches"], best["mallocs"]
+    views_timed = sorted(set(view_of_step(i) for i in range(args.steps)))
+
+    # ---- the other collective modes, same K steps (N > 1): all-reduce after every view; no all-reduce at all --------
+    modes = None
+    if world > 1:
+        modes = {"per_batch": round(world * args.steps / (t_ms / 1e3), 3)}
+        for m_ in ("per_view", "none"):
+            state["mode"] = m_
+            for i in range(3):
+                one_step(i)
+            drain()
+            torch.cuda.synchronize()
+            r_ = timed_pass()
+            modes[m_] = round(world * args.steps / (r_["t_ms"] / 1e3), 3)
+        state["mode"] = "per_batch"
+
+    # ---- collective check (N > 1, ours): one batch's bucket reduced by the product collective must equal, bit for bit,
+    # the rank-ordered sum ((g0 + g1) + g2) + ... of the W buckets gathered with NCCL; NCCL's own all-reduce of the
+    # same data is compared as well (its summation order differs for W > 2) -----------------------------------------
+    collective_check = None
+    if world > 1 and reducer is not None:
+        drain()
+        reducer.begin_batch()
+        loss, grads = arm.step(cam_of_step(0), bg, g)
+        torch.cuda.synchronize()
+        mine_b = reducer.current().clone()
+        gathered = [torch.empty_like(mine_b) for _ in range(world)]
+        dist.all_gather(gathered, mine_b)
+        want = gathered[0].clone()
+        for q in range(1, world):
+            want += gathered[q]
+        nccl = mine_b.clone()
+        dist.all_reduce(nccl)
+        reducer.launch(grads)
+        reducer.wait()
+        torch.cuda.synchronize()
+        got = reducer.current()
+        same = bool(torch.equal(got, want))
+        flags = torch.tensor([int(same)], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        scale = float(want.abs().max())
+        collective_check = {"vs_rank_ordered_sum": "bitwise-equal" if int(flags) == 1 else
+                            f"MISMATCH (max abs diff {float((got - want).abs().max()):.3e})",
+                            "vs_nccl_allreduce_max_rel_diff": float((got - nccl).abs().max()) / (scale + 1e-30),
+                            "bucket_floats": int(got.numel()), "nonzero": bool(scale > 0)}
+        del gathered, want, nccl, mine_b
     clock_info = clocks.stop() if rank == 0 else None
     value = world * args.steps / (t_ms / 1e3)
 
@@ -464,45 +540,87 @@ def run(args):
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
     loss_host = torch.zeros(1).pin_memory()
 
-    def upload(slot):
+    g_host = g["color"].detach().cpu().pin_memory()      # per-view loss input (stands for the ground-truth image)
+    g_slots = [torch.empty_like(g["color"]) for _ in range(2)]
+
+    p_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    p_consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def upload_params(pb):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(p_consumed[pb])
+            for k, v in host.items():
+                slots[pb][k].copy_(v, non_blocking=True)
+            p_ready[pb].record(copy_stream)
+
+    def upload_view(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])
-            for k, v in host.items():
-                slots[slot][k].copy_(v, non_blocking=True)
+            g_slots[slot].copy_(g_host, non_blocking=True)
             ready[slot].record(copy_stream)
 
-    def e2e_loop(n):
+    def e2e_loop(n, params_every=1):
+        """params_every = 1: the declared end-to-end mode, EVERY rasteriser input of a step comes from pinned host memory
+        (232 MB of surfel parameters + camera).  params_every = k > 1: the training-shaped mode — parameters are
+        uploaded once per optimiser batch of k views (they only change at the optimiser step, train.py:219-305), and
+        every view uploads what is new for it: camera and the image-sized loss input.  Uploads run one step (one
+        batch) ahead on a copy stream, double-buffered."""
         cur = torch.cuda.current_stream(dev)
-        for s in range(2):
-            consumed[s].record(cur)
-        upload(0)
+        for s_ in range(2):
+            consumed[s_].record(cur)
+            p_consumed[s_].record(cur)
+        per_view = params_every > 1
+        upload_params(0)
+        if per_view:
+            upload_view(0)
         for i in range(n):
-            s = i & 1
-            if i + 1 < n:
-                upload(1 - s)
-            cur.wait_event(ready[s])
+            s_, b_ = i & 1, (i // params_every) & 1
+            if i % params_every == 0:
+                cur.wait_event(p_ready[b_])
+                if i + params_every < n:
+                    upload_params(1 - b_)          # the next batch's parameters travel while this batch renders
+            if per_view:
+                if i + 1 < n:
+                    upload_view(1 - s_)
+                cur.wait_event(ready[s_])
             cam = cam_of_step(i)
-            prm = slots[s]
+            prm = slots[b_]
             if arm.name == "ours":
                 prm = {k: v.detach().requires_grad_(True) for k, v in prm.items()}
-            loss, grads = arm.step(cam, bg, g, params=prm, want_loss=True)
-            allreduce_grads(grads)
+            gg = dict(g, color=g_slots[s_]) if per_view else g
+            if state["in_batch"] == 0 and reducer is not None:
+                reducer.begin_batch()
+            loss, grads = arm.step(cam, bg, gg, params=prm, want_loss=True)
+            state["in_batch"] += 1
+            last_of_batch = (i + 1) % params_every == 0 or i + 1 == n
+            if last_of_batch:                          # gradients are reduced once per upload of the parameters
+                close_batch(grads)
+                p_consumed[b_].record(cur)
             loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-            consumed[s].record(cur)
+            if per_view:
+                consumed[s_].record(cur)
         drain()
         torch.cuda.synchronize()
         return float(loss_host.item())
 
-    e2e_loop(2)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_loop(args.steps)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.steps / float(te.item())
+    def time_e2e(params_every):
+        e2e_loop(2, params_every)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_loop(args.steps, params_every)
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return world * args.steps / float(te.item())
+
+    e2e_value = time_e2e(1)
+    batch_k = max(accum, 2) if world > 1 else max(2, min(len(all_cams), 8))
+    # (with slot double-buffering a parameter upload overwrites the slot the running batch reads only if a batch is
+    #  shorter than two steps: k >= 2)
+    e2e_batch_value = time_e2e(batch_k)
+    view_bytes = g_host.numel() * 4 + 2 * 64 + 12
+    param_bytes = sum(v.numel() * v.element_size() for v in host.values())
 
     if rank != 0:
         return
@@ -526,16 +644,26 @@ def run(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{name}: {P} surfels, {W}x{H}, fwd+bwd, all 10 output channels get gradient",
                    "views": cfg["views"], "views_per_rank": len(my_cams),
-                   "sharding": "by camera" + (", steps dealt from the cost-sorted view list" if schedule is not None else ""),
-                   "collective": ("none" if world == 1 or args.no_allreduce else
-                                  "all-reduce of the 232 B/surfel gradient bucket per step: " +
-                                  ("copy-engine reduce-scatter/all-gather over NVLink peer memory" if peer is not None
-                                   else "NCCL")),
+                   "sharding": "by camera" + (", steps dealt from the view list sorted by a geometric cost proxy (same for both arms)" if schedule is not None else ""),
+                   "collective": ("none" if world == 1 else
+                                  f"one all-reduce of the 232 B/surfel parameter gradients per batch of {accum} views per rank"),
+                   "views_timed": views_timed,
                    "l2": "inputs (232 MB parameters + per-view state) exceed the 126 MB L2; views cycle every step",
                    "V_visible": V, "R_instances": int(R)},
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                 "d2h_bytes_per_step": 4},
+        # additional, NOT the declared e2e: parameters uploaded once per optimiser batch (they only change at the
+        # optimiser step), every view uploads its camera and an image-sized loss input
+        "e2e_batch_upload": {"value": round(e2e_batch_value, 3), "unit": UNIT, "views_per_parameter_upload": batch_k,
+                             "h2d_bytes_per_step": int(view_bytes + param_bytes / batch_k), "d2h_bytes_per_step": 4},
         "gpu_launches": int(n_launch),
+        **({"collective_impl": (("fused reduce-scatter + all-gather kernel over NVLink peer memory (csrc/collective.cu)"
+                                 if args.collective == "peer" else "NCCL all-reduce of the bucket") +
+                                "; gradients accumulate inside the backward kernel, in the bucket") if reducer is not None
+                               else "NCCL all-reduce per tensor; gradients accumulate with torch adds"} if world > 1 else {}),
+        **({"collective_modes": dict(modes, unit=UNIT, note="same K steps: all-reduce per batch (the headline), after every "
+                                     "view, and not at all")} if modes else {}),
+        **({"collective_check": collective_check} if collective_check else {}),
         "host": {"enqueue_ms_per_step": round(host_ms, 4), "trivial_launch_us": round(launch_us, 2),
                  "sync_round_trip_us": round(sync_us, 1), "device_mallocs_in_timed_region": n_malloc},
         "attempts": [{"ms_per_step": round(a_["t_ms"] / args.steps, 4), "kernel_ms_per_step": round(a_["busy_ms"] / args.steps, 4),
@@ -642,13 +770,13 @@ def main():
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--schedule", default="balanced", choices=["balanced", "roundrobin"],
-                    help="N>1: which views share a lock-step (cost-sorted groups, or plain round-robin)")
+                    help="N>1: which views share a lock-step (groups of similar cost proxy, or plain round-robin)")
+    ap.add_argument("--accum", type=int, default=0,
+                    help="N>1: views per rank and batch (one all-reduce per batch); 0 = ceil(views / N)")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="gradient all-reduce at N>1: copy-engine peer-memory collective (default) or NCCL")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the timing of the SURVEY 8(f) rows / prepared variants in a subprocess after the bench")
-    ap.add_argument("--no-allreduce", action="store_true",
-                    help="diagnostic: skip the gradient all-reduce at N>1 (shows what the collective costs)")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")

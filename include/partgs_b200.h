@@ -75,7 +75,11 @@ size_t pgs_dsr_backward_scratch_bytes(int P);
  * that call (the arena is laid out for a capacity >= R that backward recovers from it).  All nine gradient arrays are fully written (no
  * pre-zeroing required): dL_dmean2D [P,3], dL_dopacity [P], dL_dcolor [P,3],
  * dL_dmean3D [P,3], dL_dtransMat [P,9], dL_dsh [P,M,3], dL_dscale [P,2], dL_drot [P,4].
- * `scratch` replaces the reference's internal dL_dnormal [P,3] tensor. */
+ * `scratch` replaces the reference's internal dL_dnormal [P,3] tensor.
+ * `debug` is a flag word: bit 0 = the reference's debug switch (synchronise and check after every stage); bit 1 =
+ * PGS_BWD_ACCUMULATE: dL_dmean3D, dL_dsh, dL_dopacity, dL_dscale and dL_drot are ADDED to (gradient accumulation over
+ * the views of a data-parallel batch: one all-reduce per batch); the other arrays are overwritten. */
+#define PGS_BWD_ACCUMULATE 2
 int pgs_dsr_backward(int P, int D, int M, int R, const float* background, int width, int height,
                      const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
                      float scale_modifier, const float* rotations, const float* transMat_precomp,
@@ -280,6 +284,16 @@ int pgs_sq2surfel_backward(int B, int Vt, int F, int K, const float* sq_r, const
                            const float* d_opacity, const float* d_vertices_in, float* d_sq_r, float* d_sq_s,
                            float* d_sq_t, float* d_sq_eps, float* d_sq_occ, float* d_alpha, float* d_scale_raw,
                            void* scratch, void* stream);
+
+/* ---- gradient all-reduce over NVLink peer memory (no counterpart in the reference, which is
+ * single-process) -------------------------------------------------------------------------------------------
+ * `buckets[q]` = address of rank q's gradient bucket as mapped into THIS process (symmetric / peer memory), q <
+ * world <= 8.  The caller owns slice [offset_floats, offset_floats + n_floats) (multiples of 4): the kernel loads
+ * it from all `world` buckets, adds in rank order and stores the sum back into all of them.  The caller brackets the
+ * call with two cross-rank barriers on `stream` (gradients complete / slices landed), see partgs_b200/dist.py.
+ * max_ctas bounds the SMs the collective takes from concurrently running kernels (0 = default 32). */
+int pgs_peer_allreduce_slice(int world, float* const* buckets, size_t offset_floats, size_t n_floats, int max_ctas,
+                             void* stream);
 
 /* ---- simple-knn ------------------------------------------------------------------
  * Replaces distCUDA2 / SimpleKNN::knn (KNN/spatial.cu:15-25, KNN/simple_knn.cu:185-221):

@@ -508,8 +508,14 @@ static int backward_impl(const SqArgs* sq, const float* sq_vertices, bool part, 
                          size_t binning_bytes, char* image_buffer,
                          const float* dL_dpix, const float* dL_dothers, float* dL_dmean2D, float* scratch,
                          float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh,
-                         float* dL_dscale, float* dL_drot, int debug, void* stream) {
+                         float* dL_dscale, float* dL_drot, int flags, void* stream) {
   (void)colors_precomp;
+  // flags: bit 0 = debug (synchronise and check after every stage, like the reference's `debug`), bit 1 =
+  // PGS_BWD_ACCUMULATE (add the five parameter gradients to the arrays instead of overwriting them)
+  const int debug = flags & 1;
+  const int accumulate = (flags & PGS_BWD_ACCUMULATE) ? 1 : 0;
+  if (accumulate && (part || sq))
+    return set_error(PGS_ERR_UNSUPPORTED, "gradient accumulation is implemented for the point-level base fork only");
   if (part) {
     if (S < 0 || S > MAX_SEMANTIC)
       return set_error(PGS_ERR_UNSUPPORTED, "semantic channels must be in [0, %d] (got %d)", MAX_SEMANTIC, S);
@@ -573,6 +579,7 @@ static int backward_impl(const SqArgs* sq, const float* sq_vertices, bool part, 
   pb.P = P; pb.D = D; pb.M = M; pb.means3D = means3D; pb.radii = radii; pb.shs = shs;
   pb.scales = transMat_precomp ? nullptr : scales; pb.rotations = rotations; pb.scale_modifier = scale_modifier;
   pb.use_sq = sq != nullptr;
+  pb.accumulate = accumulate;
   if (sq) { pb.sq = *sq; pb.sq_vertices = sq_vertices; }
   pb.transMat_precomp = transMat_precomp; pb.viewmatrix = viewmatrix; pb.projmatrix = projmatrix;
   pb.focal_x = focal_x; pb.focal_y = focal_y; pb.tan_fovx = tan_fovx; pb.tan_fovy = tan_fovy; pb.cam_pos = campos;
@@ -954,6 +961,19 @@ int pgs_densify_children(int n_children, const unsigned int* counts, const int* 
   launch_densify_children(n_children, counts, src_row, sample_row, z, xyz_in, scaling_in, rotation_in,
                           1.0f / (float)split_divisor, xyz_out, scaling_out, (cudaStream_t)stream);
   return check_cuda("densify_children");
+}
+
+int pgs_peer_allreduce_slice(int world, float* const* buckets, size_t offset_floats, size_t n_floats, int max_ctas,
+                             void* stream) {
+  if (world < 1 || world > PGS_PEER_MAX_WORLD || !buckets)
+    return set_error(PGS_ERR_INVALID_ARG, "peer all-reduce: world size must be in [1, %d]", PGS_PEER_MAX_WORLD);
+  PeerBuckets b;
+  for (int i = 0; i < PGS_PEER_MAX_WORLD; i++) b.p[i] = i < world ? buckets[i] : nullptr;
+  for (int i = 0; i < world; i++)
+    if (!b.p[i] || (reinterpret_cast<size_t>(b.p[i]) & 15)) return set_error(PGS_ERR_INVALID_ARG, "peer all-reduce: bad bucket pointer");
+  const int rc = launch_peer_allreduce_slice(b, world, offset_floats, n_floats, max_ctas, (cudaStream_t)stream);
+  if (rc) return set_error(PGS_ERR_INVALID_ARG, "peer all-reduce: slice must be a multiple of 4 floats");
+  return check_cuda("peer_allreduce_slice");
 }
 
 size_t pgs_knn_temp_bytes(int P) { return knn_temp_bytes(P > 0 ? P : 0) + 256; }

@@ -215,6 +215,9 @@ struct PreprocessBwdArgs {
   float* dL_dsh;        // [P][M][3]
   float* dL_dscales;    // [P][2]  (block-level mode: gradient w.r.t. the LOG scales sq_surfels would store)
   float* dL_drots;      // [P][4]
+  // base fork: add the five parameter gradients (mean3D, SH, opacity, scales, rotations) to what is already there
+  // instead of overwriting (gradient accumulation over the views of a data-parallel batch)
+  int accumulate;
   // block-level mode (see PreprocessFwdArgs)
   bool use_sq;
   SqArgs sq;
@@ -302,6 +305,13 @@ void launch_densify_children(int n_children, const uint32_t* counts, const int* 
 // ---- per-view epilogue of the extraction loop (extract.cu) -----------------------------------------
 void launch_extract_maps(int npix, int S, const float* semantic, const float* palette, int palette_stride,
                          const float* rend_normal, float* part_rgb, float* normal_unit, cudaStream_t s);
+
+// ---- gradient all-reduce over NVLink peer memory (collective.cu) ------------------------------------
+#define PGS_PEER_MAX_WORLD 8
+struct PeerBuckets { float* p[PGS_PEER_MAX_WORLD]; };  // the same bucket on every rank (peer-mapped addresses)
+// returns 0, -1 (slice not 16-byte aligned), -2 (world size not supported)
+int launch_peer_allreduce_slice(const PeerBuckets& b, int world, size_t offset_floats, size_t n_floats, int ctas,
+                                cudaStream_t s);
 
 // ---- distCUDA2 (simple-knn) ---------------------------------------------------
 size_t knn_temp_bytes(int P);

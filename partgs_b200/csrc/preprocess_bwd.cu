@@ -75,7 +75,8 @@ __device__ __forceinline__ void zero_sh_row(float* o_sh, int M) {
 // gradient that flows through the view direction.
 template <bool DIRECT = false>
 __device__ __forceinline__ v3 sh_backward(int idx, int deg, int M, const v3* means, v3 campos, const float* shs,
-                                          unsigned clamped, v3 dL_dcolor, v3* dL_dsh_out, v3 pos_direct = v3()) {
+                                          unsigned clamped, v3 dL_dcolor, v3* dL_dsh_out, v3 pos_direct = v3(),
+                                          bool acc = false) {
   v3 pos = DIRECT ? pos_direct : means[idx];
   v3 dir_orig = pos - campos;
   v3 dir = dir_orig / length(dir_orig);
@@ -168,17 +169,30 @@ __device__ __forceinline__ v3 sh_backward(int idx, int deg, int M, const v3* mea
       }
     }
   }
+  // acc: the row already holds the sum over the earlier views of a batch (gradient accumulation in place)
   if (M == 16) {
     float4* d4 = reinterpret_cast<float4*>(dL_dsh_out);
     const float* src = reinterpret_cast<const float*>(dL_dsh);
+    if (acc) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) d4[i] = make_float4(src[4 * i], src[4 * i + 1], src[4 * i + 2], src[4 * i + 3]);
+      for (int i = 0; i < 12; i++) {
+        const float4 o = d4[i];
+        d4[i] = make_float4(o.x + src[4 * i], o.y + src[4 * i + 1], o.z + src[4 * i + 2], o.w + src[4 * i + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 12; i++) d4[i] = make_float4(src[4 * i], src[4 * i + 1], src[4 * i + 2], src[4 * i + 3]);
+    }
   } else {
     float* dg = reinterpret_cast<float*>(dL_dsh_out);
 #pragma unroll
     for (int i = 0; i < 16; i++)
-      if (i < M) { dg[3 * i] = dL_dsh[i].x; dg[3 * i + 1] = dL_dsh[i].y; dg[3 * i + 2] = dL_dsh[i].z; }
-    for (int i = 16; i < M; i++) { dg[3 * i] = 0.f; dg[3 * i + 1] = 0.f; dg[3 * i + 2] = 0.f; }
+      if (i < M) {
+        if (acc) { dg[3 * i] += dL_dsh[i].x; dg[3 * i + 1] += dL_dsh[i].y; dg[3 * i + 2] += dL_dsh[i].z; }
+        else { dg[3 * i] = dL_dsh[i].x; dg[3 * i + 1] = dL_dsh[i].y; dg[3 * i + 2] = dL_dsh[i].z; }
+      }
+    if (!acc)
+      for (int i = 16; i < M; i++) { dg[3 * i] = 0.f; dg[3 * i + 1] = 0.f; dg[3 * i + 2] = 0.f; }
   }
   v3 dL_ddir(dot(dRGBdx, dL_dRGB), dot(dRGBdy, dL_dRGB), dot(dRGBdz, dL_dRGB));
   float3 dL_dmean = dnormvdv3(float3{dir_orig.x, dir_orig.y, dir_orig.z}, float3{dL_ddir.x, dL_ddir.y, dL_ddir.z});
@@ -201,17 +215,23 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
   float* o_T = a.dL_dtransMat + (size_t)idx * 9;
   float* o_sh = a.dL_dsh ? a.dL_dsh + (size_t)idx * M * 3 : nullptr;
 
+  // Accumulate mode (a data-parallel batch: a rank renders several views and all-reduces ONE gradient bucket): the
+  // five parameter gradients (mean3D, SH, opacity, scales, rotations) are added to what the earlier views of the
+  // batch left in place; the per-view outputs (mean2D, colours, transMat) are still overwritten.
+  const bool acc = a.accumulate != 0;
   if (!visible) {
     o_m2d[0] = o_m2d[1] = o_m2d[2] = 0.f;
     o_col[0] = o_col[1] = o_col[2] = 0.f;
+    for (int i = 0; i < 9; i++) o_T[i] = 0.f;
+    if (acc) return;   // nothing to add
     a.dL_dopacity[idx] = 0.f;
     o_m3d[0] = o_m3d[1] = o_m3d[2] = 0.f;
-    for (int i = 0; i < 9; i++) o_T[i] = 0.f;
     if (o_sh) zero_sh_row(o_sh, M);
     if (a.dL_dscales) { a.dL_dscales[idx * 2] = 0.f; a.dL_dscales[idx * 2 + 1] = 0.f; }
     if (a.dL_drots) { for (int i = 0; i < 4; i++) a.dL_drots[idx * 4 + i] = 0.f; }
     return;
   }
+  auto put = [acc](float* dst, float v) { *dst = acc ? *dst + v : v; };
 
   // accumulated per-surfel gradients from the render pass
   const float4* gq = reinterpret_cast<const float4*>(a.grad + (size_t)idx * GRAD_FLOATS);
@@ -330,14 +350,14 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
     m3 dL_dR = make_m3(dL_dRS[0] * v3(scale.x, scale.x, scale.x), dL_dRS[1] * v3(scale.y, scale.y, scale.y),
                        dL_dRS[2]);
     v4 dq = quat_to_rotmat_vjp(rot, dL_dR);
-    a.dL_drots[idx * 4 + 0] = dq.x;
-    a.dL_drots[idx * 4 + 1] = dq.y;
-    a.dL_drots[idx * 4 + 2] = dq.z;
-    a.dL_drots[idx * 4 + 3] = dq.w;
-    a.dL_dscales[idx * 2 + 0] = (float)dot(dL_dRS[0], R[0]) * (SQ ? scale.x : 1.0f);
-    a.dL_dscales[idx * 2 + 1] = (float)dot(dL_dRS[1], R[1]) * (SQ ? scale.y : 1.0f);
+    put(&a.dL_drots[idx * 4 + 0], dq.x);
+    put(&a.dL_drots[idx * 4 + 1], dq.y);
+    put(&a.dL_drots[idx * 4 + 2], dq.z);
+    put(&a.dL_drots[idx * 4 + 3], dq.w);
+    put(&a.dL_dscales[idx * 2 + 0], (float)dot(dL_dRS[0], R[0]) * (SQ ? scale.x : 1.0f));
+    put(&a.dL_dscales[idx * 2 + 1], (float)dot(dL_dRS[1], R[1]) * (SQ ? scale.y : 1.0f));
     dmean = xyz(dL_dM[2]);
-  } else {
+  } else if (!acc) {
     if (a.dL_dscales) { a.dL_dscales[idx * 2] = 0.f; a.dL_dscales[idx * 2 + 1] = 0.f; }
     if (a.dL_drots) { for (int i = 0; i < 4; i++) a.dL_drots[idx * 4 + i] = 0.f; }
   }
@@ -345,14 +365,14 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
   // SH backward (backward.cu:20-139), incl. view-direction -> mean3D path
   if (a.shs) {
     dmean += sh_backward<SQ>(idx, a.D, M, (const v3*)a.means3D, *(const v3*)a.cam_pos, a.shs, __float_as_uint(q4.w),
-                             dL_dcolor, (v3*)o_sh, v3(p_orig.x, p_orig.y, p_orig.z));
-  } else if (o_sh) {
+                             dL_dcolor, (v3*)o_sh, v3(p_orig.x, p_orig.y, p_orig.z), acc);
+  } else if (o_sh && !acc) {
     for (int i = 0; i < M * 3; i++) o_sh[i] = 0.f;
   }
 
-  o_m3d[0] = dmean.x; o_m3d[1] = dmean.y; o_m3d[2] = dmean.z;
+  put(&o_m3d[0], dmean.x); put(&o_m3d[1], dmean.y); put(&o_m3d[2], dmean.z);
   o_col[0] = dL_dcolor.x; o_col[1] = dL_dcolor.y; o_col[2] = dL_dcolor.z;
-  a.dL_dopacity[idx] = g_opacity;
+  put(&a.dL_dopacity[idx], g_opacity);
   o_m2d[0] = hack_x;
   o_m2d[1] = hack_y;
   o_m2d[2] = 0.f;

@@ -82,14 +82,17 @@ _bucket_provider = None
 
 
 def set_grad_bucket_provider(fn):
-    """``fn(numel, device) -> flat float32 tensor or None``: where the backward pass puts its five parameter
-    gradients (one flat "bucket").  A data-parallel caller hands out peer-mapped memory here so that the
-    gradients are reduced in place (partgs_b200.dist.PeerGradAllReducer).  None restores torch.empty."""
+    """``fn(numel, device) -> flat float32 tensor, (tensor, accumulate) or None``: where the backward pass puts its
+    five parameter gradients (one flat "bucket").  A data-parallel caller hands out peer-mapped memory here so that
+    the gradients are reduced in place (partgs_b200.dist).  With ``accumulate`` true the kernel ADDS this view's
+    gradients to what the bucket holds (the earlier views of a batch) instead of overwriting it — the caller must
+    then drop ``.grad`` of the parameters before every backward (autograd would otherwise add the bucket to
+    itself).  None restores torch.empty."""
     global _bucket_provider
     _bucket_provider = fn
 
 
-def _carve_bucket(dev, shapes, align_elems=64):
+def _carve_bucket(dev, shapes, align_elems=64, with_flag=False):
     """Views of the given shapes into one flat float32 buffer (each view 256-byte aligned).
     The views' ``_base`` is the bucket itself."""
     offs, total = [], 0
@@ -100,9 +103,29 @@ def _carve_bucket(dev, shapes, align_elems=64):
         offs.append((total, n))
         total += (n + align_elems - 1) // align_elems * align_elems
     flat = _bucket_provider(max(total, 1), dev) if _bucket_provider is not None else None
+    accumulate = False
+    if isinstance(flat, tuple):
+        flat, accumulate = flat
     if flat is None:
-        flat = torch.empty((max(total, 1),), dtype=torch.float32, device=dev)
-    return [flat[o:o + n].view(*shp) for (o, n), shp in zip(offs, shapes)]
+        flat, accumulate = torch.empty((max(total, 1),), dtype=torch.float32, device=dev), False
+    views = [flat[o:o + n].view(*shp) for (o, n), shp in zip(offs, shapes)]
+    return (views, bool(accumulate)) if with_flag else views
+
+
+def bucket_numel(P: int, M: int = 16, align_elems: int = 64) -> int:
+    """Floats of the gradient bucket of a model with P surfels and M SH coefficients (layout of _carve_bucket)."""
+    return sum((n + align_elems - 1) // align_elems * align_elems for n in (P * 3, P * M * 3, P, P * 2, P * 4))
+
+
+def zero_bucket_grads(P: int, M: int, dev):
+    """Zero gradients (means3D, sh, opacity, scales, rotations) laid out in the provider's bucket exactly like a
+    backward pass would leave them: what a rank WITHOUT views contributes to a data-parallel batch, so that every
+    rank issues the same collective."""
+    views, accumulate = _carve_bucket(dev, [(P, 3), (P, M, 3), (P, 1), (P, 2), (P, 4)], with_flag=True)
+    if not accumulate:
+        for v in views:
+            v.zero_()
+    return views
 
 
 def _native_backward(bg, means3D, radii, colors, scales, rotations, scale_modifier, transMat_precomp, viewmatrix,
@@ -121,8 +144,8 @@ def _native_backward(bg, means3D, radii, colors, scales, rotations, scale_modifi
     # The five parameter gradients (232 B/surfel) are carved out of ONE flat buffer ("gradient
     # bucket"): the backward-preprocess kernel writes them in place, and a data-parallel caller can
     # all-reduce the whole bucket with a single collective (see partgs_b200.dist.grad_bucket).
-    dL_dmeans3D, dL_dsh, dL_dopacity, dL_dscales, dL_drotations = _carve_bucket(
-        dev, [(P, 3), (P, M, 3), (P, 1), (P, 2), (P, 4)])
+    (dL_dmeans3D, dL_dsh, dL_dopacity, dL_dscales, dL_drotations), accumulate = _carve_bucket(
+        dev, [(P, 3), (P, M, 3), (P, 1), (P, 2), (P, 4)], with_flag=True)
     dL_dmeans2D = torch.empty((P, 3), **f32)
     dL_dcolors = torch.empty((P, NUM_CHANNELS), **f32)
     dL_dtransMat = torch.empty((P, 9), **f32)
@@ -141,7 +164,7 @@ def _native_backward(bg, means3D, radii, colors, scales, rotations, scale_modifi
                 _lib.ptr(imageBuffer), _lib.ptr(dL_dout_color), _lib.ptr(dL_dout_others), _lib.ptr(dL_dmeans2D),
                 _lib.ptr(scratch), _lib.ptr(dL_dopacity), _lib.ptr(dL_dcolors), _lib.ptr(dL_dmeans3D),
                 _lib.ptr(dL_dtransMat), _lib.ptr(dL_dsh), _lib.ptr(dL_dscales), _lib.ptr(dL_drotations),
-                int(bool(debug)), _lib.current_stream(dev))
+                int(bool(debug)) | (2 if accumulate else 0), _lib.current_stream(dev))
         _lib.check(rc, "pgs_dsr_backward")
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dscales, dL_drotations
 

@@ -92,7 +92,8 @@ def grad_bucket(grads: Iterable[torch.Tensor]):
 
 
 class GradAllReducer:
-    """Asynchronous per-parameter-group gradient all-reduce (SUM)."""
+    """Asynchronous gradient all-reduce (SUM) through torch.distributed (NCCL on GPUs, gloo in the CPU tests): one
+    collective if the gradients share one allocation (the rasteriser's bucket), one per tensor otherwise."""
 
     def __init__(self, group=None, average: bool = False):
         self.group = group
@@ -102,6 +103,9 @@ class GradAllReducer:
     @property
     def world(self) -> int:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def begin_batch(self):
+        pass
 
     def launch(self, tensors: Iterable[torch.Tensor]):
         if self.world == 1:
@@ -125,92 +129,147 @@ class GradAllReducer:
         self._pending.clear()
 
 
-class PeerGradAllReducer:
-    """Gradient all-reduce (SUM) over NVLink peer memory that uses the COPY ENGINES instead of SMs.
+class BucketBatch:
+    """Ownership of the rasteriser's gradient bucket over a data-parallel BATCH (a rank renders its
+    ceil(views / G) views, the gradients accumulate, ONE all-reduce per batch).
 
-    The render kernels of the next view run while the gradients of the current one are reduced, and they
-    are issue-bound on every SM; an NCCL all-reduce kernel running beside them takes SMs away for the whole
-    length of the collective (measured: 10-12 % of the step at 2-8 ranks).  Here the gradient bucket lives in
-    symmetric (peer-mapped) memory and the collective is
+    `begin_batch()` opens a batch on the next of `n_buckets` buffers (waiting until the collective that last used it
+    has finished).  Every backward pass of the batch then receives that same buffer from `bucket_provider`: the
+    first one overwrites it, the following ones ADD to it inside the backward-preprocess kernel (no separate
+    accumulation pass).  Contract: the caller drops `.grad` of the parameters before every backward (`p.grad =
+    None`) — autograd then adopts the bucket views as `.grad` each time; with a live `.grad` it would add the bucket
+    to itself.  `launch()` reduces the batch's buffer and closes the batch; a backward without an open batch opens
+    one implicitly (one view per batch, the per-view mode)."""
 
-        barrier -> reduce-scatter: each rank pulls "its" 1/W slice of every peer's bucket with peer DMA copies
-                -> one small kernel sums the W slices
-        barrier -> all-gather: each rank pushes its reduced slice into every peer's bucket with peer DMA copies
-        barrier
+    def __init__(self, numel: int, device, n_buckets: int = 2):
+        self.device = torch.device(device)
+        self.numel = int(numel)
+        self._alloc(n_buckets)
+        self._cur = len(self.buckets) - 1
+        self._open = False
+        self._fresh = True
+        self.done = [None] * len(self.buckets)   # CUDA event per buffer: its last collective has finished
 
-    i.e. 2 (W-1)/W of the bucket crosses NVLink per rank, exactly like a ring, but the data movement runs on
-    the copy engines; the only kernels are the W-way slice sum and the barriers' flag kernels.  Everything is
-    enqueued on a side stream; `wait()` makes the caller's stream wait for the result.
+    def _alloc(self, n_buckets):
+        self.buckets = [torch.empty(self.numel, dtype=torch.float32, device=self.device) for _ in range(n_buckets)]
 
-    The rasteriser's backward writes its five parameter gradients straight into the bucket
-    (see `bucket_provider`); two buckets alternate so that step i+1 can produce gradients while step i's are
-    still being reduced.
-    """
+    def begin_batch(self):
+        self._cur = (self._cur + 1) % len(self.buckets)
+        if self.done[self._cur] is not None and self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).wait_event(self.done[self._cur])
+        self._open, self._fresh = True, True
+
+    def bucket_provider(self, n: int, device):
+        if n > self.numel or torch.device(device) != self.device:
+            return None
+        if not self._open:
+            self.begin_batch()
+        accumulate, self._fresh = not self._fresh, False
+        return self.buckets[self._cur][:n], accumulate
+
+    def current(self) -> torch.Tensor:
+        return self.buckets[self._cur]
+
+    def _check(self, tensors):
+        """The gradients handed to launch() must be views of the open batch's buffer."""
+        tensors = [t for t in (tensors or []) if t is not None]
+        if tensors:
+            bucket = grad_bucket(tensors)
+            if bucket is None or bucket.untyped_storage().data_ptr() != self.current().untyped_storage().data_ptr():
+                raise RuntimeError("gradients do not live in the bucket of the open batch (install bucket_provider "
+                                   "before the backward pass and drop .grad before every backward)")
+        if self._fresh:
+            raise RuntimeError("no backward pass has written the bucket of this batch")
+
+
+class NcclBucketAllReducer(BucketBatch):
+    """BucketBatch reduced with one NCCL all-reduce per batch (the comparison point of the peer-memory collective)."""
 
     def __init__(self, numel: int, device, group=None, n_buckets: int = 2):
-        import torch.distributed._symmetric_memory as symm_mem
+        super().__init__(numel, device, n_buckets)
+        self.group = group
+        self._pending = []
+
+    def launch(self, tensors: Iterable[torch.Tensor] | None = None):
+        self._check(tensors)
+        i = self._cur
+        h = dist.all_reduce(self.buckets[i], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._pending.append((h, i))
+        self._open = False
+
+    def wait(self):
+        for h, i in self._pending:
+            h.wait()          # the caller's stream waits for the collective
+            if self.device.type == "cuda":
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+                self.done[i] = ev
+        self._pending.clear()
+
+
+class PeerGradAllReducer(BucketBatch):
+    """Gradient all-reduce (SUM) over NVLink peer memory as ONE kernel per batch (csrc/collective.cu).
+
+    The bucket lives in symmetric (peer-mapped) memory — the backward-preprocess kernel writes / accumulates the
+    gradients straight into it.  The collective is
+
+        barrier                      every rank's gradients are complete
+        pgs_peer_allreduce_slice     rank r loads slice r of all W buckets over NVLink, adds them in rank order and
+                                     stores the sum into slice r of all W buckets (reduce-scatter + all-gather fused)
+        barrier                      every slice has landed everywhere
+
+    on a side stream; `wait()` makes the caller's stream wait for the result.  2 (W-1)/W of the bucket crosses NVLink
+    per rank, like a ring all-reduce, but in one pass, without staging copies, with a bounded number of CTAs
+    (`max_ctas`: the render kernels of the next views run beside it and want the SMs), and with a fixed summation
+    order: every rank ends with bitwise the same sums, equal to ((g0 + g1) + g2) + ... .
+    `n_buckets` buffers alternate so that the next batch can accumulate while this one is being reduced."""
+
+    def __init__(self, numel: int, device, group=None, n_buckets: int = 2, max_ctas: int = 32):
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
-        self.device = torch.device(device)
+        if self.world > 8:
+            raise RuntimeError("PeerGradAllReducer supports up to 8 ranks (one NVSwitch domain)")
         align = 64 * self.world
-        self.numel = (int(numel) + align - 1) // align * align
+        super().__init__((int(numel) + align - 1) // align * align, device, n_buckets)
         self.slice = self.numel // self.world
-        self.buckets, self.handles, self.peers = [], [], []
+        self.max_ctas = int(max_ctas)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.ready = torch.cuda.Event()
+        self._inflight = []
+
+    def _alloc(self, n_buckets):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        self.buckets, self.handles, self.peers, self.peer_ptrs = [], [], [], []
         for _ in range(n_buckets):
             b = symm_mem.empty(self.numel, dtype=torch.float32, device=self.device)
             h = symm_mem.rendezvous(b, group=self.group.group_name)
             self.buckets.append(b)
             self.handles.append(h)
-            self.peers.append([h.get_buffer(p, (self.numel,), torch.float32) for p in range(self.world)])
-        self.tmp = torch.empty(self.world, self.slice, dtype=torch.float32, device=self.device)
-        self.stream = torch.cuda.Stream(device=self.device)
-        self.ready = torch.cuda.Event()
-        self.done = [torch.cuda.Event() for _ in range(n_buckets)]
-        self._next = 0
-        self._inflight = []
+            peers = [h.get_buffer(p, (self.numel,), torch.float32) for p in range(self.world)]
+            self.peers.append(peers)
+            self.peer_ptrs.append((C.c_void_p * self.world)(*[t.data_ptr() for t in peers]))
 
-    # -- bucket hand-out: the rasteriser asks for `n` floats for this frame's parameter gradients
-    def bucket_provider(self, n: int, device):
-        if n > self.numel or torch.device(device) != self.device:
-            return None
-        i = self._next
-        self._next = (i + 1) % len(self.buckets)
-        # the bucket may still be the target of peer copies of the collective launched two steps ago
-        torch.cuda.current_stream(self.device).wait_event(self.done[i])
-        return self.buckets[i][:n]
-
-    def index_of(self, t: torch.Tensor):
-        for i, b in enumerate(self.buckets):
-            if t.untyped_storage().data_ptr() == b.untyped_storage().data_ptr():
-                return i
-        return None
-
-    def launch(self, tensors: Iterable[torch.Tensor]):
-        bucket = grad_bucket(list(tensors))
-        i = self.index_of(bucket) if bucket is not None else None
-        if i is None:
-            raise RuntimeError("PeerGradAllReducer: gradients do not live in one of its buckets "
-                               "(install bucket_provider before the backward pass)")
+    def launch(self, tensors: Iterable[torch.Tensor] | None = None):
+        from . import _lib
+        self._check(tensors)
+        i = self._cur
         cur = torch.cuda.current_stream(self.device)
         self.ready.record(cur)
-        r, W, sl = self.rank, self.world, self.slice
-        mine = slice(r * sl, (r + 1) * sl)
-        with torch.cuda.stream(self.stream):
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             self.stream.wait_event(self.ready)
-            h, peers, b = self.handles[i], self.peers[i], self.buckets[i]
-            h.barrier(channel=0)                       # every rank's gradients are complete
-            for j in range(W):                         # reduce-scatter by peer DMA (start with my own slice)
-                p = (r + j) % W
-                self.tmp[p].copy_(peers[p][mine], non_blocking=True)
-            torch.sum(self.tmp, dim=0, out=b[mine])
-            h.barrier(channel=1)                       # nobody still reads the slice I am about to overwrite remotely
-            for j in range(1, W):                      # all-gather by peer DMA
-                p = (r + j) % W
-                peers[p][mine].copy_(b[mine], non_blocking=True)
-            h.barrier(channel=2)                       # every slice has landed everywhere
-            self.done[i].record(self.stream)
+            h = self.handles[i]
+            h.barrier(channel=0)
+            rc = _lib.load().pgs_peer_allreduce_slice(self.world, self.peer_ptrs[i], self.rank * self.slice, self.slice,
+                                                      self.max_ctas, _lib.current_stream(self.device))
+            _lib.check(rc, "pgs_peer_allreduce_slice")
+            h.barrier(channel=1)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+            self.done[i] = ev
         self._inflight.append(i)
+        self._open = False
 
     def wait(self):
         cur = torch.cuda.current_stream(self.device)
@@ -220,33 +279,54 @@ class PeerGradAllReducer:
 
 
 def sharded_step(render_loss: Callable[[int], torch.Tensor], params: Dict[str, torch.Tensor], n_views: int,
-                 reducer: GradAllReducer | None = None, rank: int | None = None, world: int | None = None,
+                 reducer=None, rank: int | None = None, world: int | None = None,
                  order: Sequence[str] = ("means3D", "shs", "opacities", "scales", "rotations")):
-    """One data-parallel step over ``n_views`` cameras.
+    """One data-parallel step over ``n_views`` cameras (train.py:93-99,219-225 per rank).
 
-    ``render_loss(view_index)`` must render that view from ``params`` and return a scalar loss.
-    Every rank back-propagates its own views (gradients accumulate in ``params[k].grad``) and the
-    accumulated gradients are then summed over ranks.  Returns (local_loss_sum, my_view_indices).
-    """
+    ``render_loss(view_index)`` must render that view from ``params`` and return a scalar loss.  Every rank
+    back-propagates its own views, the gradients accumulate over them, and the accumulated gradients are summed
+    over ranks with ONE collective.  With a bucket reducer (`PeerGradAllReducer`, `NcclBucketAllReducer`, provider
+    installed with `diff_surfel_rasterization.set_grad_bucket_provider`) the accumulation happens inside the
+    backward kernel, in the buffer the collective reduces; otherwise autograd accumulates into ``.grad``.
+    Returns (local_loss_sum, my_view_indices)."""
     if rank is None:
         rank = dist.get_rank() if dist.is_initialized() else 0
     if world is None:
         world = dist.get_world_size() if dist.is_initialized() else 1
     reducer = reducer or GradAllReducer()
+    bucketed = isinstance(reducer, BucketBatch)
     for p in params.values():
         p.grad = None
     mine = shard_views(n_views, rank, world)
+    reducer.begin_batch()
     total = None
     for v in mine:
+        if bucketed:                      # the kernel accumulates in the bucket: autograd must adopt, not add
+            for p in params.values():
+                p.grad = None
         loss = render_loss(v)
         loss.backward()
         total = loss.detach() if total is None else total + loss.detach()
+    present = [k for k in order if params.get(k) is not None]
+    if n_views < world and world > 1 and present:
+        # Some rank has no view.  It still has to join the collective, and with the SAME layout as its peers: the
+        # ranks that rendered say whether their gradients came out as one bucket (the rasteriser's) or as separate
+        # tensors (any other model); an idle rank then builds zero gradients of that layout — one bucket carved like
+        # a backward pass would, or one tensor per parameter.  (Five small collectives against one large one would
+        # hang NCCL or reduce garbage.)
+        ref = params[present[0]]
+        bucketed_here = 1 if not mine else int(grad_bucket([params[k].grad for k in present]) is not None)
+        flag = torch.tensor([bucketed_here], dtype=torch.int32, device=ref.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=getattr(reducer, "group", None))
+        if not mine and int(flag.item()) == 1 and set(present) == set(order):
+            from . import diff_surfel_rasterization as dsr
+            P, M = params["means3D"].shape[0], params["shs"].shape[1]
+            for k, z in zip(order, dsr.zero_bucket_grads(P, M, ref.device)):
+                params[k].grad = z
     grads = []
-    for k in order:
-        p = params.get(k)
-        if p is None:
-            continue
-        if p.grad is None:            # a rank without views still has to join the collective
+    for k in present:
+        p = params[k]
+        if p.grad is None:
             p.grad = torch.zeros_like(p)
         grads.append(p.grad)
     reducer.launch(grads)

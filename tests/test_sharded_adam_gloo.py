@@ -136,38 +136,53 @@ def _scene_and_views(n_views):
     return scene, cams, ups
 
 
-def _raster_worker(rank, world, port, n_views, out):
+def _raster_worker(rank, world, port, n_views, bucketed, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     _patch_emulated_library()
-    from partgs_b200.dist import GradAllReducer, sharded_step
-    scene, cams, ups = _scene_and_views(n_views)
+    from partgs_b200.dist import GradAllReducer, NcclBucketAllReducer, sharded_step
+    from partgs_b200 import diff_surfel_rasterization as dsr
+    scene, cams, ups = _scene_and_views(max(n_views, 1))
     params = {k: scene[k].clone().requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
-    total, mine = sharded_step(lambda v: _render_loss(params, cams[v], ups[v]), params, n_views, GradAllReducer())
+    if bucketed:
+        # the batch mode of SURVEY 8(e): the backward kernel accumulates the views of this rank in ONE bucket, which a
+        # single collective reduces (here over gloo; PeerGradAllReducer is the NVLink version of the same class)
+        reducer = NcclBucketAllReducer(dsr.bucket_numel(120, 16), "cpu")
+        dsr.set_grad_bucket_provider(reducer.bucket_provider)
+    else:
+        reducer = GradAllReducer()
+    total, mine = sharded_step(lambda v: _render_loss(params, cams[v], ups[v]), params, n_views, reducer)
+    if bucketed:
+        from partgs_b200.dist import grad_bucket
+        flat = grad_bucket([params[k].grad for k in ("means3D", "shs", "opacities", "scales", "rotations")])
+        assert flat is not None and flat.untyped_storage().data_ptr() == reducer.current().untyped_storage().data_ptr()
     out[rank] = (mine, {k: p.grad.clone() for k, p in params.items()})
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_camera_sharded_step_with_the_real_rasteriser(monkeypatch):
+@pytest.mark.parametrize("n_views,bucketed", [(3, False), (5, True), (1, True), (1, False)])
+def test_camera_sharded_step_with_the_real_rasteriser(monkeypatch, n_views, bucketed):
     """Views shard by camera, parameters are replicated, the five parameter gradients are summed over the ranks:
-    equal to one process back-propagating all views — with the product's own kernels (emulated)."""
+    equal to one process back-propagating all views — with the product's own kernels (emulated).
+    bucketed: gradients accumulate inside the backward kernel in one bucket per batch (rank 0 renders three views,
+    rank 1 two), one collective.  n_views = 1: rank 1 has no view and must still join with the same layout."""
     import build as emu_build
     try:
         emu_build.build_full()
     except emu_build.EmuUnavailable as ex:
         pytest.skip(str(ex))
-    world, n_views = 2, 3
+    world = 2
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_raster_worker, args=(world, _free_port(), n_views, out), nprocs=world, join=True)
+    mp.spawn(_raster_worker, args=(world, _free_port(), n_views, bucketed, out), nprocs=world, join=True)
     _patch_emulated_library(monkeypatch)
     scene, cams, ups = _scene_and_views(n_views)
     params = {k: scene[k].clone().requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
     for v in range(n_views):
         _render_loss(params, cams[v], ups[v]).backward()
-    assert out[0][0] == [0, 2] and out[1][0] == [1]
+    assert out[0][0] == list(range(0, n_views, 2)) and out[1][0] == list(range(1, n_views, 2))
     for rank in range(world):
         for k, p in params.items():
             got = out[rank][1][k]
