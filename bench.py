@@ -237,6 +237,45 @@ class OursArm:
         return int(self.lib.pgs_launch_count())
 
 
+class OursBlocksArm(OursArm):
+    """C5: the scene is a set of superquadrics; surfel i is generated inside preprocess (pgs_dsr_forward_blocks /
+    _backward_blocks).  Parameters: the five block parameters + per-surfel SH coefficients."""
+
+    def __init__(self, model, shs, dev):
+        from partgs_b200 import _lib
+        from partgs_b200.diff_surfel_rasterization import GaussianRasterizationSettings
+        from partgs_b200.superquadric import rasterize_blocks
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.S = GaussianRasterizationSettings
+        self.rasterize_blocks = rasterize_blocks
+        self.model = model
+        self.dev = dev
+        self.order = ("sq_r", "sq_s", "sq_t", "sq_eps", "sq_occ", "shs")
+        self.params = {k: getattr(model, k).detach().clone().requires_grad_(True) for k in self.order[:5]}
+        self.params["shs"] = shs.clone().requires_grad_(True)
+        self.last_radii = None
+
+    def step(self, cam, bg, g, params=None, want_loss=False):
+        p = params or self.params
+        for t in p.values():
+            t.grad = None
+        m = self.model
+        settings = self.S(image_height=cam.image_height, image_width=cam.image_width, tanfovx=cam.tanfovx,
+                          tanfovy=cam.tanfovy, bg=bg, scale_modifier=1.0, viewmatrix=cam.viewmatrix,
+                          projmatrix=cam.projmatrix, sh_degree=3, campos=cam.campos, prefiltered=False, debug=False)
+        color, radii, allmap, _ = self.rasterize_blocks(settings, p["sq_r"], p["sq_s"], p["sq_t"], p["sq_eps"], p["sq_occ"],
+                                                        m.alpha, m._scale, p["shs"], m.sq_eta, m.sq_omega, m.faces)
+        loss = None
+        if want_loss:
+            loss = (color * g["color"]).sum() + (allmap * g["allmap"]).sum()
+            loss.backward()
+        else:
+            torch.autograd.backward([color, allmap], [g["color"], g["allmap"]])
+        self.last_radii = radii
+        return loss, [p[k].grad for k in self.order]
+
+
 class ReferenceArm:
     name = "reference"
 
@@ -278,7 +317,25 @@ def run(args):
     name = args.workload
     cfg = dict(synth.CONFIGS[name])
     seed = synth.SEED_BASE + synth.CONFIG_INDEX[name]
-    scene = synth.make_point_scene(cfg["P"], seed, S=0, device=dev)
+    block_model = None
+    if name == "C5":
+        # BASELINE configs[4]: 3 M surfels generated from superquadrics (8 blocks x 320 faces x 1172 samples); the
+        # reference arm rasterises the same surfels, materialised once (it has no fused path: its generation cost,
+        # ~45 ATen kernels per view, is left out of its time)
+        from partgs_b200.superquadric import BlockSurfelModel
+        gen = torch.Generator().manual_seed(seed)
+        block_model = BlockSurfelModel(8, cfg["P"] // (8 * 320), device=dev, generator=gen)
+        Pb = 8 * block_model.per_gs_num
+        shs = torch.zeros(Pb, 16, 3)
+        shs[:, 0] = synth.RGB2SH(torch.rand(Pb, 3, generator=gen))
+        shs[:, 1:] = 0.05 * torch.randn(Pb, 15, 3, generator=gen)
+        with torch.no_grad():
+            scene = dict(means3D=block_model.get_xyz.detach().contiguous(), scales=block_model.get_scaling.detach().contiguous(),
+                         rotations=block_model.get_rotation.detach().contiguous(),
+                         opacities=block_model.get_opacity.detach().reshape(-1, 1).contiguous(), shs=shs.to(dev))
+        cfg["P"] = Pb
+    else:
+        scene = synth.make_point_scene(cfg["P"], seed, S=0, device=dev)
     all_cams = synth.make_cameras(cfg["views"], cfg["W"], cfg["H"], seed, device=dev)
     my_cams = all_cams[rank::world] or all_cams
     W, H, P = cfg["W"], cfg["H"], cfg["P"]
@@ -294,6 +351,8 @@ def run(args):
                                   "unavailable": "oracle/_ref/ref_dsr_C.so not built (needs /root/reference)"}))
             return
         arm = ReferenceArm(scene, dev)
+    elif block_model is not None:
+        arm = OursBlocksArm(block_model, scene["shs"], dev)
     else:
         arm = OursArm(scene, dev)
 
@@ -303,7 +362,7 @@ def run(args):
     # ---- data-parallel batch: accum views per rank and batch, one all-reduce per batch ----------
     accum = args.accum if args.accum > 0 else (len(all_cams) + world - 1) // world
     reducer = None
-    if world > 1 and arm.name == "ours":
+    if world > 1 and arm.name == "ours" and block_model is None:
         # the backward kernel accumulates the batch in ONE bucket (232 B/surfel) that lives in peer-mapped memory and
         # is reduced by one kernel over NVLink (partgs_b200.dist.PeerGradAllReducer), or by one NCCL all-reduce
         from partgs_b200.dist import NcclBucketAllReducer, PeerGradAllReducer
@@ -382,7 +441,10 @@ def run(args):
 
     def view_of_step(i):
         if schedule is not None:
-            return schedule[i % len(schedule)][rank]
+            # the views of a group are sorted by cost: rotate which rank takes which, or rank 0 would always render
+            # the most expensive view of its group
+            k_ = i % len(schedule)
+            return schedule[k_][(rank + i // len(schedule) + k_) % world]
         if world > 1:
             return (rank + world * (i % len(my_cams))) % len(all_cams)
         # N = 1: stride through the camera ring (the views sweep the azimuth in order; K < views consecutive ones
