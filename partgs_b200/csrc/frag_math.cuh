@@ -61,7 +61,10 @@ __device__ __forceinline__ bool frag_geometry(const float2 pixf, const float3 Tu
   f.d = make_float2(__fsub_rn(xy.x, pixf.x), __fsub_rn(xy.y, pixf.y));
   if (PART) {
     const float dd = __fmaf_rn(f.d.x, f.d.x, __fmul_rn(f.d.y, f.d.y));
-    f.rho2d = (float)((double)dd * (1 / (0.7071067811865476 * 0.7071067811865476)));
+    // reference: (float)((double)dd * (1 / 0.7071067811865476^2)).  The double constant is 2 (1 +- 2.2e-16), 2 dd is
+    // a float, and the double product lies 2.2e-16 (relative) from it — eight orders of magnitude inside the
+    // rounding interval of that float: the conversion returns 2 dd, always.  No double arithmetic needed.
+    f.rho2d = __fadd_rn(dd, dd);
   } else {
     const float dd = __fmaf_rn(f.d.y, f.d.y, __fmul_rn(f.d.x, f.d.x));
     f.rho2d = __fadd_rn(dd, dd);  // FilterInvSquare = 2
@@ -88,7 +91,9 @@ __device__ __forceinline__ bool frag_eval(const float2 pixf, const float4 q0, co
   bool ok = frag_geometry<PART>(pixf, make_float3(q0.x, q0.y, q0.z), make_float3(q1.x, q1.y, q1.z),
                                 make_float3(q2.x, q2.y, q2.z), make_float2(q0.w, q1.w), f);
   depth = f.depth;
-  if (PART) ok = ok && !((double)depth < 0.2);
+  // `_part` compares in double: (double)depth < 0.2.  The largest float below 0.2 (double) is the predecessor of
+  // 0.2f, and 0.2f itself lies above 0.2 (double): as a float comparison this is depth < 0.2f, exactly.
+  if (PART) ok = ok && !(depth < 0.2f);
   else ok = ok && !(depth < 0.2f);
   float power, G;
   alpha = frag_alpha(f.rho3d, f.rho2d, q2.w, power, G);

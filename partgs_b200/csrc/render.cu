@@ -37,6 +37,7 @@
 // The forward per-fragment arithmetic is pinned in frag_math.cuh; accumulations below use the
 // reference's rounding sequence (explicit fma/mul), so images are bit-identical.
 #include "common.cuh"
+#include "f32x2.cuh"
 #include "frag_math.cuh"
 #include "kernels.h"
 #include "render_common.cuh"
@@ -215,10 +216,12 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 4) render_fwd_kernel(Rend
   float N[3] = {0.f, 0.f, 0.f};
   float D = 0.f, M1 = 0.f, M2 = 0.f, distortion = 0.f, median_depth = 0.f, median_weight = 0.f;
   float median_contributor = -1.f;
-  float Sem[MAX_SEMANTIC];
+  // `_part`: the S <= 16 part channels are blended as 8 packed pairs (FMUL2 + FFMA2 per pair: each half is rounded
+  // exactly like the scalar fma(T, sem * alpha, acc) of the reference build)
+  P2 Sem2[MAX_SEMANTIC / 2];
   if (PART) {
 #pragma unroll
-    for (int i = 0; i < MAX_SEMANTIC; i++) Sem[i] = 0.f;
+    for (int i = 0; i < MAX_SEMANTIC / 2; i++) Sem2[i] = bc(0.f);
   }
 
   const float4 nobox = make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);
@@ -242,9 +245,15 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 4) render_fwd_kernel(Rend
       for (int q = 0; q < REC_QUADS; q++) cp_async16(&st.rec[slot][q], src + q);
       st.pos[slot] = (uint32_t)(base + lane + 1);
       if (PART) {
+        // the survivor's part row rides the same cp.async group as its record: 16-byte copies when the rows are
+        // 16-byte aligned (S = 4, 8, 12, 16), scalar loads otherwise; channels >= S of the slot are never consumed
         float* sem_stage = s_sem_dyn + ((size_t)(buf * nw + lw) * CHUNK + slot) * MAX_SEMANTIC;
         const float* sem = a.semantics + (size_t)id * S;
-        for (int ch = 0; ch < S; ch++) sem_stage[ch] = __ldg(sem + ch);
+        if ((S & 3) == 0 && (reinterpret_cast<size_t>(a.semantics) & 15) == 0) {
+          for (int q = 0; q < (S >> 2); q++) cp_async16(sem_stage + 4 * q, sem + 4 * q);
+        } else {
+          for (int ch = 0; ch < S; ch++) sem_stage[ch] = __ldg(sem + ch);
+        }
       }
     }
     cp_async_commit();
@@ -338,9 +347,15 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 4) render_fwd_kernel(Rend
           C[0] = __fmaf_rn(T, __fmul_rn(q4.x, alpha), C[0]);
           C[1] = __fmaf_rn(T, __fmul_rn(q4.y, alpha), C[1]);
           C[2] = __fmaf_rn(T, __fmul_rn(q4.z, alpha), C[2]);
+          const float4* srow = reinterpret_cast<const float4*>(sem_stage + j * MAX_SEMANTIC);
+          const P2 a2 = bc(alpha), T2 = bc(T);
 #pragma unroll
-          for (int ch = 0; ch < MAX_SEMANTIC; ch++)
-            if (ch < S) Sem[ch] = __fmaf_rn(T, __fmul_rn(sem_stage[j * MAX_SEMANTIC + ch], alpha), Sem[ch]);
+          for (int q = 0; q < MAX_SEMANTIC / 4; q++)
+            if (4 * q < S) {   // channels in [S, 4 ceil(S/4)) of a quad accumulate stale values that are never stored
+              const float4 v = srow[q];
+              Sem2[2 * q] = fma2(T2, mul2(pk(v.x, v.y), a2), Sem2[2 * q]);
+              Sem2[2 * q + 1] = fma2(T2, mul2(pk(v.z, v.w), a2), Sem2[2 * q + 1]);
+            }
         }
         T = test_T;
         last_contributor = contributor;
@@ -402,7 +417,7 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 4) render_fwd_kernel(Rend
       a.out_others[pix_id + MEDIAN_WEIGHT_OFFSET * HW] = median_weight;
 #pragma unroll
       for (int ch = 0; ch < MAX_SEMANTIC; ch++)
-        if (ch < S) a.out_semantic[ch * HW + pix_id] = Sem[ch];
+        if (ch < S) a.out_semantic[ch * HW + pix_id] = (ch & 1) ? hi(Sem2[ch >> 1]) : lo(Sem2[ch >> 1]);
     }
   }
 }
