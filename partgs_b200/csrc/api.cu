@@ -42,22 +42,34 @@ int check_sync(cudaStream_t s, const char* what) {
 
 // ---- optional per-stage device timing (CUDA events on the launching stream) ------
 // bench.py uses it to time the dominant kernel live inside its timed region.
-struct StageSpan { int stage; cudaEvent_t a, b; };
+struct StageSpan { int stage; int dev; cudaEvent_t a, b; };
 static std::atomic<int> g_timing{0};
 static std::mutex g_timing_mu;
 static std::vector<StageSpan> g_spans;
-static std::vector<cudaEvent_t> g_event_pool;
-static cudaEvent_t get_event() {
-  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+// CUDA events belong to the device they were created on: one pool per device (a process may drive several GPUs)
+constexpr int PGS_MAX_DEVICES = 64;
+static std::vector<cudaEvent_t> g_event_pool[PGS_MAX_DEVICES];
+static int current_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < PGS_MAX_DEVICES) ? dev : -1;
+}
+static cudaEvent_t get_event(int dev) {
+  auto& pool = g_event_pool[dev];
+  if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 struct StageTimer {
-  bool on; int stage; cudaStream_t s; cudaEvent_t a, b;
-  StageTimer(int stage_, cudaStream_t s_) : on(g_timing.load() != 0), stage(stage_), s(s_) {
-    if (on) { std::lock_guard<std::mutex> lk(g_timing_mu); a = get_event(); b = get_event(); cudaEventRecord(a, s); }
+  bool on; int stage; int dev; cudaStream_t s; cudaEvent_t a, b;
+  StageTimer(int stage_, cudaStream_t s_) : on(g_timing.load() != 0), stage(stage_), dev(-1), s(s_) {
+    if (on) {
+      dev = current_device_slot();
+      on = dev >= 0;
+    }
+    if (on) { std::lock_guard<std::mutex> lk(g_timing_mu); a = get_event(dev); b = get_event(dev); cudaEventRecord(a, s); }
   }
   ~StageTimer() {
-    if (on) { cudaEventRecord(b, s); std::lock_guard<std::mutex> lk(g_timing_mu); g_spans.push_back({stage, a, b}); }
+    if (on) { cudaEventRecord(b, s); std::lock_guard<std::mutex> lk(g_timing_mu); g_spans.push_back({stage, dev, a, b}); }
   }
 };
 
@@ -72,11 +84,10 @@ struct CountFetch {
     return true;
   }
 };
-static CountFetch& count_fetch() {
-  static thread_local CountFetch cf[16];
-  int dev = 0;
-  cudaGetDevice(&dev);
-  return cf[dev & 15];
+static CountFetch* count_fetch() {   // one slot per device and host thread; nullptr for a device index out of range
+  static thread_local CountFetch cf[PGS_MAX_DEVICES];
+  const int dev = current_device_slot();
+  return dev < 0 ? nullptr : &cf[dev];
 }
 
 // reference getHigherMsb (rasterizer_impl.cu:35-50)
@@ -211,8 +222,8 @@ int pgs_timing_read(double* ms, unsigned long long* counts, int reset) {
     if (e == cudaSuccess) e = cudaEventElapsedTime(&t, sp.a, sp.b);
     if (e != cudaSuccess) return set_error(PGS_ERR_CUDA, "timing: %s", cudaGetErrorString(e));
     if (sp.stage >= 0 && sp.stage < PGS_NUM_STAGES) { acc_ms[sp.stage] += t; acc_n[sp.stage]++; }
-    g_event_pool.push_back(sp.a);
-    g_event_pool.push_back(sp.b);
+    g_event_pool[sp.dev].push_back(sp.a);
+    g_event_pool[sp.dev].push_back(sp.b);
   }
   g_spans.clear();
   for (int i = 0; i < PGS_NUM_STAGES; i++) {
@@ -365,7 +376,9 @@ static int forward_impl(const SqForward* sqf, bool part, int S, const float* sem
   // arena (first frames of a scene only).
   int dev = 0;
   cudaGetDevice(&dev);
-  CountFetch& cf = count_fetch();
+  CountFetch* cfp = count_fetch();
+  if (!cfp) return set_error(PGS_ERR_UNSUPPORTED, "device index %d out of range (max %d devices per process)", dev, PGS_MAX_DEVICES);
+  CountFetch& cf = *cfp;
   if (!cf.init()) return set_error(PGS_ERR_CUDA, "pinned count buffer: %s", cudaGetErrorString(cudaGetLastError()));
   const uint32_t* n_dev = geom.total;
 
@@ -425,9 +438,9 @@ static int forward_impl(const SqForward* sqf, bool part, int S, const float* sem
     return 0;
   };
 
-  static std::atomic<size_t> capacity_hint[16];
+  static std::atomic<size_t> capacity_hint[PGS_MAX_DEVICES];
   static const bool no_spec = getenv("PGS_NO_SPECULATE") != nullptr;  // diagnostic switch
-  const bool speculate = !debug && !no_spec && dev < 16 && capacity_hint[dev].load() > 0;
+  const bool speculate = !debug && !no_spec && capacity_hint[dev].load() > 0;
   size_t capacity = 0;
   if (speculate) {
     capacity = BinningState::capacity_for(capacity_hint[dev].load());
@@ -447,14 +460,14 @@ static int forward_impl(const SqForward* sqf, bool part, int S, const float* sem
   if (!speculate || (size_t)num_rendered > capacity) {
     // first frame / debug mode / the speculative capacity was too small
     size_t want = (size_t)num_rendered + (size_t)num_rendered / 4;
-    if (dev < 16 && !debug) {
+    if (!debug) {
       size_t cur = capacity_hint[dev].load();
       while (want > cur && !capacity_hint[dev].compare_exchange_weak(cur, want)) {}
       want = std::max(want, cur);
     }
     capacity = BinningState::capacity_for(debug ? (size_t)num_rendered : want);
     if (int e = launch_rest(capacity, nullptr, num_rendered)) return e;
-  } else if (dev < 16 && (size_t)num_rendered * 2 < capacity_hint[dev].load()) {
+  } else if ((size_t)num_rendered * 2 < capacity_hint[dev].load()) {
     // the arena is more than twice what this frame needed: let the remembered capacity decay (3 % per such
     // frame, never below 1.25 x this frame), so that one exceptional frame does not size every later arena
     size_t cur = capacity_hint[dev].load();

@@ -105,7 +105,8 @@ class ShardedFusedAdam:
     the collectives move one contiguous range each and no gather / scatter copies exist.  The update itself is the
     library's one-launch Adam (``pgs_adam_step``): one table entry per (parameter ∩ my slice), each with its group's
     learning rate.  ``param_groups`` keeps the ``{"name", "lr"}`` entries the reference's schedulers write to
-    (scene/gaussian_model.py:268-275).  Arithmetic = torch.optim.Adam(eps=1e-15) on the rank-summed gradient.
+    (scene/gaussian_model.py:268-275); it is NOT interchangeable with torch.optim.Adam beyond that (fixed-size models;
+    see `state`, `state_dict`, `rebuild` below).  Arithmetic = torch.optim.Adam(eps=1e-15) on the rank-summed gradient.
     """
 
     def __init__(self, named_params, betas=(0.9, 0.999), eps=1e-15, group=None, average: bool = False):
@@ -146,6 +147,41 @@ class ShardedFusedAdam:
         self.grad_slice = torch.zeros(self.slice, dtype=torch.float32, device=dev)
         self.step_count = 0
         self._lo = lo
+
+    # ---- what this optimiser is NOT: a drop-in for model surgery --------------------------------------------------
+    # It owns flat parameter / gradient buffers and re-points `p.data` / `p.grad` at views of them, and it keeps only
+    # 1/W of the moments.  Densification (densify.rewrap_optimizer, prune / cat of the reference) replaces the
+    # Parameters and resizes per-parameter state: rebuild a new ShardedFusedAdam from the new tensors afterwards
+    # (`rebuild`), the moments of surviving rows are carried over by the caller through state_dict / load_state_dict
+    # of the gathered state.  `state` (torch's per-parameter dict) does not exist here, on purpose.
+    @property
+    def state(self):
+        raise RuntimeError("ShardedFusedAdam keeps ONE sharded moment buffer, not torch's per-parameter `state`: use "
+                           "state_dict() / load_state_dict(), and rebuild() after the parameter tensors were replaced "
+                           "(densification); for optimiser-state surgery use FusedAdam")
+
+    def state_dict(self):
+        """This rank's shard: {'step', 'rank', 'world', 'numel', 'exp_avg', 'exp_avg_sq', 'param_groups': [{name, lr}]}.
+        A checkpoint of the whole optimiser is the list of the W shards (torch.distributed.all_gather_object, or
+        one file per rank)."""
+        return {"step": self.step_count, "rank": self.rank, "world": self.world, "numel": self.numel,
+                "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "param_groups": [{"name": g["name"], "lr": g["lr"]} for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        if sd["world"] != self.world or sd["rank"] != self.rank or sd["numel"] != self.numel:
+            raise RuntimeError("ShardedFusedAdam.load_state_dict: shard of another layout "
+                               f"(rank {sd['rank']}/{sd['world']}, {sd['numel']} elements)")
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        for g, h in zip(self.param_groups, sd["param_groups"]):
+            g["lr"] = float(h["lr"])
+
+    def rebuild(self, named_params):
+        """A fresh optimiser over new parameter tensors (after densification replaced them), same hyper-parameters;
+        moments start at zero like the reference's cat_tensors_to_optimizer does for new rows."""
+        return ShardedFusedAdam(named_params, betas=self.betas, eps=self.eps, group=self.group, average=self.average)
 
     def zero_grad(self, set_to_none: bool = False):
         """Gradients are views of the flat buffer that autograd accumulates into in place: they are zeroed and

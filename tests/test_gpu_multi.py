@@ -21,8 +21,6 @@ def test_peer_allreduce_equals_nccl():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.xfail(strict=False, reason="ShardedFusedAdam over NCCL: green over gloo + the CPU emulator "
-                                        "(tests/test_sharded_adam_gloo.py), first multi-GPU run pending")
 def test_sharded_adam_equals_replicated_adam():
     n = min(torch.cuda.device_count(), 8)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
@@ -30,3 +28,12 @@ def test_sharded_adam_equals_replicated_adam():
                         str(ROOT / "tools" / "sharded_adam_check.py"), "--P", "200000"], capture_output=True, text=True,
                        timeout=600)
     assert "SHARDED_ADAM_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_sharded_batch_step_on_gpus_equals_single_process_accumulation():
+    n = min(torch.cuda.device_count(), 8)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29535",
+                        str(ROOT / "tools" / "sharded_step_check.py")], capture_output=True, text=True, timeout=600)
+    assert "SHARDED_STEP_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
