@@ -480,6 +480,11 @@ def run(args):
         one_step(i)
     drain()
     torch.cuda.synchronize()
+    if arm.name == "ours" and block_model is None and not args.no_lazy:
+        # every view has been rendered once: from here on the forward call does not wait for the frame's instance count
+        # (partgs_b200.diff_surfel_rasterization.set_lazy_count); every backward verifies that its frame fitted
+        from partgs_b200 import diff_surfel_rasterization as dsr_
+        dsr_.set_lazy_count(True)
 
     # ---- host health: enqueue cost of a trivial kernel and a sync round trip on this box ------------
     # (some boxes of the pool enqueue 10-50x slower than others; a step of this arm is ~16 launches plus
@@ -690,6 +695,9 @@ def run(args):
     # ---- R of the last view (needed by the byte model); taken outside the timed region --
     cam = cam_of_step(args.steps - 1)
     if arm.name == "ours":
+        from partgs_b200 import diff_surfel_rasterization as dsr_
+        dsr_.set_lazy_count(False)
+        dsr_.resolve_count()
         from partgs_b200.diff_surfel_rasterization import _C
         e = torch.empty(0, device=dev)
         R = _C.rasterize_gaussians(bg, scene["means3D"], e, scene["opacities"], scene["scales"], scene["rotations"],
@@ -710,6 +718,8 @@ def run(args):
                    "collective": ("none" if world == 1 else
                                   f"one all-reduce of the 232 B/surfel parameter gradients per batch of {accum} views per rank"),
                    "views_timed": views_timed,
+                   "instance_count": ("lazy: the forward does not wait for it, every backward verifies it" if
+                                      (arm.name == "ours" and block_model is None and not args.no_lazy) else "waited for in the forward call"),
                    "l2": "inputs (232 MB parameters + per-view state) exceed the 126 MB L2; views cycle every step",
                    "V_visible": V, "R_instances": int(R)},
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
@@ -833,6 +843,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--schedule", default="balanced", choices=["balanced", "roundrobin"],
                     help="N>1: which views share a lock-step (groups of similar cost proxy, or plain round-robin)")
+    ap.add_argument("--no-lazy", action="store_true",
+                    help="ours: wait for every frame's instance count inside the forward call (the round-1 behaviour)")
     ap.add_argument("--accum", type=int, default=0,
                     help="N>1: views per rank and batch (one all-reduce per batch); 0 = ceil(views / N)")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],

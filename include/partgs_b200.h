@@ -66,6 +66,25 @@ int pgs_dsr_forward(pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_alloc
                     const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered,
                     float* out_color, float* out_others, int* radii, int debug, void* stream);
 
+/* Lazy instance count.  `debug` of the forward entry points is a flag word: bit 0 = the reference's debug switch, bit 1 =
+ * PGS_FWD_LAZY_COUNT: do not wait for the frame's instance count (the reference blocks on it, rasterizer_impl.cu:282;
+ * by default this library waits AFTER queueing the frame).  The frame is queued for the instance capacity remembered
+ * from earlier frames and the call returns PGS_COUNT_PENDING, which pgs_dsr_backward accepts as R; the first frames of a
+ * scene (no capacity remembered yet) and debug calls are not lazy and return the count.  A forward call issued while its
+ * stream is being captured into a CUDA graph is always lazy (a capture cannot contain the host wait).
+ * pgs_dsr_resolve_count() waits for the counts of all lazy frames of this host thread on the current device (or, with
+ * none pending, reports the slot a replayed graph refreshed — synchronise the stream first) and returns the latest;
+ * *overflow = 1 if a frame needed more instances than it was queued for: its outputs are invalid (its kernels did
+ * nothing) and it must be rendered again — the remembered capacity has been raised.  At most 8 lazy frames may be
+ * outstanding. */
+#define PGS_FWD_LAZY_COUNT 2
+#define PGS_COUNT_PENDING 0x7fffffff
+int pgs_dsr_resolve_count(int* overflow);
+/* The instance capacity speculative / lazy frames on the current device are queued for (x 1.25, rounded up to 512 Ki);
+ * it grows with the frames seen and decays slowly.  0 forgets it (the next frame counts first, like the reference) —
+ * e.g. when switching to a much smaller scene. */
+void pgs_dsr_set_capacity_hint(size_t instances);
+
 /* Bytes of scratch pgs_dsr_backward needs (per-surfel gradient accumulators). */
 size_t pgs_dsr_backward_scratch_bytes(int P);
 

@@ -101,6 +101,8 @@ SIGNATURES = {
     "pgs_dsr_duplicate_with_keys": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "pgs_identify_tile_ranges": (C.c_int, [C.c_int, _vp, _vp, C.c_int, _vp]),
     "pgs_peer_allreduce_slice": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_size_t, C.c_size_t, C.c_int, _vp]),
+    "pgs_dsr_set_capacity_hint": (None, [C.c_size_t]),
+    "pgs_dsr_resolve_count": (C.c_int, [C.POINTER(C.c_int)]),
     "pgs_dsr_sorted_keys": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_size_t, C.c_int, _vp, _vp]),
     "pgs_higher_msb": (C.c_uint32, [C.c_uint32]),
     "pgs_dsr_get_layout": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(DsrLayout)]),

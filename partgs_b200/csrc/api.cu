@@ -75,20 +75,37 @@ struct StageTimer {
 
 // pinned host word + event through which forward reads the instance count of the frame in flight
 struct CountFetch {
-  int* host = nullptr;
-  cudaEvent_t ev = nullptr;
+  // a small ring of pinned words: a lazy forward (PGS_FWD_LAZY_COUNT) leaves its count in the next slot and returns
+  // without waiting; pgs_dsr_resolve_count() later checks every slot still pending
+  static constexpr int SLOTS = 8;
+  int* host = nullptr;            // [SLOTS] pinned
+  cudaEvent_t ev[SLOTS] = {};
+  size_t cap[SLOTS] = {};         // capacity the frame was launched with
+  bool pending[SLOTS] = {};
+  bool captured[SLOTS] = {};      // the slot belongs to a captured CUDA graph (every replay refreshes it): never reused
+  int next = 0, last = 0;
   bool init() {
     if (host) return true;
     if (cudaHostAlloc((void**)&host, 64, cudaHostAllocDefault) != cudaSuccess) { host = nullptr; return false; }
-    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return false;
+    for (int i = 0; i < SLOTS; i++) {
+      host[i] = 0;
+      if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return false;
+    }
     return true;
   }
 };
-static CountFetch* count_fetch() {   // one slot per device and host thread; nullptr for a device index out of range
-  static thread_local CountFetch cf[PGS_MAX_DEVICES];
+// One ring per device, shared by all host threads (PyTorch runs the backward pass on its autograd thread: the count
+// a forward left pending on the caller's thread is resolved from there).  Calls on one device are expected to be
+// ordered by the caller (they share a stream); the mutex only keeps the bookkeeping consistent.
+static std::mutex g_count_mu;
+static CountFetch* count_fetch() {
+  static CountFetch cf[PGS_MAX_DEVICES];
   const int dev = current_device_slot();
   return dev < 0 ? nullptr : &cf[dev];
 }
+
+// instance capacity remembered per device (grow-only with slow decay): what speculative / lazy frames are sized for
+static std::atomic<size_t> g_capacity_hint[PGS_MAX_DEVICES];
 
 // reference getHigherMsb (rasterizer_impl.cu:35-50)
 static uint32_t higher_msb(uint32_t n) {
@@ -290,8 +307,10 @@ static int forward_impl(const SqForward* sqf, bool part, int S, const float* sem
                         const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,
                         const float* rotations, const float* transMat_precomp, const float* viewmatrix,
                         const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered,
-                        float* out_color, float* out_others, int* radii, int debug, void* stream) {
+                        float* out_color, float* out_others, int* radii, int flags, void* stream) {
   (void)prefiltered;
+  // flags: bit 0 = the reference's `debug` (synchronise and check after every stage), bit 1 = PGS_FWD_LAZY_COUNT
+  const int debug = flags & 1;
   if (part) {
     if (S < 0 || S > MAX_SEMANTIC)
       return set_error(PGS_ERR_UNSUPPORTED, "semantic channels must be in [0, %d] (got %d)", MAX_SEMANTIC, S);
@@ -379,7 +398,20 @@ static int forward_impl(const SqForward* sqf, bool part, int S, const float* sem
   CountFetch* cfp = count_fetch();
   if (!cfp) return set_error(PGS_ERR_UNSUPPORTED, "device index %d out of range (max %d devices per process)", dev, PGS_MAX_DEVICES);
   CountFetch& cf = *cfp;
+  std::unique_lock<std::mutex> count_lock(g_count_mu);
   if (!cf.init()) return set_error(PGS_ERR_CUDA, "pinned count buffer: %s", cudaGetErrorString(cudaGetLastError()));
+  // Lazy count (flag bit 1, or implied by stream capture — a capture cannot contain the host wait): see below
+  cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &cap_status);
+  const bool capturing = cap_status != cudaStreamCaptureStatusNone;
+  const bool want_lazy = !debug && (capturing || (flags & PGS_FWD_LAZY_COUNT));
+  int slot = cf.next;
+  for (int k = 0; k < CountFetch::SLOTS && cf.captured[slot]; k++) slot = (slot + 1) % CountFetch::SLOTS;
+  if (cf.captured[slot])
+    return set_error(PGS_ERR_UNSUPPORTED, "all %d count slots belong to captured graphs", CountFetch::SLOTS);
+  if (cf.pending[slot])
+    return set_error(PGS_ERR_UNSUPPORTED, "more than %d frames rendered with a lazy instance count without "
+                                          "pgs_dsr_resolve_count()", CountFetch::SLOTS);
   const uint32_t* n_dev = geom.total;
 
   const int end_bit = 32 + (int)higher_msb(gx * gy);
@@ -409,9 +441,9 @@ static int forward_impl(const SqForward* sqf, bool part, int S, const float* sem
     }
     if (int e = check_cuda("emit_instances")) return e;
     if (count_dev) {  // speculative launch: the count goes to the host while the rest of the frame is queued
-      cudaError_t ce = cudaMemcpyAsync(cf.host, geom.total, sizeof(int), cudaMemcpyDeviceToHost, s);
+      cudaError_t ce = cudaMemcpyAsync(cf.host + slot, geom.total, sizeof(int), cudaMemcpyDeviceToHost, s);
       if (ce != cudaSuccess) return set_error(PGS_ERR_CUDA, "memcpy num_rendered: %s", cudaGetErrorString(ce));
-      cudaEventRecord(cf.ev, s);
+      if (!capturing) cudaEventRecord(cf.ev[slot], s);
     }
     if (n > 0) {
       { StageTimer t(PGS_STAGE_SORT, s);
@@ -438,41 +470,57 @@ static int forward_impl(const SqForward* sqf, bool part, int S, const float* sem
     return 0;
   };
 
-  static std::atomic<size_t> capacity_hint[PGS_MAX_DEVICES];
   static const bool no_spec = getenv("PGS_NO_SPECULATE") != nullptr;  // diagnostic switch
-  const bool speculate = !debug && !no_spec && capacity_hint[dev].load() > 0;
+  const bool speculate = !debug && !no_spec && g_capacity_hint[dev].load() > 0;
+  if (want_lazy && !speculate)
+    if (capturing)
+      return set_error(PGS_ERR_UNSUPPORTED, "stream capture needs a remembered instance capacity: render one frame of "
+                                            "the scene eagerly before capturing");
+  const bool lazy = want_lazy && speculate;
   size_t capacity = 0;
   if (speculate) {
-    capacity = BinningState::capacity_for(capacity_hint[dev].load());
+    capacity = BinningState::capacity_for(g_capacity_hint[dev].load());
     if (int e = launch_rest(capacity, n_dev, 0)) return e;
   } else {
     // no capacity to speculate with (first frame, debug mode): count first, as the reference does
     launch_inclusive_scan_u32(geom.tiles_touched, geom.point_offsets, P, geom.scan_temp, s);
     if (int e = check_cuda("scan")) return e;
-    cudaError_t ce0 = cudaMemcpyAsync(cf.host, geom.point_offsets + P - 1, sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaError_t ce0 = cudaMemcpyAsync(cf.host + slot, geom.point_offsets + P - 1, sizeof(int), cudaMemcpyDeviceToHost, s);
     if (ce0 != cudaSuccess) return set_error(PGS_ERR_CUDA, "memcpy num_rendered: %s", cudaGetErrorString(ce0));
-    cudaEventRecord(cf.ev, s);
+    cudaEventRecord(cf.ev[slot], s);
   }
-  cudaError_t ce = cudaEventSynchronize(cf.ev);
+  if (lazy) {
+    // The caller does not want to wait: the frame is queued for `capacity`; whether it fitted is established by
+    // pgs_dsr_resolve_count() (at the backward's entry, or after a CUDA-graph replay).
+    cf.pending[slot] = !capturing;   // a captured frame has no host-side bookkeeping: replays just refresh the slot
+    cf.captured[slot] = capturing;
+    cf.cap[slot] = capacity;
+    cf.last = slot;
+    cf.next = (slot + 1) % CountFetch::SLOTS;
+    return PGS_COUNT_PENDING;
+  }
+  cudaError_t ce = cudaEventSynchronize(cf.ev[slot]);
   if (ce != cudaSuccess) return set_error(PGS_ERR_CUDA, "scan/num_rendered: %s", cudaGetErrorString(ce));
-  const int num_rendered = *cf.host;
+  const int num_rendered = cf.host[slot];
+  cf.cap[slot] = capacity;
+  cf.last = slot;
   if (num_rendered < 0) return set_error(PGS_ERR_UNSUPPORTED, "more than 2^31 surfel-tile instances");
   if (!speculate || (size_t)num_rendered > capacity) {
     // first frame / debug mode / the speculative capacity was too small
     size_t want = (size_t)num_rendered + (size_t)num_rendered / 4;
     if (!debug) {
-      size_t cur = capacity_hint[dev].load();
-      while (want > cur && !capacity_hint[dev].compare_exchange_weak(cur, want)) {}
+      size_t cur = g_capacity_hint[dev].load();
+      while (want > cur && !g_capacity_hint[dev].compare_exchange_weak(cur, want)) {}
       want = std::max(want, cur);
     }
     capacity = BinningState::capacity_for(debug ? (size_t)num_rendered : want);
     if (int e = launch_rest(capacity, nullptr, num_rendered)) return e;
-  } else if ((size_t)num_rendered * 2 < capacity_hint[dev].load()) {
+  } else if ((size_t)num_rendered * 2 < g_capacity_hint[dev].load()) {
     // the arena is more than twice what this frame needed: let the remembered capacity decay (3 % per such
     // frame, never below 1.25 x this frame), so that one exceptional frame does not size every later arena
-    size_t cur = capacity_hint[dev].load();
+    size_t cur = g_capacity_hint[dev].load();
     const size_t floor_ = (size_t)num_rendered + (size_t)num_rendered / 4;
-    capacity_hint[dev].store(std::max(floor_, cur - cur / 32));
+    g_capacity_hint[dev].store(std::max(floor_, cur - cur / 32));
   }
   if (debug) if (int e = check_sync(s, "render_fwd")) return e;
   return num_rendered;
@@ -507,6 +555,46 @@ int pgs_dsrp_forward(pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_allo
                       projmatrix, cam_pos, tan_fovx, tan_fovy, prefiltered, out_color, out_others, radii, debug, stream);
 }
 
+void pgs_dsr_set_capacity_hint(size_t instances) {
+  const int dev = current_device_slot();
+  if (dev >= 0) g_capacity_hint[dev].store(instances);
+}
+
+int pgs_dsr_resolve_count(int* overflow) {
+  if (overflow) *overflow = 0;
+  CountFetch* cf = count_fetch();
+  std::unique_lock<std::mutex> count_lock(g_count_mu);
+  if (!cf || !cf->host) return 0;
+  const int dev = current_device_slot();
+  int last_count = cf->host[cf->last];
+  bool any = false;
+  for (int k = 0; k < CountFetch::SLOTS; k++) {
+    const int i = (cf->next + k) % CountFetch::SLOTS;   // oldest first
+    if (!cf->pending[i]) continue;
+    any = true;
+    cudaError_t ce = cudaEventSynchronize(cf->ev[i]);
+    if (ce != cudaSuccess) return set_error(PGS_ERR_CUDA, "resolve_count: %s", cudaGetErrorString(ce));
+    cf->pending[i] = false;
+    const int n = cf->host[i];
+    last_count = n;
+    if (n < 0 || (size_t)n > cf->cap[i]) {
+      if (overflow) *overflow = 1;
+      // remember the larger need, so that the re-rendered frame (and the following ones) fit
+      size_t want = (size_t)(n < 0 ? 0x7fffffff : n);
+      want += want / 4;
+      size_t cur = g_capacity_hint[dev].load();
+      while (want > cur && !g_capacity_hint[dev].compare_exchange_weak(cur, want)) {}
+    }
+  }
+  if (!any) {
+    // nothing pending: a captured frame replayed by the caller (who synchronised the stream): report its slot
+    const int n = cf->host[cf->last];
+    if (overflow && (n < 0 || (size_t)n > cf->cap[cf->last])) *overflow = 1;
+    return n;
+  }
+  return last_count;
+}
+
 size_t pgs_dsr_backward_scratch_bytes(int P) { return (size_t)(P > 0 ? P : 0) * GRAD_FLOATS * sizeof(float) + 256; }
 
 }  // extern "C"
@@ -538,6 +626,7 @@ static int backward_impl(const SqArgs* sq, const float* sq_vertices, bool part, 
   }
   cudaStream_t s = (cudaStream_t)stream;
   if (P <= 0 || width <= 0 || height <= 0 || R < 0) return set_error(PGS_ERR_INVALID_ARG, "bad sizes");
+  const bool r_pending = R == PGS_COUNT_PENDING;   // lazy forward: the count is not known here; the arena's capacity is
   if (!geom_buffer || !image_buffer || (R > 0 && !binning_buffer))
     return set_error(PGS_ERR_INVALID_ARG, "null state buffer");
   if (!dL_dpix || !dL_dothers || !scratch || !dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D ||
@@ -559,7 +648,7 @@ static int backward_impl(const SqArgs* sq, const float* sq_vertices, bool part, 
   size_t mask_stride = 0;
   if (R > 0) {
     const size_t capacity = BinningState::capacity_from_bytes(binning_bytes, end_bit);
-    if (capacity == 0 || capacity < (size_t)R)
+    if (capacity == 0 || (!r_pending && capacity < (size_t)R))
       return set_error(PGS_ERR_INVALID_ARG, "binning buffer of %zu bytes was not produced by the forward pass of "
                                             "this frame (%d instances)", binning_bytes, R);
     BinningState bin = BinningState::from(binning_buffer, capacity, end_bit);

@@ -67,7 +67,7 @@ def _native_forward(bg, means3D, colors, opacity, scales, rotations, scale_modif
                 _lib.ptr(scales), float(scale_modifier), _lib.ptr(rotations), _lib.ptr(transMat_precomp),
                 _lib.ptr(viewmatrix), _lib.ptr(projmatrix), _lib.ptr(campos), float(tan_fovx), float(tan_fovy),
                 int(bool(prefiltered)), _lib.ptr(out_color), _lib.ptr(out_others), _lib.ptr(radii),
-                int(bool(debug)), _lib.current_stream(dev))
+                int(bool(debug)) | (2 if _lazy_count else 0), _lib.current_stream(dev))
         if sc.error is not None:
             raise sc.error
         rendered = _lib.check(rc, "pgs_dsr_forward")
@@ -78,6 +78,39 @@ def _native_forward(bg, means3D, colors, opacity, scales, rotations, scale_modif
     return rendered, out_color, out_others, radii, sc.tensor(sc.GEOM), sc.tensor(sc.BINNING), sc.tensor(sc.IMAGE)
 
 
+_lazy_count = False
+
+
+def set_lazy_count(flag: bool):
+    """Do not wait for the frame's instance count inside the forward call (PGS_FWD_LAZY_COUNT, include/partgs_b200.h).
+    The reference blocks on that count before binning (rasterizer_impl.cu:282); by default this library waits after
+    it has queued the whole frame.  Lazy: the forward returns at once, the count is checked at the entry of the
+    backward pass (`resolve_count`) — by then it has long arrived, so the host runs a whole forward ahead of the GPU.
+    A frame that needed more instances than the remembered capacity raises there (its outputs are invalid; render
+    the scene's views once eagerly first — the capacity is 1.25 x the largest frame seen).  Frames issued under
+    CUDA-graph capture are lazy regardless (`partgs_b200.graphs`)."""
+    global _lazy_count
+    _lazy_count = bool(flag)
+
+
+def resolve_count(device=None):
+    """(num_rendered, overflow) of the lazy frames outstanding on the current device (see set_lazy_count)."""
+    import ctypes as C
+    ov = C.c_int(0)
+    with (torch.cuda.device(device) if device is not None else _null()):
+        n = _lib.load().pgs_dsr_resolve_count(C.byref(ov))
+    return _lib.check(n, "pgs_dsr_resolve_count"), bool(ov.value)
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+COUNT_PENDING = 0x7fffffff
 _bucket_provider = None
 
 
@@ -150,6 +183,13 @@ def _native_backward(bg, means3D, radii, colors, scales, rotations, scale_modifi
     dL_dcolors = torch.empty((P, NUM_CHANNELS), **f32)
     dL_dtransMat = torch.empty((P, 9), **f32)
     if P != 0:
+        if int(R) == COUNT_PENDING and not torch.cuda.is_current_stream_capturing():
+            # lazy forward: the count has arrived long ago (it is produced early in the frame); make sure it fitted
+            n, overflow = resolve_count()
+            if overflow:
+                raise RuntimeError(f"lazy instance count: a frame needed {n} instances, more than it was queued for; its "
+                                   "outputs are invalid.  The remembered capacity has been raised — render again (or "
+                                   "render every view once before set_lazy_count(True))")
         means3D = means3D.contiguous()
         dL_dout_color = _lib.require_cuda_float(dL_dout_color, "dL_dout_color")
         dL_dout_others = _lib.require_cuda_float(dL_dout_others, "dL_dout_others")

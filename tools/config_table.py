@@ -233,6 +233,23 @@ def main():
                 losses(color, post_oracle.surface_maps(allmap, cam, 1.0), loss_oracle.photometric_loss).backward()
 
             row = dict(kernel="training iteration (render + surface maps + losses + backward)", cfg=name, W=W, H=H)
+            # the same iteration with the host out of the loop: lazy instance count, and as a replayed CUDA graph
+            from partgs_b200 import diff_surfel_rasterization as dsr
+            from partgs_b200.graphs import GraphedIteration
+            for cam in cams:
+                ours(cam)
+            dsr.set_lazy_count(True)
+            ts = []
+            for cam in cams:
+                ours(cam)
+                ts += timed(lambda: ours(cam), a.reps)
+            row["ours_lazy_count_ms"] = round(statistics.median(ts), 4)
+            dsr.set_lazy_count(False)
+            dsr.resolve_count()
+            git = GraphedIteration(lambda: ours(cams[0]), warmup=2)
+            row["ours_cuda_graph_ms"] = round(statistics.median(timed(lambda: git.replay(check=False), 3 * a.reps)), 4)
+            git.verify()
+            del git
             for nm, fn in (("reference_ms", ref), ("ours_ms", ours)):
                 if nm == "reference_ms" and not ref_cuda.available("ref_dsr_C"):
                     continue
