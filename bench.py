@@ -234,7 +234,8 @@ class OursArm:
         return loss, [p[k].grad for k in ("means3D", "shs", "opacities", "scales", "rotations")]
 
     def launches(self):
-        return int(self.lib.pgs_launch_count())
+        # kernels launched by the host + kernels of this library executed by replayed CUDA graphs
+        return int(self.lib.pgs_launch_count()) + getattr(self, "replayed_launches", 0)
 
 
 class OursBlocksArm(OursArm):
@@ -391,12 +392,61 @@ def run(args):
         for t in grads:
             ref_pending.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
 
+    # ---- CUDA-graph replay of a step (ours, point-level): forward + backward of one view captured once per variant
+    # (which bucket, overwrite or accumulate), the view's camera copied into three small static tensors before each
+    # replay.  The forward inside a capture never waits for the instance count (PGS_FWD_LAZY_COUNT); the counts of
+    # the captured variants are checked after the timed region.
+    graphs = {}
+    gcam = None
+
+    def graph_view(i, first):
+        nonlocal gcam
+        cam = cam_of_step(i)
+        if gcam is None:
+            gcam = cam.to(dev)
+            gcam = type(cam)(cam.image_width, cam.image_height, cam.tanfovx, cam.tanfovy, cam.viewmatrix.clone(),
+                             cam.projmatrix.clone(), cam.campos.clone())
+        gcam.viewmatrix.copy_(cam.viewmatrix)
+        gcam.projmatrix.copy_(cam.projmatrix)
+        gcam.campos.copy_(cam.campos)
+        key = (reducer._cur if reducer is not None else -1, bool(first) if reducer is not None else True)
+        if key not in graphs:
+            arm._lib.timing_enable(False)
+            fresh_state = (reducer._open, reducer._fresh) if reducer is not None else None
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                 # warm-up on a side stream, as torch.cuda.graph asks
+                for _ in range(2):
+                    if reducer is not None:
+                        reducer._open, reducer._fresh = fresh_state
+                    arm.step(gcam, bg, g)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            if reducer is not None:
+                reducer._open, reducer._fresh = fresh_state
+            gr = torch.cuda.CUDAGraph()
+            l0_ = int(arm.lib.pgs_launch_count())
+            with torch.cuda.graph(gr):
+                arm.step(gcam, bg, g)
+            graphs[key] = (gr, int(arm.lib.pgs_launch_count()) - l0_)   # kernels of this library inside the graph
+            gr.replay()                                                   # the capture itself executes nothing
+            arm.replayed_launches = getattr(arm, "replayed_launches", 0) + graphs[key][1]
+        else:
+            graphs[key][0].replay()
+            arm.replayed_launches = getattr(arm, "replayed_launches", 0) + graphs[key][1]
+        if reducer is not None:
+            reducer._fresh = False
+        return None, None
+
     def one_step(i):
         per = 1 if state["mode"] == "per_view" else accum
         first = state["in_batch"] == 0
         if first and reducer is not None:
             reducer.begin_batch()
-        loss, grads = arm.step(cam_of_step(i), bg, g)
+        if state.get("graph"):
+            loss, grads = graph_view(i, first)
+        else:
+            loss, grads = arm.step(cam_of_step(i), bg, g)
         if reducer is None and world > 1 and per > 1 and state["mode"] != "none":
             # reference arm: what train.py would do with a data-parallel batch — accumulate in torch
             if first:
@@ -540,6 +590,28 @@ def run(args):
     # EXACTLY K timed steps, timed twice; the faster pass is reported and both are listed in the JSON line (some boxes
     # of the pool have hosts that enqueue 10-50x slower than others and stumble in a pass).  Same rule for both arms.
     attempts = [timed_pass(), timed_pass()]
+    for a_ in attempts:
+        a_["mode"] = "eager launches"
+    stage_eager = min(attempts, key=lambda a_: a_["t_ms"])["stage"]
+    use_graph = arm.name == "ours" and block_model is None and not args.no_graph
+    if use_graph:
+        # the same K steps replayed as CUDA graphs (no host launches inside the step); the per-stage timings above come
+        # from the eager passes (the library's stage timers are host-recorded events)
+        state["graph"] = True
+        for i in range(2 * accum + 4 if world > 1 else 4):   # captures every (bucket, accumulate) variant, untimed
+            one_step(i)
+        drain()
+        torch.cuda.synchronize()
+        for _ in range(2):
+            a_ = timed_pass()
+            a_["mode"] = "CUDA-graph replay"
+            a_["stage"] = stage_eager
+            a_["busy_ms"] = min(x["busy_ms"] for x in attempts if x["mode"] == "eager launches")
+            attempts.append(a_)
+        from partgs_b200 import diff_surfel_rasterization as dsr_
+        n_, overflow_ = dsr_.resolve_count()
+        if overflow_:
+            raise SystemExit("a captured frame exceeded its instance capacity: graph numbers invalid")
     best = min(attempts, key=lambda a_: a_["t_ms"])
     t_ms, host_ms, stage = best["t_ms"], best["host_ms"], best["stage"]
     n_launch, n_malloc = best["launches"], best["mallocs"]
@@ -718,6 +790,8 @@ def run(args):
                    "collective": ("none" if world == 1 else
                                   f"one all-reduce of the 232 B/surfel parameter gradients per batch of {accum} views per rank"),
                    "views_timed": views_timed,
+                   "launch": ("CUDA-graph replay of forward + backward per view (eager passes listed under attempts)"
+                              if (arm.name == "ours" and block_model is None and not args.no_graph) else "eager kernel launches"),
                    "instance_count": ("lazy: the forward does not wait for it, every backward verifies it" if
                                       (arm.name == "ours" and block_model is None and not args.no_lazy) else "waited for in the forward call"),
                    "l2": "inputs (232 MB parameters + per-view state) exceed the 126 MB L2; views cycle every step",
@@ -738,7 +812,7 @@ def run(args):
         **({"collective_check": collective_check} if collective_check else {}),
         "host": {"enqueue_ms_per_step": round(host_ms, 4), "trivial_launch_us": round(launch_us, 2),
                  "sync_round_trip_us": round(sync_us, 1), "device_mallocs_in_timed_region": n_malloc},
-        "attempts": [{"ms_per_step": round(a_["t_ms"] / args.steps, 4), "kernel_ms_per_step": round(a_["busy_ms"] / args.steps, 4),
+        "attempts": [{"mode": a_.get("mode"), "ms_per_step": round(a_["t_ms"] / args.steps, 4), "kernel_ms_per_step": round(a_["busy_ms"] / args.steps, 4),
                       "host_enqueue_ms_per_step": round(a_["host_ms"], 4), "device_mallocs": a_["mallocs"]} for a_ in attempts],
         "clocks": clock_info,
         "frame_roofline": {"algorithmic_bytes": int(a_f + a_b), "achieved_gbs": round((a_f + a_b) / (t_ms / args.steps * 1e-3) / 1e9, 1),
@@ -843,6 +917,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--schedule", default="balanced", choices=["balanced", "roundrobin"],
                     help="N>1: which views share a lock-step (groups of similar cost proxy, or plain round-robin)")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="ours: do not replay the timed steps as CUDA graphs (eager launches only)")
     ap.add_argument("--no-lazy", action="store_true",
                     help="ours: wait for every frame's instance count inside the forward call (the round-1 behaviour)")
     ap.add_argument("--accum", type=int, default=0,

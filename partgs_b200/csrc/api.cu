@@ -590,6 +590,8 @@ int pgs_dsr_resolve_count(int* overflow) {
     // nothing pending: a captured frame replayed by the caller (who synchronised the stream): report its slot
     const int n = cf->host[cf->last];
     if (overflow && (n < 0 || (size_t)n > cf->cap[cf->last])) *overflow = 1;
+    for (int i = 0; i < CountFetch::SLOTS; i++)   // every captured graph's latest replay
+      if (overflow && cf->captured[i] && (cf->host[i] < 0 || (size_t)cf->host[i] > cf->cap[i])) *overflow = 1;
     return n;
   }
   return last_count;
