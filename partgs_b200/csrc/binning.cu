@@ -179,7 +179,10 @@ constexpr int RS_BITS = 8;
 constexpr int RS_RADIX = 1 << RS_BITS;
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 12;
+#ifndef PGS_RS_ITEMS
+#define PGS_RS_ITEMS 12
+#endif
+constexpr int RS_ITEMS = PGS_RS_ITEMS;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 3072 pairs / CTA
 constexpr int RS_MAX_PASSES = PGS_RS_MAX_PASSES;
 constexpr int RS_MAX_PASSES_TILE = 4;  // tile ids: at most 32 bits

@@ -70,7 +70,7 @@ def other(a):
             losses.photometric_loss(img, gt, 0.2).backward()
             allmap.grad = None
             maps = renderer.surface_maps(allmap, cams[0], 0.0)
-            sum(m_.sum() for m_ in maps).backward()
+            sum(m_.sum() for m_ in maps.values()).backward()
             for p_ in prm:
                 p_.grad = torch.ones_like(p_)
             opt.step()
