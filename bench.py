@@ -447,8 +447,13 @@ def run(args):
             loss, grads = graph_view(i, first)
         else:
             loss, grads = arm.step(cam_of_step(i), bg, g)
+        after_step(grads, per, first)
+        return loss, grads
+
+    def after_step(grads, per, first, force_close=False):
+        """Batch bookkeeping after a view: the arm without a bucket accumulates in torch; the batch closes after `per` views."""
         if reducer is None and world > 1 and per > 1 and state["mode"] != "none":
-            # reference arm: what train.py would do with a data-parallel batch — accumulate in torch
+            # what train.py would do with a data-parallel batch — accumulate in torch
             if first:
                 for h in ref_pending:
                     h.wait()
@@ -460,9 +465,8 @@ def run(args):
             else:
                 torch._foreach_add_(ref_acc, list(grads))
         state["in_batch"] += 1
-        if state["in_batch"] >= per:
+        if state["in_batch"] >= per or force_close:
             close_batch(ref_acc if (reducer is None and per > 1 and ref_acc) else grads)
-        return loss, grads
 
     def drain():
         if state["in_batch"] > 0 and reducer is not None and not reducer._fresh and state["mode"] != "none" and world > 1:
@@ -685,11 +689,23 @@ def run(args):
     p_ready = [torch.cuda.Event(), torch.cuda.Event()]
     p_consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
+    # N > 1: the parameters are replicated, so pushing N copies of them through the host's PCIe root is the wrong plan on
+    # an NVSwitch box: every rank uploads 1/N of every parameter tensor from pinned host memory and the ranks all-gather
+    # the rest over NVLink (in place, on the copy stream).  Same harness for both arms.
+    shard_upload = world > 1 and all(v.numel() % world == 0 for v in host.values())
+
     def upload_params(pb):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(p_consumed[pb])
             for k, v in host.items():
-                slots[pb][k].copy_(v, non_blocking=True)
+                if shard_upload:
+                    dst, src = slots[pb][k].view(-1), v.view(-1)
+                    n_ = dst.numel() // world
+                    mine_ = dst[rank * n_:(rank + 1) * n_]
+                    mine_.copy_(src[rank * n_:(rank + 1) * n_], non_blocking=True)
+                    dist.all_gather_into_tensor(dst, mine_)
+                else:
+                    slots[pb][k].copy_(v, non_blocking=True)
             p_ready[pb].record(copy_stream)
 
     def upload_view(slot):
@@ -727,14 +743,14 @@ def run(args):
             if arm.name == "ours":
                 prm = {k: v.detach().requires_grad_(True) for k, v in prm.items()}
             gg = dict(g, color=g_slots[s_]) if per_view else g
-            if state["in_batch"] == 0 and reducer is not None:
+            first = state["in_batch"] == 0
+            if first and reducer is not None:
                 reducer.begin_batch()
             loss, grads = arm.step(cam, bg, gg, params=prm, want_loss=True)
-            state["in_batch"] += 1
-            last_of_batch = (i + 1) % params_every == 0 or i + 1 == n
-            if last_of_batch:                          # gradients are reduced once per upload of the parameters
-                close_batch(grads)
-                p_consumed[b_].record(cur)
+            # the metric's data-parallel batch: one all-reduce per `accum` views, as in the device-timed value
+            after_step(grads, accum, first, force_close=(i + 1 == n))
+            if (i + 1) % params_every == 0 or i + 1 == n:
+                p_consumed[b_].record(cur)             # this upload of the parameters has been used for the last time
             loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
             if per_view:
                 consumed[s_].record(cur)
@@ -760,6 +776,8 @@ def run(args):
     e2e_batch_value = time_e2e(batch_k)
     view_bytes = g_host.numel() * 4 + 2 * 64 + 12
     param_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    rank_param_bytes = param_bytes // world if shard_upload else param_bytes     # what ONE rank copies from the host
+    h2d_bytes = rank_param_bytes + 2 * 64 + 12
 
     if rank != 0:
         return
@@ -796,12 +814,15 @@ def run(args):
                                       (arm.name == "ours" and block_model is None and not args.no_lazy) else "waited for in the forward call"),
                    "l2": "inputs (232 MB parameters + per-view state) exceed the 126 MB L2; views cycle every step",
                    "V_visible": V, "R_instances": int(R)},
+        # h2d_bytes_per_step: per rank (a step of the job is one view on every rank: x n_gpus for the job's total)
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
-                "d2h_bytes_per_step": 4},
+                "d2h_bytes_per_step": 4,
+                **({"parameter_upload": f"each rank uploads 1/{world} of every parameter tensor from pinned host memory, "
+                                        "all-gather over NVLink (in place)"} if shard_upload else {})},
         # additional, NOT the declared e2e: parameters uploaded once per optimiser batch (they only change at the
         # optimiser step), every view uploads its camera and an image-sized loss input
         "e2e_batch_upload": {"value": round(e2e_batch_value, 3), "unit": UNIT, "views_per_parameter_upload": batch_k,
-                             "h2d_bytes_per_step": int(view_bytes + param_bytes / batch_k), "d2h_bytes_per_step": 4},
+                             "h2d_bytes_per_step": int(view_bytes + rank_param_bytes / batch_k), "d2h_bytes_per_step": 4},
         "gpu_launches": int(n_launch),
         **({"collective_impl": (("fused reduce-scatter + all-gather kernel over NVLink peer memory (csrc/collective.cu)"
                                  if args.collective == "peer" else "NCCL all-reduce of the bucket") +
