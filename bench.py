@@ -363,12 +363,16 @@ def run(args):
     # ---- data-parallel batch: accum views per rank and batch, one all-reduce per batch ----------
     accum = args.accum if args.accum > 0 else (len(all_cams) + world - 1) // world
     reducer = None
-    if world > 1 and arm.name == "ours" and block_model is None:
+    if world > 1 and arm.name == "ours":
         # the backward kernel accumulates the batch in ONE bucket (232 B/surfel) that lives in peer-mapped memory and
         # is reduced by one kernel over NVLink (partgs_b200.dist.PeerGradAllReducer), or by one NCCL all-reduce
         from partgs_b200.dist import NcclBucketAllReducer, PeerGradAllReducer
         from partgs_b200 import diff_surfel_rasterization as dsr
-        numel = dsr.bucket_numel(P, 16)
+        if block_model is None:
+            numel = dsr.bucket_numel(P, 16)
+        else:
+            from partgs_b200.superquadric import blocks_bucket_numel
+            numel = blocks_bucket_numel(P, 8, 16)
         reducer = PeerGradAllReducer(numel, dev) if args.collective == "peer" else NcclBucketAllReducer(numel, dev)
         dsr.set_grad_bucket_provider(reducer.bucket_provider)
     ref_acc, ref_pending = [], []   # reference arm: gradients accumulated with torch adds, NCCL all-reduce per batch

@@ -617,8 +617,10 @@ static int backward_impl(const SqArgs* sq, const float* sq_vertices, bool part, 
   // PGS_BWD_ACCUMULATE (add the five parameter gradients to the arrays instead of overwriting them)
   const int debug = flags & 1;
   const int accumulate = (flags & PGS_BWD_ACCUMULATE) ? 1 : 0;
-  if (accumulate && (part || sq))
-    return set_error(PGS_ERR_UNSUPPORTED, "gradient accumulation is implemented for the point-level base fork only");
+  if (accumulate && part)
+    return set_error(PGS_ERR_UNSUPPORTED, "gradient accumulation is not implemented for the _part fork");
+  // (block-level mode: only dL_dsh accumulates in the kernel — the per-surfel geometry gradients are scratch of the
+  //  superquadric backward; the caller adds the five small block gradients itself)
   if (part) {
     if (S < 0 || S > MAX_SEMANTIC)
       return set_error(PGS_ERR_UNSUPPORTED, "semantic channels must be in [0, %d] (got %d)", MAX_SEMANTIC, S);

@@ -218,15 +218,18 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
   // Accumulate mode (a data-parallel batch: a rank renders several views and all-reduces ONE gradient bucket): the
   // five parameter gradients (mean3D, SH, opacity, scales, rotations) are added to what the earlier views of the
   // batch left in place; the per-view outputs (mean2D, colours, transMat) are still overwritten.
-  const bool acc = a.accumulate != 0;
+  // Block-level mode: only the SH rows are parameters (and accumulate); mean3D / scales / rotations / opacity are
+  // per-view scratch that the face -> vertex -> block reduction consumes right after this kernel: always overwritten.
+  const bool acc_sh = a.accumulate != 0;
+  const bool acc = acc_sh && !SQ;
   if (!visible) {
     o_m2d[0] = o_m2d[1] = o_m2d[2] = 0.f;
     o_col[0] = o_col[1] = o_col[2] = 0.f;
     for (int i = 0; i < 9; i++) o_T[i] = 0.f;
+    if (o_sh && !acc_sh) zero_sh_row(o_sh, M);
     if (acc) return;   // nothing to add
     a.dL_dopacity[idx] = 0.f;
     o_m3d[0] = o_m3d[1] = o_m3d[2] = 0.f;
-    if (o_sh) zero_sh_row(o_sh, M);
     if (a.dL_dscales) { a.dL_dscales[idx * 2] = 0.f; a.dL_dscales[idx * 2 + 1] = 0.f; }
     if (a.dL_drots) { for (int i = 0; i < 4; i++) a.dL_drots[idx * 4 + i] = 0.f; }
     return;
@@ -365,8 +368,8 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
   // SH backward (backward.cu:20-139), incl. view-direction -> mean3D path
   if (a.shs) {
     dmean += sh_backward<SQ>(idx, a.D, M, (const v3*)a.means3D, *(const v3*)a.cam_pos, a.shs, __float_as_uint(q4.w),
-                             dL_dcolor, (v3*)o_sh, v3(p_orig.x, p_orig.y, p_orig.z), acc);
-  } else if (o_sh && !acc) {
+                             dL_dcolor, (v3*)o_sh, v3(p_orig.x, p_orig.y, p_orig.z), acc_sh);
+  } else if (o_sh && !acc_sh) {
     for (int i = 0; i < M * 3; i++) o_sh[i] = 0.f;
   }
 

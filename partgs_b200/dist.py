@@ -318,7 +318,8 @@ def sharded_step(render_loss: Callable[[int], torch.Tensor], params: Dict[str, t
         bucketed_here = 1 if not mine else int(grad_bucket([params[k].grad for k in present]) is not None)
         flag = torch.tensor([bucketed_here], dtype=torch.int32, device=ref.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=getattr(reducer, "group", None))
-        if not mine and int(flag.item()) == 1 and set(present) == set(order):
+        point_level = tuple(order) == ("means3D", "shs", "opacities", "scales", "rotations")
+        if not mine and int(flag.item()) == 1 and set(present) == set(order) and point_level:
             from . import diff_surfel_rasterization as dsr
             P, M = params["means3D"].shape[0], params["shs"].shape[1]
             for k, z in zip(order, dsr.zero_bucket_grads(P, M, ref.device)):

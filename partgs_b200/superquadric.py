@@ -276,11 +276,22 @@ class _RasterizeBlocks(torch.autograd.Function):
         g_color = _lib.require_cuda_float(g_color if g_color is not None else torch.zeros((3, H, W), **f32), "g")
         g_others = _lib.require_cuda_float(g_others if g_others is not None else torch.zeros((7, H, W), **f32), "g")
         need = ctx.needs_input_grad
-        d_r, d_s, d_t = torch.empty((B, 4), **f32), torch.empty((B, 3), **f32), torch.empty((B, 3), **f32)
-        d_e, d_o = torch.empty((B, 2), **f32), torch.empty((B,), **f32)
+        # The parameter gradients of the block-level model — per-surfel SH rows and the five block parameters — are
+        # carved out of ONE flat buffer like the point-level rasteriser's (diff_surfel_rasterization._carve_bucket): a
+        # data-parallel caller hands out its batch bucket there and reduces it with one collective.  In accumulate mode
+        # (second and later views of a batch) the SH rows are added inside the backward kernel; the block gradients
+        # (13 floats per block) are produced into temporaries and added here.
+        from . import diff_surfel_rasterization as _dsr
+        (b_sh, b_r, b_s, b_t, b_e, b_o), accumulate = _dsr._carve_bucket(
+            dev, [(P, M, 3), (B, 4), (B, 3), (B, 3), (B, 2), (B,)], with_flag=True)
+        d_sh = b_sh
+        if accumulate:
+            d_r, d_s, d_t = torch.empty((B, 4), **f32), torch.empty((B, 3), **f32), torch.empty((B, 3), **f32)
+            d_e, d_o = torch.empty((B, 2), **f32), torch.empty((B,), **f32)
+        else:
+            d_r, d_s, d_t, d_e, d_o = b_r, b_s, b_t, b_e, b_o
         d_alpha = torch.empty((B * F, K, 3), **f32) if need[5] else None
         d_scale = torch.empty((B, F * K), **f32) if need[6] else None
-        d_sh = torch.empty((P, M, 3), **f32)
         d_m2d = torch.empty((P, 3), **f32)
         d_col = torch.empty((P, 3), **f32)
         scratch = torch.empty(lib.pgs_dsr_backward_blocks_scratch_bytes(B, Vt, F, K), dtype=torch.uint8, device=dev)
@@ -293,14 +304,22 @@ class _RasterizeBlocks(torch.autograd.Function):
                 float(rs.tanfovx), float(rs.tanfovy), radii.data_ptr(), _lib.ptr(geom), _lib.ptr(binning),
                 int(binning.numel()), _lib.ptr(img), g_color.data_ptr(), g_others.data_ptr(), d_m2d.data_ptr(),
                 scratch.data_ptr(), d_col.data_ptr(), d_sh.data_ptr(), d_r.data_ptr(), d_s.data_ptr(), d_t.data_ptr(),
-                d_e.data_ptr(), d_o.data_ptr(), _lib.ptr(d_alpha), _lib.ptr(d_scale), int(bool(rs.debug)),
-                _lib.current_stream(dev))
+                d_e.data_ptr(), d_o.data_ptr(), _lib.ptr(d_alpha), _lib.ptr(d_scale),
+                int(bool(rs.debug)) | (2 if accumulate else 0), _lib.current_stream(dev))
         _lib.check(rc, "pgs_dsr_backward_blocks")
+        if accumulate:
+            torch._foreach_add_([b_r, b_s, b_t, b_e, b_o], [d_r, d_s, d_t, d_e, d_o])
+            d_r, d_s, d_t, d_e, d_o = b_r, b_s, b_t, b_e, b_o
         occ_shape, alpha_shape, scale_shape = ctx.shapes
         return (d_r, d_s, d_t, d_e, d_o.reshape(occ_shape),
                 d_alpha.reshape(alpha_shape) if d_alpha is not None else None,
                 d_scale.reshape(scale_shape) if d_scale is not None else None,
                 d_sh if need[7] else None, d_m2d if need[8] else None, None, None, None, None, None, None, None)
+
+
+def blocks_bucket_numel(P: int, B: int, M: int = 16, align_elems: int = 64) -> int:
+    """Floats of the gradient bucket of a block-level model (layout of _RasterizeBlocks.backward)."""
+    return sum((n + align_elems - 1) // align_elems * align_elems for n in (P * M * 3, B * 4, B * 3, B * 3, B * 2, B))
 
 
 def rasterize_blocks(raster_settings, sq_r, sq_s, sq_t, sq_eps, sq_occ, alpha, scale_raw, shs, eta, omega, faces,
