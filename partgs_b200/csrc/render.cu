@@ -365,14 +365,13 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 4) render_fwd_kernel(Rend
       // before they are blended in order.  The deepest tiles (thousands of fragments on the same
       // pixels, one warp alone on its scheduler at the end of the launch) are bound by the latency
       // of this chain, not by issue slots.
-      for (int j = 0; j < n_c; j += FWD_ILP) {
+      const int n_even = n_c & ~(FWD_ILP - 1);
+      for (int j = 0; j < n_even; j += FWD_ILP) {
         float alpha[FWD_ILP], depth[FWD_ILP];
         bool ok[FWD_ILP];
 #pragma unroll
-        for (int u = 0; u < FWD_ILP; u++) {
-          const int ju = min(j + u, CHUNK - 1);
-          ok[u] = frag_eval<PART>(pixf, st.rec[ju][0], st.rec[ju][1], st.rec[ju][2], alpha[u], depth[u]) && (j + u < n_c);
-        }
+        for (int u = 0; u < FWD_ILP; u++)
+          ok[u] = frag_eval<PART>(pixf, st.rec[j + u][0], st.rec[j + u][1], st.rec[j + u][2], alpha[u], depth[u]);
 #pragma unroll
         for (int u = 0; u < FWD_ILP; u++) {
           bool b = false;
@@ -380,6 +379,16 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 4) render_fwd_kernel(Rend
           const unsigned m = __ballot_sync(RFULL, b);
           if ((int)lane == j + u) my_mask = m;
         }
+      }
+      // an odd survivor count: the last one alone (half of all steps: evaluating a stale second slot there used to
+      // cost 4 % of the kernel's instructions)
+      for (int j = n_even; j < n_c; j++) {
+        float alpha, depth;
+        const bool ok = frag_eval<PART>(pixf, st.rec[j][0], st.rec[j][1], st.rec[j][2], alpha, depth);
+        bool b = false;
+        if (ok && !done) b = blend(j, alpha, depth);
+        const unsigned m = __ballot_sync(RFULL, b);
+        if ((int)lane == j) my_mask = m;
       }
     }
     // what backward needs to know about this step: per candidate, the pixels that blended it
