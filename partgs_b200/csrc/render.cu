@@ -46,7 +46,10 @@ namespace pgs {
 
 // Fragments evaluated ahead of the in-order blend.  Measured on C3: 2 -> 1.11 ms, 4 -> 1.14-1.23 ms, 8 -> 1.37-1.43 ms
 // (a deeper look-ahead evaluates up to ILP-1 slots past the end of every step and costs registers).
-constexpr int FWD_ILP = 2;
+#ifndef PGS_FWD_ILP
+#define PGS_FWD_ILP 2
+#endif
+constexpr int FWD_ILP = PGS_FWD_ILP;
 
 struct __align__(16) WarpStage {
   float4 rec[CHUNK][REC_QUADS];  // 32 x 80 B
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(TILE_PIX, PART ? 2 : 4) render_fwd_kernel(Rend
       // before they are blended in order.  The deepest tiles (thousands of fragments on the same
       // pixels, one warp alone on its scheduler at the end of the launch) are bound by the latency
       // of this chain, not by issue slots.
-      const int n_even = n_c & ~(FWD_ILP - 1);
+      const int n_even = n_c - n_c % FWD_ILP;
       for (int j = 0; j < n_even; j += FWD_ILP) {
         float alpha[FWD_ILP], depth[FWD_ILP];
         bool ok[FWD_ILP];
