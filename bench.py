@@ -373,7 +373,9 @@ def run(args):
         else:
             from partgs_b200.superquadric import blocks_bucket_numel
             numel = blocks_bucket_numel(P, 8, 16)
-        reducer = PeerGradAllReducer(numel, dev) if args.collective == "peer" else NcclBucketAllReducer(numel, dev)
+        lanes_ = 1 if (args.no_overlap or args.no_graph or block_model is not None) else 2
+        reducer = (PeerGradAllReducer(numel, dev, n_lanes=lanes_) if args.collective == "peer"
+                   else NcclBucketAllReducer(numel, dev, n_lanes=lanes_))
         dsr.set_grad_bucket_provider(reducer.bucket_provider)
     ref_acc, ref_pending = [], []   # reference arm: gradients accumulated with torch adds, NCCL all-reduce per batch
 
@@ -388,7 +390,7 @@ def run(args):
             return
         if reducer is not None:
             reducer.wait()                     # the previous batch's collective (launched a whole batch ago)
-            reducer.launch(grads)
+            reducer.launch(grads, streams=lane_streams if state.get("graph") else None)
             return
         for h in ref_pending:
             h.wait()
@@ -397,59 +399,91 @@ def run(args):
             ref_pending.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
 
     # ---- CUDA-graph replay of a step (ours, point-level): forward + backward of one view captured once per variant
-    # (which bucket, overwrite or accumulate), the view's camera copied into three small static tensors before each
-    # replay.  The forward inside a capture never waits for the instance count (PGS_FWD_LAZY_COUNT); the counts of
-    # the captured variants are checked after the timed region.
+    # (which lane, which bucket, overwrite or accumulate), the view's camera copied into three small static tensors
+    # before each replay.  Consecutive views are independent (the parameters are fixed over a batch), so they are
+    # replayed on TWO alternating streams ("lanes"): view k+1's preprocess + binning chain (latency-bound, 0.3 ms of a
+    # mostly idle GPU) then runs beside view k's render kernels.  Each lane accumulates in a buffer of its own
+    # (dist.BucketBatch lanes), folded into the batch's bucket before the collective.  The forward inside a capture
+    # never waits for the instance count (PGS_FWD_LAZY_COUNT); the counts of the captured variants are checked after
+    # the timed region.
     graphs = {}
-    gcam = None
+    n_lanes = 1 if args.no_overlap else 2
+    lane_streams = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)]
+    gcams = [None] * n_lanes
+    lane_ctr = {"i": 0}
 
-    def graph_view(i, first):
-        nonlocal gcam
+    def lanes_fork():
+        cur = torch.cuda.current_stream(dev)
+        for s_ in lane_streams:
+            s_.wait_stream(cur)
+
+    def lanes_join():
+        cur = torch.cuda.current_stream(dev)
+        for s_ in lane_streams:
+            cur.wait_stream(s_)
+
+    def graph_view(i, lane, first_in_lane):
         cam = cam_of_step(i)
-        if gcam is None:
-            gcam = cam.to(dev)
-            gcam = type(cam)(cam.image_width, cam.image_height, cam.tanfovx, cam.tanfovy, cam.viewmatrix.clone(),
-                             cam.projmatrix.clone(), cam.campos.clone())
-        gcam.viewmatrix.copy_(cam.viewmatrix)
-        gcam.projmatrix.copy_(cam.projmatrix)
-        gcam.campos.copy_(cam.campos)
-        key = (reducer._cur if reducer is not None else -1, bool(first) if reducer is not None else True)
+        if gcams[lane] is None:
+            gcams[lane] = type(cam)(cam.image_width, cam.image_height, cam.tanfovx, cam.tanfovy, cam.viewmatrix.clone(),
+                                    cam.projmatrix.clone(), cam.campos.clone())
+        gcam = gcams[lane]
+        key = (lane, reducer._cur if reducer is not None else -1, bool(first_in_lane) if reducer is not None else True)
         if key not in graphs:
+            lanes_join()
+            torch.cuda.synchronize()
             arm._lib.timing_enable(False)
-            fresh_state = (reducer._open, reducer._fresh) if reducer is not None else None
+            saved = (reducer._open, list(reducer._fresh_lane)) if reducer is not None else None
+
+            def restore():
+                if reducer is not None:
+                    reducer._open, reducer._fresh_lane = saved[0], list(saved[1])
+                    reducer.set_lane(lane)
+
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):                 # warm-up on a side stream, as torch.cuda.graph asks
                 for _ in range(2):
-                    if reducer is not None:
-                        reducer._open, reducer._fresh = fresh_state
+                    restore()
                     arm.step(gcam, bg, g)
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize()
-            if reducer is not None:
-                reducer._open, reducer._fresh = fresh_state
+            restore()
             gr = torch.cuda.CUDAGraph()
             l0_ = int(arm.lib.pgs_launch_count())
             with torch.cuda.graph(gr):
                 arm.step(gcam, bg, g)
             graphs[key] = (gr, int(arm.lib.pgs_launch_count()) - l0_)   # kernels of this library inside the graph
-            gr.replay()                                                   # the capture itself executes nothing
-            arm.replayed_launches = getattr(arm, "replayed_launches", 0) + graphs[key][1]
-        else:
+            restore()
+            lanes_fork()
+        with torch.cuda.stream(lane_streams[lane]):
+            gcam.viewmatrix.copy_(cam.viewmatrix, non_blocking=True)
+            gcam.projmatrix.copy_(cam.projmatrix, non_blocking=True)
+            gcam.campos.copy_(cam.campos, non_blocking=True)
             graphs[key][0].replay()
-            arm.replayed_launches = getattr(arm, "replayed_launches", 0) + graphs[key][1]
+        arm.replayed_launches = getattr(arm, "replayed_launches", 0) + graphs[key][1]
         if reducer is not None:
-            reducer._fresh = False
+            reducer._fresh_lane[lane] = False
         return None, None
 
     def one_step(i):
         per = 1 if state["mode"] == "per_view" else accum
         first = state["in_batch"] == 0
-        if first and reducer is not None:
-            reducer.begin_batch()
         if state.get("graph"):
-            loss, grads = graph_view(i, first)
+            if reducer is not None:
+                lane = state["in_batch"] % n_lanes
+                if first:
+                    reducer.begin_batch(streams=lane_streams)
+                reducer.set_lane(lane)
+                loss, grads = graph_view(i, lane, state["in_batch"] < n_lanes)
+            else:
+                lane = lane_ctr["i"] % n_lanes
+                lane_ctr["i"] += 1
+                loss, grads = graph_view(i, lane, True)
         else:
+            if first and reducer is not None:
+                reducer.begin_batch()
+                reducer.set_lane(0)
             loss, grads = arm.step(cam_of_step(i), bg, g)
         after_step(grads, per, first)
         return loss, grads
@@ -572,12 +606,16 @@ def run(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        if state.get("graph"):
+            lanes_fork()
         host_t0 = time.perf_counter()
         for i in range(args.steps):
             one_step(i)
             if rank == 0 and (i & 7) == 3:
                 clocks.sample_now()   # ~20 us of host time, GPU queue stays full
         drain()
+        if state.get("graph"):
+            lanes_join()
         host_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps   # host time to ENQUEUE one step (incl. waits)
         e1.record()
         barrier()
@@ -606,9 +644,11 @@ def run(args):
         # the same K steps replayed as CUDA graphs (no host launches inside the step); the per-stage timings above come
         # from the eager passes (the library's stage timers are host-recorded events)
         state["graph"] = True
-        for i in range(2 * accum + 4 if world > 1 else 4):   # captures every (bucket, accumulate) variant, untimed
+        lanes_fork()
+        for i in range(2 * accum + 4 if world > 1 else 4):   # captures every (lane, bucket, accumulate) variant, untimed
             one_step(i)
         drain()
+        lanes_join()
         torch.cuda.synchronize()
         for _ in range(2):
             a_ = timed_pass()
@@ -631,9 +671,13 @@ def run(args):
         modes = {"per_batch": round(world * args.steps / (t_ms / 1e3), 3)}
         for m_ in ("per_view", "none"):
             state["mode"] = m_
+            if state.get("graph"):
+                lanes_fork()
             for i in range(3):
                 one_step(i)
             drain()
+            if state.get("graph"):
+                lanes_join()
             torch.cuda.synchronize()
             r_ = timed_pass()
             modes[m_] = round(world * args.steps / (r_["t_ms"] / 1e3), 3)
@@ -642,6 +686,29 @@ def run(args):
     # ---- collective check (N > 1, ours): one batch's bucket reduced by the product collective must equal, bit for bit,
     # the rank-ordered sum ((g0 + g1) + g2) + ... of the W buckets gathered with NCCL; NCCL's own all-reduce of the
     # same data is compared as well (its summation order differs for W > 2) -----------------------------------------
+    # ---- the replayed, two-lane batch must produce the gradients of the eager, single-stream batch (N > 1, ours) ----
+    graph_batch_check = None
+    if world > 1 and reducer is not None and use_graph:
+        def one_batch(as_graph):
+            drain()
+            state["graph"], state["mode"], state["in_batch"] = as_graph, "per_batch", 0
+            if as_graph:
+                lanes_fork()
+            for i in range(accum):
+                one_step(i)                       # the last view closes the batch: one all-reduce
+            reducer.wait()
+            if as_graph:
+                lanes_join()
+            torch.cuda.synchronize()
+            return reducer.current().clone()
+        b_graph, b_eager = one_batch(True), one_batch(False)
+        scale_ = float(b_eager.abs().max())
+        graph_batch_check = {"views_per_batch": accum, "max_rel_diff_vs_eager_batch":
+                             float((b_graph - b_eager).abs().max()) / (scale_ + 1e-30), "nonzero": bool(scale_ > 0)}
+        del b_graph, b_eager
+    state["graph"] = False          # everything below launches eagerly on the current stream
+    if reducer is not None:
+        reducer.set_lane(0)
     collective_check = None
     if world > 1 and reducer is not None:
         drain()
@@ -812,7 +879,7 @@ def run(args):
                    "collective": ("none" if world == 1 else
                                   f"one all-reduce of the 232 B/surfel parameter gradients per batch of {accum} views per rank"),
                    "views_timed": views_timed,
-                   "launch": ("CUDA-graph replay of forward + backward per view (eager passes listed under attempts)"
+                   "launch": ("CUDA-graph replay of forward + backward per view" + ("" if args.no_overlap else ", consecutive views on two alternating streams") + " (eager passes listed under attempts)"
                               if (arm.name == "ours" and block_model is None and not args.no_graph) else "eager kernel launches"),
                    "instance_count": ("lazy: the forward does not wait for it, every backward verifies it" if
                                       (arm.name == "ours" and block_model is None and not args.no_lazy) else "waited for in the forward call"),
@@ -835,6 +902,7 @@ def run(args):
         **({"collective_modes": dict(modes, unit=UNIT, note="same K steps: all-reduce per batch (the headline), after every "
                                      "view, and not at all")} if modes else {}),
         **({"collective_check": collective_check} if collective_check else {}),
+        **({"graph_batch_check": graph_batch_check} if graph_batch_check else {}),
         "host": {"enqueue_ms_per_step": round(host_ms, 4), "trivial_launch_us": round(launch_us, 2),
                  "sync_round_trip_us": round(sync_us, 1), "device_mallocs_in_timed_region": n_malloc},
         "attempts": [{"mode": a_.get("mode"), "ms_per_step": round(a_["t_ms"] / args.steps, 4), "kernel_ms_per_step": round(a_["busy_ms"] / args.steps, 4),
@@ -942,6 +1010,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--schedule", default="balanced", choices=["balanced", "roundrobin"],
                     help="N>1: which views share a lock-step (groups of similar cost proxy, or plain round-robin)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="ours: replay the graphs on one stream (no overlap of consecutive views)")
     ap.add_argument("--no-graph", action="store_true",
                     help="ours: do not replay the timed steps as CUDA graphs (eager launches only)")
     ap.add_argument("--no-lazy", action="store_true",

@@ -75,8 +75,8 @@ int pgs_dsr_forward(pgs_alloc_fn geometry_buffer, void* geometry_user, pgs_alloc
  * pgs_dsr_resolve_count() waits for the counts of all lazy frames of this host thread on the current device (or, with
  * none pending, reports the slot a replayed graph refreshed — synchronise the stream first) and returns the latest;
  * *overflow = 1 if a frame needed more instances than it was queued for: its outputs are invalid (its kernels did
- * nothing) and it must be rendered again — the remembered capacity has been raised.  At most 8 lazy frames may be
- * outstanding. */
+ * nothing) and it must be rendered again — the remembered capacity has been raised.  At most 32 count slots exist:
+ * outstanding lazy frames plus captured graphs (a captured forward keeps its slot). */
 #define PGS_FWD_LAZY_COUNT 2
 #define PGS_COUNT_PENDING 0x7fffffff
 int pgs_dsr_resolve_count(int* overflow);

@@ -75,9 +75,9 @@ struct StageTimer {
 
 // pinned host word + event through which forward reads the instance count of the frame in flight
 struct CountFetch {
-  // a small ring of pinned words: a lazy forward (PGS_FWD_LAZY_COUNT) leaves its count in the next slot and returns
+  // a ring of pinned words: a lazy forward (PGS_FWD_LAZY_COUNT) leaves its count in the next slot and returns
   // without waiting; pgs_dsr_resolve_count() later checks every slot still pending
-  static constexpr int SLOTS = 8;
+  static constexpr int SLOTS = 32;
   int* host = nullptr;            // [SLOTS] pinned
   cudaEvent_t ev[SLOTS] = {};
   size_t cap[SLOTS] = {};         // capacity the frame was launched with
@@ -86,7 +86,7 @@ struct CountFetch {
   int next = 0, last = 0;
   bool init() {
     if (host) return true;
-    if (cudaHostAlloc((void**)&host, 64, cudaHostAllocDefault) != cudaSuccess) { host = nullptr; return false; }
+    if (cudaHostAlloc((void**)&host, SLOTS * sizeof(int), cudaHostAllocDefault) != cudaSuccess) { host = nullptr; return false; }
     for (int i = 0; i < SLOTS; i++) {
       host[i] = 0;
       if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return false;

@@ -141,22 +141,45 @@ class BucketBatch:
     to itself.  `launch()` reduces the batch's buffer and closes the batch; a backward without an open batch opens
     one implicitly (one view per batch, the per-view mode)."""
 
-    def __init__(self, numel: int, device, n_buckets: int = 2):
+    def __init__(self, numel: int, device, n_buckets: int = 2, n_lanes: int = 1):
         self.device = torch.device(device)
         self.numel = int(numel)
+        self.n_lanes = max(int(n_lanes), 1)
         self._alloc(n_buckets)
+        # Lanes: the views of a batch may be rendered on several CUDA streams at once (view k+1's latency-bound
+        # binning chain then hides behind view k's render kernels).  Two backward passes must not read-modify-write
+        # one buffer concurrently, so every lane beyond the first accumulates in a private (local) buffer that
+        # `launch()` adds to the batch's bucket before the collective.  `set_lane()` selects the lane of the next
+        # backward passes.
+        self.side = [[torch.empty(self.numel, dtype=torch.float32, device=self.device) for _ in range(self.n_lanes - 1)]
+                     for _ in range(len(self.buckets))]
+        self._lane = 0
         self._cur = len(self.buckets) - 1
         self._open = False
-        self._fresh = True
+        self._fresh_lane = [True] * self.n_lanes
         self.done = [None] * len(self.buckets)   # CUDA event per buffer: its last collective has finished
+
+    @property
+    def _fresh(self):      # no backward pass has written anything for this batch yet
+        return all(self._fresh_lane)
+
+    @_fresh.setter
+    def _fresh(self, v):
+        self._fresh_lane = [bool(v)] * self.n_lanes
 
     def _alloc(self, n_buckets):
         self.buckets = [torch.empty(self.numel, dtype=torch.float32, device=self.device) for _ in range(n_buckets)]
 
-    def begin_batch(self):
+    def set_lane(self, lane: int):
+        self._lane = int(lane) % self.n_lanes
+
+    def begin_batch(self, streams=None):
+        """`streams`: the lanes' streams — all of them must wait until the buffer's previous collective has finished
+        (default: the current stream)."""
         self._cur = (self._cur + 1) % len(self.buckets)
         if self.done[self._cur] is not None and self.device.type == "cuda":
-            torch.cuda.current_stream(self.device).wait_event(self.done[self._cur])
+            for s in (streams or [torch.cuda.current_stream(self.device)]):
+                s.wait_event(self.done[self._cur])
         self._open, self._fresh = True, True
 
     def bucket_provider(self, n: int, device):
@@ -164,18 +187,34 @@ class BucketBatch:
             return None
         if not self._open:
             self.begin_batch()
-        accumulate, self._fresh = not self._fresh, False
-        return self.buckets[self._cur][:n], accumulate
+        lane = self._lane
+        accumulate, self._fresh_lane[lane] = not self._fresh_lane[lane], False
+        buf = self.buckets[self._cur] if lane == 0 else self.side[self._cur][lane - 1]
+        return buf[:n], accumulate
 
     def current(self) -> torch.Tensor:
         return self.buckets[self._cur]
+
+    def _merge_lanes(self):
+        """Fold the private buffers of lanes 1.. into the batch's bucket (call on the stream that runs the collective,
+        after it waits for every lane)."""
+        main = self.buckets[self._cur]
+        for lane in range(1, self.n_lanes):
+            if self._fresh_lane[lane]:
+                continue
+            if self._fresh_lane[0]:
+                main.copy_(self.side[self._cur][lane - 1])
+                self._fresh_lane[0] = False
+            else:
+                main.add_(self.side[self._cur][lane - 1])
 
     def _check(self, tensors):
         """The gradients handed to launch() must be views of the open batch's buffer."""
         tensors = [t for t in (tensors or []) if t is not None]
         if tensors:
             bucket = grad_bucket(tensors)
-            if bucket is None or bucket.untyped_storage().data_ptr() != self.current().untyped_storage().data_ptr():
+            mine = [self.current()] + self.side[self._cur]
+            if bucket is None or all(bucket.untyped_storage().data_ptr() != b.untyped_storage().data_ptr() for b in mine):
                 raise RuntimeError("gradients do not live in the bucket of the open batch (install bucket_provider "
                                    "before the backward pass and drop .grad before every backward)")
         if self._fresh:
@@ -185,13 +224,18 @@ class BucketBatch:
 class NcclBucketAllReducer(BucketBatch):
     """BucketBatch reduced with one NCCL all-reduce per batch (the comparison point of the peer-memory collective)."""
 
-    def __init__(self, numel: int, device, group=None, n_buckets: int = 2):
-        super().__init__(numel, device, n_buckets)
+    def __init__(self, numel: int, device, group=None, n_buckets: int = 2, n_lanes: int = 1):
+        super().__init__(numel, device, n_buckets, n_lanes)
         self.group = group
         self._pending = []
 
-    def launch(self, tensors: Iterable[torch.Tensor] | None = None):
+    def launch(self, tensors: Iterable[torch.Tensor] | None = None, streams=None):
         self._check(tensors)
+        if self.device.type == "cuda":
+            cur = torch.cuda.current_stream(self.device)
+            for s_ in (streams or []):
+                cur.wait_stream(s_)
+        self._merge_lanes()
         i = self._cur
         h = dist.all_reduce(self.buckets[i], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self._pending.append((h, i))
@@ -224,14 +268,14 @@ class PeerGradAllReducer(BucketBatch):
     order: every rank ends with bitwise the same sums, equal to ((g0 + g1) + g2) + ... .
     `n_buckets` buffers alternate so that the next batch can accumulate while this one is being reduced."""
 
-    def __init__(self, numel: int, device, group=None, n_buckets: int = 2, max_ctas: int = 32):
+    def __init__(self, numel: int, device, group=None, n_buckets: int = 2, max_ctas: int = 32, n_lanes: int = 1):
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         if self.world > 8:
             raise RuntimeError("PeerGradAllReducer supports up to 8 ranks (one NVSwitch domain)")
         align = 64 * self.world
-        super().__init__((int(numel) + align - 1) // align * align, device, n_buckets)
+        super().__init__((int(numel) + align - 1) // align * align, device, n_buckets, n_lanes)
         self.slice = self.numel // self.world
         self.max_ctas = int(max_ctas)
         self.stream = torch.cuda.Stream(device=self.device)
@@ -251,14 +295,15 @@ class PeerGradAllReducer(BucketBatch):
             self.peers.append(peers)
             self.peer_ptrs.append((C.c_void_p * self.world)(*[t.data_ptr() for t in peers]))
 
-    def launch(self, tensors: Iterable[torch.Tensor] | None = None):
+    def launch(self, tensors: Iterable[torch.Tensor] | None = None, streams=None):
+        """`streams`: the lanes' streams whose backward passes fed this batch (default: the current stream)."""
         from . import _lib
         self._check(tensors)
         i = self._cur
-        cur = torch.cuda.current_stream(self.device)
-        self.ready.record(cur)
+        for s_ in (streams or [torch.cuda.current_stream(self.device)]):
+            self.stream.wait_stream(s_)
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
-            self.stream.wait_event(self.ready)
+            self._merge_lanes()
             h = self.handles[i]
             h.barrier(channel=0)
             rc = _lib.load().pgs_peer_allreduce_slice(self.world, self.peer_ptrs[i], self.rank * self.slice, self.slice,
