@@ -325,7 +325,7 @@ class PeerGradAllReducer(BucketBatch):
 
 def sharded_step(render_loss: Callable[[int], torch.Tensor], params: Dict[str, torch.Tensor], n_views: int,
                  reducer=None, rank: int | None = None, world: int | None = None,
-                 order: Sequence[str] = ("means3D", "shs", "opacities", "scales", "rotations")):
+                 order: Sequence[str] = ("means3D", "shs", "opacities", "scales", "rotations"), streams=None):
     """One data-parallel step over ``n_views`` cameras (train.py:93-99,219-225 per rank).
 
     ``render_loss(view_index)`` must render that view from ``params`` and return a scalar loss.  Every rank
@@ -333,6 +333,9 @@ def sharded_step(render_loss: Callable[[int], torch.Tensor], params: Dict[str, t
     over ranks with ONE collective.  With a bucket reducer (`PeerGradAllReducer`, `NcclBucketAllReducer`, provider
     installed with `diff_surfel_rasterization.set_grad_bucket_provider`) the accumulation happens inside the
     backward kernel, in the buffer the collective reduces; otherwise autograd accumulates into ``.grad``.
+    ``streams`` (CUDA streams, at most ``reducer.n_lanes``): consecutive views run on alternating streams — the
+    parameters are fixed over a batch, so view k+1's preprocess + binning chain overlaps view k's render kernels; each
+    stream accumulates in its own lane of the bucket reducer.
     Returns (local_loss_sum, my_view_indices)."""
     if rank is None:
         rank = dist.get_rank() if dist.is_initialized() else 0
@@ -343,15 +346,33 @@ def sharded_step(render_loss: Callable[[int], torch.Tensor], params: Dict[str, t
     for p in params.values():
         p.grad = None
     mine = shard_views(n_views, rank, world)
-    reducer.begin_batch()
+    lanes = list(streams or [])
+    if lanes and not (bucketed and len(lanes) <= reducer.n_lanes):
+        raise RuntimeError("sharded_step(streams=...) needs a bucket reducer with at least as many lanes")
+    if lanes:
+        cur = torch.cuda.current_stream(lanes[0].device)
+        for s_ in lanes:
+            s_.wait_stream(cur)
+        reducer.begin_batch(streams=lanes)
+    else:
+        reducer.begin_batch()
     total = None
-    for v in mine:
+    for j, v in enumerate(mine):
         if bucketed:                      # the kernel accumulates in the bucket: autograd must adopt, not add
             for p in params.values():
                 p.grad = None
-        loss = render_loss(v)
-        loss.backward()
+            reducer.set_lane(j % len(lanes) if lanes else 0)
+        if lanes:
+            with torch.cuda.stream(lanes[j % len(lanes)]):
+                loss = render_loss(v)
+                loss.backward()
+        else:
+            loss = render_loss(v)
+            loss.backward()
         total = loss.detach() if total is None else total + loss.detach()
+    if lanes:
+        for s_ in lanes:                  # the caller's stream sees every lane's work (losses, gradients)
+            cur.wait_stream(s_)
     present = [k for k in order if params.get(k) is not None]
     if n_views < world and world > 1 and present:
         # Some rank has no view.  It still has to join the collective, and with the SAME layout as its peers: the
@@ -375,6 +396,21 @@ def sharded_step(render_loss: Callable[[int], torch.Tensor], params: Dict[str, t
         if p.grad is None:
             p.grad = torch.zeros_like(p)
         grads.append(p.grad)
-    reducer.launch(grads)
-    reducer.wait()
+    if bucketed and mine:
+        # with lanes the parameters' .grad views belong to the last view's lane: after the collective the reduced
+        # gradients live in the batch's bucket, so .grad is re-pointed at it (same carving as the backward pass's)
+        reducer.launch(None if lanes else grads)
+        reducer.wait()
+        if lanes:
+            from . import diff_surfel_rasterization as dsr
+            flat = reducer.current()
+            off = 0
+            for k in present:
+                p = params[k]
+                n = p.numel()
+                p.grad = flat[off:off + n].view(p.shape)
+                off += (n + 63) // 64 * 64
+    else:
+        reducer.launch(grads)
+        reducer.wait()
     return total, mine

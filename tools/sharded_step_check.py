@@ -31,13 +31,14 @@ def render_loss(params, v):
 
 
 ok = True
-for label, make in (("peer", lambda: PeerGradAllReducer(dsr.bucket_numel(P, 16), dev)),
-                    ("nccl-bucket", lambda: NcclBucketAllReducer(dsr.bucket_numel(P, 16), dev))):
+for label, make in (("peer", lambda: PeerGradAllReducer(dsr.bucket_numel(P, 16), dev, n_lanes=2)),
+                    ("nccl-bucket", lambda: NcclBucketAllReducer(dsr.bucket_numel(P, 16), dev, n_lanes=2))):
     red = make()
     dsr.set_grad_bucket_provider(red.bucket_provider)
-    for n_views in (len(cams), 1):
+    two = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    for n_views, lanes in ((len(cams), None), (1, None), (len(cams), two)):
         params = {k: scene[k].clone().requires_grad_(True) for k in names}
-        total, mine = sharded_step(lambda v: render_loss(params, v), params, n_views, red)
+        total, mine = sharded_step(lambda v: render_loss(params, v), params, n_views, red, streams=lanes)
         torch.cuda.synchronize()
         got = {k: params[k].grad.clone() for k in names}
         dsr.set_grad_bucket_provider(None)          # single-process reference: plain autograd accumulation
@@ -50,7 +51,7 @@ for label, make in (("peer", lambda: PeerGradAllReducer(dsr.bucket_numel(P, 16),
             if not e <= 2e-6:
                 ok = False
             if rank == 0:
-                print(f"{label} views={n_views} {k}: rel err vs single-process accumulation {e:.2e}")
+                print(f"{label} views={n_views} lanes={2 if lanes else 1} {k}: rel err vs single-process accumulation {e:.2e}")
     dsr.set_grad_bucket_provider(None)
 # ---- block-level model (surfels generated inside preprocess): SH rows accumulate in the kernel, the five block
 # gradients are added into the same bucket; one collective per batch
