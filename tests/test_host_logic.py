@@ -74,3 +74,38 @@ def test_bench_next_rows_never_raises_and_reports_errors_as_rows():
         assert all("error" in r and len(r["error"]) <= 160 for r in rows)
     rows = bench.next_rows(rows="adam", reps=1, timeout_s=0.01)
     assert len(rows) == 1 and "TimeoutExpired" in rows[0]["error"]
+
+
+def test_bucket_batch_lanes_accumulate_separately_and_merge():
+    """dist.BucketBatch: one buffer per batch slot, the first backward of a lane overwrites, the following ones
+    accumulate; lanes beyond the first own private buffers that are folded into the bucket before the collective."""
+    from partgs_b200.dist import BucketBatch
+    bb = BucketBatch(8, "cpu", n_buckets=2, n_lanes=2)
+    bb.begin_batch()
+    first = bb.current()
+    seq = []
+    for j in range(5):                       # views alternate lanes 0, 1, 0, 1, 0
+        bb.set_lane(j % 2)
+        buf, acc = bb.bucket_provider(8, "cpu")
+        seq.append(acc)
+        if acc:
+            buf += float(j + 1)              # what the backward kernel does in accumulate mode
+        else:
+            buf.fill_(float(j + 1))
+    assert seq == [False, False, True, True, True]
+    assert float(bb.current()[0]) == 1 + 3 + 5 and float(bb.side[bb._cur][0][0]) == 2 + 4
+    bb._merge_lanes()
+    assert torch.equal(bb.current(), torch.full((8,), 15.0))
+    bb._open = False
+    bb.begin_batch()                         # next batch: the other slot, fresh lanes
+    assert bb.current().data_ptr() != first.data_ptr() and bb._fresh
+    bb.set_lane(1)                           # a batch whose only view ran on lane 1
+    buf, acc = bb.bucket_provider(8, "cpu")
+    assert acc is False
+    buf.fill_(7.0)
+    bb._merge_lanes()
+    assert torch.equal(bb.current(), torch.full((8,), 7.0))
+    with pytest.raises(RuntimeError):
+        bb._open = False
+        bb.begin_batch()
+        bb._check(None)                      # nothing written in this batch
