@@ -373,7 +373,7 @@ def run(args):
         else:
             from partgs_b200.superquadric import blocks_bucket_numel
             numel = blocks_bucket_numel(P, 8, 16)
-        lanes_ = 1 if (args.no_overlap or args.no_graph or block_model is not None) else 2
+        lanes_ = 1 if (args.no_overlap or args.no_graph) else 2
         reducer = (PeerGradAllReducer(numel, dev, n_lanes=lanes_) if args.collective == "peer"
                    else NcclBucketAllReducer(numel, dev, n_lanes=lanes_))
         dsr.set_grad_bucket_provider(reducer.bucket_provider)
@@ -572,7 +572,7 @@ def run(args):
         one_step(i)
     drain()
     torch.cuda.synchronize()
-    if arm.name == "ours" and block_model is None and not args.no_lazy:
+    if arm.name == "ours" and not args.no_lazy:
         # every view has been rendered once: from here on the forward call does not wait for the frame's instance count
         # (partgs_b200.diff_surfel_rasterization.set_lazy_count); every backward verifies that its frame fitted
         from partgs_b200 import diff_surfel_rasterization as dsr_
@@ -639,7 +639,7 @@ def run(args):
     for a_ in attempts:
         a_["mode"] = "eager launches"
     stage_eager = min(attempts, key=lambda a_: a_["t_ms"])["stage"]
-    use_graph = arm.name == "ours" and block_model is None and not args.no_graph
+    use_graph = arm.name == "ours" and not args.no_graph
     if use_graph:
         # the same K steps replayed as CUDA graphs (no host launches inside the step); the per-stage timings above come
         # from the eager passes (the library's stage timers are host-recorded events)
@@ -880,9 +880,9 @@ def run(args):
                                   f"one all-reduce of the 232 B/surfel parameter gradients per batch of {accum} views per rank"),
                    "views_timed": views_timed,
                    "launch": ("CUDA-graph replay of forward + backward per view" + ("" if args.no_overlap else ", consecutive views on two alternating streams") + " (eager passes listed under attempts)"
-                              if (arm.name == "ours" and block_model is None and not args.no_graph) else "eager kernel launches"),
+                              if (arm.name == "ours" and not args.no_graph) else "eager kernel launches"),
                    "instance_count": ("lazy: the forward does not wait for it, every backward verifies it" if
-                                      (arm.name == "ours" and block_model is None and not args.no_lazy) else "waited for in the forward call"),
+                                      (arm.name == "ours" and not args.no_lazy) else "waited for in the forward call"),
                    "l2": "inputs (232 MB parameters + per-view state) exceed the 126 MB L2; views cycle every step",
                    "V_visible": V, "R_instances": int(R)},
         # h2d_bytes_per_step: per rank (a step of the job is one view on every rank: x n_gpus for the job's total)

@@ -164,6 +164,7 @@ int pgs_dsr_backward_blocks(int B, int Vt, int F, int K, const float* sq_r, cons
                             const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
                             float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer,
                             size_t binning_bytes, char* image_buffer, const float* dL_dpix, const float* dL_dothers,
+                            const float* dL_dvertices, /* [B,Vt,3] or NULL: upstream gradient of the returned vertices */
                             float* dL_dmean2D, void* scratch, float* dL_dcolor, float* dL_dsh, float* d_sq_r,
                             float* d_sq_s, float* d_sq_t, float* d_sq_eps, float* d_sq_occ, float* d_alpha,
                             float* d_scale_raw, int debug, void* stream);

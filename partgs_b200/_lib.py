@@ -69,7 +69,7 @@ SIGNATURES = {
                                                                         C.c_int, C.c_int, _f32p, _f32p, C.c_float,
                                                                         _f32p, _f32p, _f32p, C.c_float, C.c_float,
                                                                         _vp, _vp, _vp, C.c_size_t, _vp, _f32p, _f32p,
-                                                                        _f32p, _vp, _f32p, _f32p] + [_f32p] * 7 +
+                                                                        _f32p, _f32p, _vp, _f32p, _f32p] + [_f32p] * 7 +
                                 [C.c_int, _vp]),
     "pgs_surface_maps_forward": (C.c_int, [C.c_int, C.c_int] + [_f32p] * 5 + [C.c_float] + [_f32p] * 3 + [_vp]),
     "pgs_surface_maps_backward_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),

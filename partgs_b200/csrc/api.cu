@@ -846,7 +846,8 @@ int pgs_dsr_backward_blocks(int B, int Vt, int F, int K, const float* sq_r, cons
                             const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
                             float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer,
                             size_t binning_bytes, char* image_buffer, const float* dL_dpix, const float* dL_dothers,
-                            float* dL_dmean2D, void* scratch, float* dL_dcolor, float* dL_dsh, float* d_sq_r,
+                            const float* dL_dvertices, float* dL_dmean2D, void* scratch, float* dL_dcolor,
+                            float* dL_dsh, float* d_sq_r,
                             float* d_sq_s, float* d_sq_t, float* d_sq_eps, float* d_sq_occ, float* d_alpha,
                             float* d_scale_raw, int debug, void* stream) {
   SqArgs a;
@@ -874,7 +875,10 @@ int pgs_dsr_backward_blocks(int B, int Vt, int F, int K, const float* sq_r, cons
                             dL_dsh, d_scaling, d_rotation, debug, stream))
     return e;
   // per-surfel -> per-face -> per-vertex -> 13 parameters per block
-  cudaMemsetAsync(d_vertices, 0, (size_t)B * Vt * 3 * sizeof(float), s);
+  if (dL_dvertices)   // a loss on the returned mesh vertices: its gradient joins the face -> vertex sums
+    cudaMemcpyAsync(d_vertices, dL_dvertices, (size_t)B * Vt * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  else
+    cudaMemsetAsync(d_vertices, 0, (size_t)B * Vt * 3 * sizeof(float), s);
   cudaMemsetAsync(d_occ_acc, 0, (size_t)B * sizeof(float), s);
   {
     StageTimer t(PGS_STAGE_SQ_BWD, s);

@@ -235,6 +235,8 @@ class _RasterizeBlocks(torch.autograd.Function):
                     torch.empty((P, 1), **f32)]
         cam = [_lib.require_cuda_float(x, n) for x, n in ((rs.bg, "bg"), (rs.viewmatrix, "viewmatrix"),
                                                          (rs.projmatrix, "projmatrix"), (rs.campos, "campos"))]
+        from . import diff_surfel_rasterization as _dsr
+        ctx.set_materialize_grads(False)      # outputs a loss does not use arrive as None, not as zero images
         sc = _lib.AllocScope(dev)
         with torch.cuda.device(dev), sc:
             rc = lib.pgs_dsr_forward_blocks(
@@ -243,7 +245,8 @@ class _RasterizeBlocks(torch.autograd.Function):
                 float(scale_min), int(rs.sh_degree), int(M), cam[0].data_ptr(), W, H, shs_c.data_ptr(), None,
                 float(rs.scale_modifier), cam[1].data_ptr(), cam[2].data_ptr(), cam[3].data_ptr(), float(rs.tanfovx),
                 float(rs.tanfovy), vertices.data_ptr(), *[_lib.ptr(m) for m in mats], out_color.data_ptr(),
-                out_others.data_ptr(), radii.data_ptr(), int(bool(rs.debug)), _lib.current_stream(dev))
+                out_others.data_ptr(), radii.data_ptr(), int(bool(rs.debug)) | (2 if _dsr._lazy_count else 0),
+                _lib.current_stream(dev))
         if sc.error is not None:
             raise sc.error
         rendered = _lib.check(rc, "pgs_dsr_forward_blocks")
@@ -270,9 +273,14 @@ class _RasterizeBlocks(torch.autograd.Function):
         dev = sq_r.device
         P = B * F * K
         f32 = dict(dtype=torch.float32, device=dev)
-        if g_vertices is not None and bool((g_vertices != 0).any()):
-            raise RuntimeError("rasterize_blocks: gradients w.r.t. the returned vertices are not supported; use "
-                               "sq_to_surfels for losses on the mesh vertices")
+        from . import diff_surfel_rasterization as _dsr
+        if int(R) == _dsr.COUNT_PENDING and not torch.cuda.is_current_stream_capturing():
+            n, overflow = _dsr.resolve_count()     # lazy forward (set_lazy_count): the count arrived long ago
+            if overflow:
+                raise RuntimeError(f"lazy instance count: a frame needed {n} instances, more than it was queued for; its "
+                                   "outputs are invalid.  The remembered capacity has been raised — render again")
+        # a loss on the returned mesh vertices joins the face -> vertex gradient sums inside the library
+        g_vertices = None if g_vertices is None else _lib.require_cuda_float(g_vertices, "g_vertices")
         g_color = _lib.require_cuda_float(g_color if g_color is not None else torch.zeros((3, H, W), **f32), "g")
         g_others = _lib.require_cuda_float(g_others if g_others is not None else torch.zeros((7, H, W), **f32), "g")
         need = ctx.needs_input_grad
@@ -281,7 +289,6 @@ class _RasterizeBlocks(torch.autograd.Function):
         # data-parallel caller hands out its batch bucket there and reduces it with one collective.  In accumulate mode
         # (second and later views of a batch) the SH rows are added inside the backward kernel; the block gradients
         # (13 floats per block) are produced into temporaries and added here.
-        from . import diff_surfel_rasterization as _dsr
         (b_sh, b_r, b_s, b_t, b_e, b_o), accumulate = _dsr._carve_bucket(
             dev, [(P, M, 3), (B, 4), (B, 3), (B, 3), (B, 2), (B,)], with_flag=True)
         d_sh = b_sh
@@ -302,7 +309,8 @@ class _RasterizeBlocks(torch.autograd.Function):
                 scale_min, vertices.data_ptr(), int(rs.sh_degree), int(M), int(R), bg.data_ptr(), W, H,
                 shs_c.data_ptr(), None, float(rs.scale_modifier), view.data_ptr(), proj.data_ptr(), campos.data_ptr(),
                 float(rs.tanfovx), float(rs.tanfovy), radii.data_ptr(), _lib.ptr(geom), _lib.ptr(binning),
-                int(binning.numel()), _lib.ptr(img), g_color.data_ptr(), g_others.data_ptr(), d_m2d.data_ptr(),
+                int(binning.numel()), _lib.ptr(img), g_color.data_ptr(), g_others.data_ptr(), _lib.ptr(g_vertices),
+                d_m2d.data_ptr(),
                 scratch.data_ptr(), d_col.data_ptr(), d_sh.data_ptr(), d_r.data_ptr(), d_s.data_ptr(), d_t.data_ptr(),
                 d_e.data_ptr(), d_o.data_ptr(), _lib.ptr(d_alpha), _lib.ptr(d_scale),
                 int(bool(rs.debug)) | (2 if accumulate else 0), _lib.current_stream(dev))

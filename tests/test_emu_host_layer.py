@@ -372,3 +372,18 @@ def test_fused_block_rasteriser_equals_unfused_composition(emulated_host):
     for n in names:
         assert pu.rel_err(pb[n].grad, pa[n].grad) <= 1e-3, n
     assert pu.rel_err(shs_b.grad, shs_a.grad) <= 1e-3 and pu.rel_err(m2d_b.grad, m2d_a.grad) <= 1e-3
+    # a loss on the returned mesh vertices (alone: the images get no gradient, which arrives as None) flows to the
+    # block parameters exactly like through sq_to_surfels
+    gv = torch.randn(_verts.shape, generator=gen)
+    pc = {n: getattr(model, n).detach().clone().requires_grad_(True) for n in names}
+    verts_c = sq_to_surfels(pc["sq_r"], pc["sq_s"], pc["sq_t"], pc["sq_eps"], pc["sq_occ"], model.alpha, model._scale,
+                            model.sq_eta, model.sq_omega, model.faces)[0]
+    verts_c.backward(gv)
+    pd = {n: getattr(model, n).detach().clone().requires_grad_(True) for n in names}
+    out_d = rasterize_blocks(settings, pd["sq_r"], pd["sq_s"], pd["sq_t"], pd["sq_eps"], pd["sq_occ"], model.alpha,
+                             model._scale, shs0, model.sq_eta, model.sq_omega, model.faces)
+    assert torch.equal(out_d[3], verts_c.detach())
+    out_d[3].backward(gv)
+    for n in ("sq_r", "sq_s", "sq_t", "sq_eps"):
+        assert float(pc[n].grad.abs().max()) > 0 and pu.rel_err(pd[n].grad, pc[n].grad) <= 1e-5, n
+    assert float(pd["sq_occ"].grad.abs().max()) == 0.0

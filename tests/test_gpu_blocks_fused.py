@@ -84,3 +84,38 @@ def test_fused_blocks_without_materialisation():
                          model._scale, shs, model.sq_eta, model.sq_omega, model.faces)
     assert len(b) == 4 and len(a) == 8
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+
+
+def test_vertex_loss_flows_through_the_fused_op():
+    """A loss on the returned mesh vertices (pgs_dsr_backward_blocks' dL_dvertices) reaches the block parameters like
+    through sq_to_surfels, alone and on top of the image gradients."""
+    from partgs_b200.superquadric import rasterize_blocks, sq_to_surfels
+    model, shs0, cams, g = _scene(6, 4, 320, 240)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=DEV)
+    settings = pu.settings_from_cam(cams[0], bg)
+    names = ("sq_r", "sq_s", "sq_t", "sq_eps", "sq_occ")
+
+    def fused(with_images, gv):
+        p = {n: getattr(model, n).detach().clone().requires_grad_(True) for n in names}
+        color, _, allmap, verts = rasterize_blocks(settings, p["sq_r"], p["sq_s"], p["sq_t"], p["sq_eps"], p["sq_occ"],
+                                                   model.alpha, model._scale, shs0, model.sq_eta, model.sq_omega,
+                                                   model.faces)
+        outs, gs = ([color, allmap], [g["color"], g["allmap"]]) if with_images else ([], [])
+        if gv is not None:
+            outs, gs = outs + [verts], gs + [gv]
+        torch.autograd.backward(outs, gs)
+        return {n: p[n].grad for n in names}, verts.detach()
+
+    gv = torch.randn(6, model.sq_eta.shape[1], 3, device=DEV, generator=torch.Generator(DEV).manual_seed(3))
+    pc = {n: getattr(model, n).detach().clone().requires_grad_(True) for n in names}
+    verts_c = sq_to_surfels(pc["sq_r"], pc["sq_s"], pc["sq_t"], pc["sq_eps"], pc["sq_occ"], model.alpha, model._scale,
+                            model.sq_eta, model.sq_omega, model.faces)[0]
+    verts_c.backward(gv)
+    only_v, verts = fused(False, gv)
+    assert torch.equal(verts, verts_c.detach())
+    for n in names[:4]:
+        assert pu.rel_err(only_v[n], pc[n].grad) <= 1e-5, n
+    only_img, _ = fused(True, None)
+    both, _ = fused(True, gv)
+    for n in names[:4]:
+        assert pu.rel_err(both[n], only_img[n] + only_v[n]) <= 1e-4, n

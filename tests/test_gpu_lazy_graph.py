@@ -103,3 +103,63 @@ def test_cuda_graph_of_an_iteration_replays_other_views(lazy):
                      ("rotations", leaf["rotations"]), ("sh", leaf["shs"]), ("means2D", means2D)):
             pu.assert_grad_close(k, p.grad, e["grads"][k], rtol=1e-5, afloor=1e-6)
     assert _lib.load().pgs_launch_count() == l1 > l0      # replays issue no launches from the host
+
+
+def test_block_level_iteration_lazy_and_graphed(lazy):
+    """The block-level op (surfels generated inside preprocess, C5's path) with a lazy count and captured as a CUDA
+    graph gives the images and the block / SH gradients of the default waiting path, other views included."""
+    from partgs_b200 import synth
+    from partgs_b200.graphs import GraphedIteration
+    from partgs_b200.superquadric import BlockSurfelModel, rasterize_blocks
+    dsr = lazy
+    gen = torch.Generator().manual_seed(5)
+    model = BlockSurfelModel(8, 4, device=DEV, generator=gen)
+    P = 8 * model.per_gs_num
+    shs = torch.zeros(P, 16, 3, device=DEV)
+    shs[:, 0] = synth.RGB2SH(torch.rand(P, 3, generator=gen)).to(DEV)
+    W, H = 640, 480
+    cams = synth.make_cameras(3, W, H, seed=23, device=DEV)
+    g = synth.upstream_grads(W, H, 8, device=DEV)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=DEV)
+    names = ("sq_r", "sq_s", "sq_t", "sq_eps", "sq_occ")
+    leaf = {n: getattr(model, n).detach().clone().requires_grad_(True) for n in names}
+    leaf["shs"] = shs.clone().requires_grad_(True)
+    view, proj, campos = cams[0].viewmatrix.clone(), cams[0].projmatrix.clone(), cams[0].campos.clone()
+    st = pu.settings_from_cam(cams[0], bg)._replace(viewmatrix=view, projmatrix=proj, campos=campos)
+
+    def step():
+        for t in leaf.values():
+            t.grad = None
+        color, radii, allmap, _ = rasterize_blocks(st, leaf["sq_r"], leaf["sq_s"], leaf["sq_t"], leaf["sq_eps"],
+                                                   leaf["sq_occ"], model.alpha, model._scale, leaf["shs"], model.sq_eta,
+                                                   model.sq_omega, model.faces)
+        torch.autograd.backward([color, allmap], [g["color"], g["allmap"]])
+        return color.detach(), allmap.detach(), radii
+
+    def at(c):
+        view.copy_(c.viewmatrix); proj.copy_(c.projmatrix); campos.copy_(c.campos)
+
+    eager = []
+    for c in cams:
+        at(c)
+        color, allmap, radii = step()
+        eager.append((color.clone(), allmap.clone(), radii.clone(), {k: v.grad.clone() for k, v in leaf.items()}))
+    assert int((eager[0][2] > 0).sum()) > 1000
+
+    def check(out, e):
+        color, allmap, radii = out
+        assert torch.equal(radii, e[2])
+        pu.assert_equal_images("color", color, e[0])
+        pu.assert_equal_images("allmap", allmap, e[1])
+        for k, v in leaf.items():
+            pu.assert_grad_close(k, v.grad, e[3][k], rtol=1e-4, afloor=1e-5)     # float atomics order only
+
+    dsr.set_lazy_count(True)
+    for c, e in zip(cams, eager):
+        at(c)
+        check(step(), e)
+    dsr.set_lazy_count(False)
+    it = GraphedIteration(step, warmup=2)
+    for c, e in zip(cams, eager):
+        at(c)
+        check(it.replay(), e)
