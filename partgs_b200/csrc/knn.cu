@@ -83,7 +83,7 @@ struct KnnGrid {
 };
 
 #ifndef KNN_FINE_RINGS
-#define KNN_FINE_RINGS 2
+#define KNN_FINE_RINGS 3
 #endif
 
 __device__ __forceinline__ int3 cell_of(const KnnGrid& g, float x, float y, float z) {

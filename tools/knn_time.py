@@ -26,7 +26,7 @@ def timed(fn, x, n=5):
 
 
 gen = torch.Generator().manual_seed(0)
-for P in (100_000, 1_000_000, 3_000_000):
+for P in [int(a) for a in sys.argv[1:]] or (100_000, 1_000_000, 3_000_000):
     clouds = {"synth_scene": synth.make_point_scene(P, 42, device=dev)["means3D"],
               "blob": torch.randn(P, 3, generator=gen).to(dev), "uniform": torch.rand(P, 3, generator=gen).to(dev)}
     v = torch.randn(P, 3, generator=gen)
