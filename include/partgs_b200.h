@@ -317,7 +317,9 @@ int pgs_peer_allreduce_slice(int world, float* const* buckets, size_t offset_flo
 
 /* ---- simple-knn ------------------------------------------------------------------
  * Replaces distCUDA2 / SimpleKNN::knn (KNN/spatial.cu:15-25, KNN/simple_knn.cu:185-221):
- * mean squared distance of every point to its 3 nearest neighbours (exact).
+ * mean squared distance of every point to its 3 nearest neighbours (exact).  Two grid levels over the bounding
+ * box: a ring search with pruning in the fine one, a bottom-up octree walk (Morton-numbered coarse cells) for the
+ * queries the rings leave open.
  * points [P,3] float32 device, mean_dist2 [P] float32 device, temp >= pgs_knn_temp_bytes(P).
  * Synchronises the stream once (bounding-box read-back). */
 size_t pgs_knn_temp_bytes(int P);
