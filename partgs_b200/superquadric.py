@@ -336,7 +336,7 @@ def rasterize_blocks(raster_settings, sq_r, sq_s, sq_t, sq_eps, sq_occ, alpha, s
     (+ ``xyz, _scaling, _rotation, opacity`` when ``materialize``).  ``raster_settings`` is the
     ``GaussianRasterizationSettings`` of the base rasteriser; ``means2D`` ([P,3], optional) receives the
     screen-space densification gradient like in ``GaussianRasterizer``."""
-    if means2D is None:
-        means2D = torch.zeros((shs.shape[0], 3), dtype=torch.float32, device=shs.device)
+    if means2D is None:   # only its gradient slot matters (the op never reads it): no 12 B/surfel zero fill
+        means2D = torch.empty((shs.shape[0], 3), dtype=torch.float32, device=shs.device)
     return _RasterizeBlocks.apply(sq_r, sq_s, sq_t, sq_eps, sq_occ, alpha, scale_raw, shs, means2D, eta, omega, faces,
                                   ratio_block_scene, scale_block_min, raster_settings, materialize)

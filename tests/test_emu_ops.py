@@ -54,6 +54,49 @@ def test_emulated_dist2_matches_brute_force(emu, P):
     np.testing.assert_allclose(out, want, rtol=2e-5, atol=1e-12)
 
 
+def _knn_clouds():
+    g = np.random.default_rng(7)
+    P = 4000
+    sph = g.normal(size=(P, 3))
+    return {
+        # dense core + sparse fringe: the fine ring search closes the core, the octree walk takes the fringe
+        "blob": g.normal(size=(P, 3)),
+        # far sparser than the fine grid: (almost) every query ends in the octree
+        "uniform": g.random((P, 3)),
+        # two tight clusters and one far outlier: the outlier climbs to the root of the octree
+        "clusters+outlier": np.concatenate([g.normal(size=(P // 2, 3)) * 0.01, g.normal(size=(P // 2, 3)) * 0.01 + 5.0,
+                                            [[100.0, -50.0, 3.0]]]),
+        # far from the origin: the cell-boundary slack has to cover the ulps of the coordinates
+        "offset": g.normal(size=(P, 3)) * 0.5 + 1000.0,
+        "flat": np.concatenate([g.random((P, 2)), np.zeros((P, 1))], 1),           # a degenerate axis
+        "surface": sph / np.linalg.norm(sph, axis=1, keepdims=True),
+        "anisotropic": g.random((P, 3)) * np.array([4.0, 1.0, 0.25]),
+        "duplicates": np.tile(g.random((P // 4, 3)), (4, 1)),                      # every point four times
+    }
+
+
+@pytest.mark.parametrize("name", sorted(_knn_clouds()))
+def test_emulated_dist2_cloud_shapes(emu, name):
+    """Both search levels of distCUDA2 (knn.cu: pruned ring search in the fine grid, bottom-up octree walk for the
+    queries it leaves open) against an exact k-d tree in float64, on the cloud shapes that stress each of them."""
+    from scipy.spatial import cKDTree
+    pts = np.ascontiguousarray(_knn_clouds()[name], np.float32)
+    P = pts.shape[0]
+    out = np.full(P, np.nan, np.float32)
+    temp = np.zeros(emu.pgs_knn_temp_bytes(P) + 256, np.uint8)
+    assert emu.pgs_knn_dist2(P, _p(pts), _p(out), (temp.ctypes.data + 255) // 256 * 256, None) >= 0
+    p64 = pts.astype(np.float64)
+    d, _ = cKDTree(p64).query(p64, k=4)
+    want = (d[:, 1:] ** 2).sum(1) / 3
+    np.testing.assert_allclose(out, want, rtol=2e-5, atol=1e-12)
+    # invariant under a permutation of the points
+    perm = np.random.default_rng(1).permutation(P)
+    out_p = np.full(P, np.nan, np.float32)
+    assert emu.pgs_knn_dist2(P, _p(np.ascontiguousarray(pts[perm])), _p(out_p), (temp.ctypes.data + 255) // 256 * 256,
+                             None) >= 0
+    np.testing.assert_array_equal(out_p, out[perm])
+
+
 def test_emulated_surface_maps_match_the_oracle(emu):
     from oracle import post_oracle
     from partgs_b200.renderer import _camera_constants
