@@ -292,44 +292,46 @@ __global__ void __launch_bounds__(128) knn_search_tree_kernel(const uint32_t* __
                                                               int levels, const float4* __restrict__ sorted,
                                                               const uint32_t* __restrict__ incl,
                                                               float* __restrict__ out) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= *n_work) return;
-  const uint32_t i = work[t];
-  const float4 q = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], __int_as_float((int)i));
-  const uint32_t leaf = morton3(coarse_of(cell_of(gf, q.x, q.y, q.z)));
-  float best[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+  // the work list's length is only known on the device: a fixed grid strides over it
   uint32_t stack[KNN_TREE_STACK];
-  int sp = 0;
-  for (int k = levels - 1; k >= 0; k--) {      // siblings of the ancestor at level k; lower levels end up on top
-    const uint32_t a = leaf >> (3 * k);
-    for (int j = 7; j >= 1; j--) stack[sp++] = ((uint32_t)k << 24) | (a ^ (uint32_t)j);
-  }
-  stack[sp++] = leaf;                           // level 0
-  while (sp > 0) {
-    const uint32_t e = stack[--sp];
-    const int k = (int)(e >> 24);
-    const uint32_t m = e & 0xffffffu;
-    const float hk = gc.h * (float)(1 << k);
-    const float bx = gc.ox + (float)compact3(m) * hk, by = gc.oy + (float)compact3(m >> 1) * hk,
-                bz = gc.oz + (float)compact3(m >> 2) * hk;
-    const float dx = fmaxf(fmaxf(fmaxf(bx - q.x, q.x - (bx + hk)), 0.f) - gc.eps, 0.f);
-    const float dy = fmaxf(fmaxf(fmaxf(by - q.y, q.y - (by + hk)), 0.f) - gc.eps, 0.f);
-    const float dz = fmaxf(fmaxf(fmaxf(bz - q.z, q.z - (bz + hk)), 0.f) - gc.eps, 0.f);
-    if (dx * dx + dy * dy + dz * dz >= best[2]) continue;
-    const uint32_t lo = m << (3 * k), hi = ((m + 1u) << (3 * k)) - 1u;
-    const uint32_t s = lo == 0 ? 0u : incl[lo - 1], en = incl[hi];
-    if (s == en) continue;
-    // a leaf, a node with few points, or (cannot happen: <= 7 levels x 7 siblings + 7 per level descended) no room
-    if (k == 0 || en - s <= KNN_TREE_SCAN || sp + 8 > KNN_TREE_STACK) {
-      scan_points(sorted, s, en, q, best);
-      continue;
+  const uint32_t n = *n_work;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const uint32_t i = work[t];
+    const float4 q = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], __int_as_float((int)i));
+    const uint32_t leaf = morton3(coarse_of(cell_of(gf, q.x, q.y, q.z)));
+    float best[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+    int sp = 0;
+    for (int k = levels - 1; k >= 0; k--) {      // siblings of the ancestor at level k; lower levels end up on top
+      const uint32_t a = leaf >> (3 * k);
+      for (int j = 7; j >= 1; j--) stack[sp++] = ((uint32_t)k << 24) | (a ^ (uint32_t)j);
     }
-    // eight children, the octant nearest to the query on top
-    const float half = 0.5f * hk;
-    const uint32_t qo = (q.x >= bx + half ? 1u : 0u) | (q.y >= by + half ? 2u : 0u) | (q.z >= bz + half ? 4u : 0u);
-    for (int j = 7; j >= 0; j--) stack[sp++] = ((uint32_t)(k - 1) << 24) | ((m << 3) | ((uint32_t)j ^ qo));
+    stack[sp++] = leaf;                           // level 0
+    while (sp > 0) {
+      const uint32_t e = stack[--sp];
+      const int k = (int)(e >> 24);
+      const uint32_t m = e & 0xffffffu;
+      const float hk = gc.h * (float)(1 << k);
+      const float bx = gc.ox + (float)compact3(m) * hk, by = gc.oy + (float)compact3(m >> 1) * hk,
+                  bz = gc.oz + (float)compact3(m >> 2) * hk;
+      const float dx = fmaxf(fmaxf(fmaxf(bx - q.x, q.x - (bx + hk)), 0.f) - gc.eps, 0.f);
+      const float dy = fmaxf(fmaxf(fmaxf(by - q.y, q.y - (by + hk)), 0.f) - gc.eps, 0.f);
+      const float dz = fmaxf(fmaxf(fmaxf(bz - q.z, q.z - (bz + hk)), 0.f) - gc.eps, 0.f);
+      if (dx * dx + dy * dy + dz * dz >= best[2]) continue;
+      const uint32_t lo = m << (3 * k), hi = ((m + 1u) << (3 * k)) - 1u;
+      const uint32_t s = lo == 0 ? 0u : incl[lo - 1], en = incl[hi];
+      if (s == en) continue;
+      // a leaf, a node with few points, or (cannot happen: <= 7 levels x 7 siblings + 7 per level descended) no room
+      if (k == 0 || en - s <= KNN_TREE_SCAN || sp + 8 > KNN_TREE_STACK) {
+        scan_points(sorted, s, en, q, best);
+        continue;
+      }
+      // eight children, the octant nearest to the query on top
+      const float half = 0.5f * hk;
+      const uint32_t qo = (q.x >= bx + half ? 1u : 0u) | (q.y >= by + half ? 2u : 0u) | (q.z >= bz + half ? 4u : 0u);
+      for (int j = 7; j >= 0; j--) stack[sp++] = ((uint32_t)(k - 1) << 24) | ((m << 3) | ((uint32_t)j ^ qo));
+    }
+    out[i] = (best[0] + best[1] + best[2]) / 3.0f;
   }
-  out[i] = (best[0] + best[1] + best[2]) / 3.0f;
 }
 
 static int knn_coarse_res(int P) {
@@ -421,7 +423,8 @@ int launch_knn_dist2(int P, const float* points, float* out, void* temp, cudaStr
   count_launch();
   knn_search_fine_kernel<<<(P + 127) / 128, 128, 0, s>>>(P, gf, sorted_f, incl_f, out, work, n_work);
   count_launch();
-  knn_search_tree_kernel<<<(P + 127) / 128, 128, 0, s>>>(n_work, work, points, gf, gc, levels, sorted_c, incl_c, out);
+  knn_search_tree_kernel<<<min((P + 127) / 128, 148 * 16), 128, 0, s>>>(n_work, work, points, gf, gc, levels, sorted_c,
+                                                                         incl_c, out);
   count_launch();
   return 0;
 }
